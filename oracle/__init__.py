@@ -1,0 +1,22 @@
+"""Oracle: fp32 pure-PyTorch restatement of the EdgeStyle per-step denoise hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``edgestyle_b200/`` may import this package; only
+``tests/``, ``__graft_entry__.smoke()`` and the CPU-baseline / ``--impl reference`` legs of
+``bench.py`` do, and there only as the checker / the reported CPU baseline.
+
+PARITY UNPINNED: the reference ships no unit tests, golden vectors or
+fixtures for this path, and its arithmetic lives in the third-party ``diffusers==0.26.3``
+(pinned at /root/reference/requirements-jetson.txt:25), which is neither vendored under
+/root/reference nor installed here.  What IS pinned:
+
+* the pure-torch slices of the reference that execute without diffusers (``ControlNetBlock``,
+  ``interleave_tensors``; model/edgestyle_multicontrolnet.py:23-63,479-514) were run in the
+  build container by ``tests/golden/make_golden.py`` and their outputs are committed under
+  ``tests/golden/`` -- ``oracle.merge`` is checked against them bit-for-bit-tolerance;
+* the published parameter counts (UNet 859 520 964, ControlNet 361 279 120) and the residual
+  shape table (model/edgestyle_onnx_pipeline.py:244-258);
+* algebraic identities (LoRA fuse == unfused, zero zero-convs => cond-independent UNet, DDIM
+  schedule constants).
+
+Everything else follows SURVEY.md Appendix A (diffusers 0.26.3 semantics for SD1.5).
+"""

@@ -1,0 +1,140 @@
+"""Oracle pinned against outputs of the reference's own (pure-torch) merge code and self-checks
+(SURVEY.md 8(c)): golden replay, parameter counts, shape table, algebraic identities."""
+import os
+
+import pytest
+import torch
+
+from oracle import merge as om
+from oracle.controllora import ControlLoRAModel
+from oracle.schedulers import DDIMScheduler, UniPCMultistepScheduler, alphas_cumprod
+from oracle.sd15 import ControlNetModel, LoRALinearLayer, SD15Config, UNet2DConditionModel, count_params
+from oracle.step import build_models, cfg_combine, denoise, fused_step, synthetic_inputs
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "merge_block_golden.pt")
+TINY = SD15Config(block_out_channels=(32, 64, 64, 64), cross_attention_dim=32)
+
+
+def test_merge_block_matches_reference_golden():
+    cases = torch.load(GOLD)
+    assert len(cases) == 3
+    for case in cases:
+        c, h, w, b = case["shape"]
+        blk = om.ControlNetBlock(c, (h, w), 6)
+        blk.load_state_dict(case["state_dict"])
+        inter = om.interleave_tensors(case["residuals"])
+        assert torch.equal(inter, case["interleaved"])
+        with torch.no_grad():
+            out = blk(inter)
+            closed = om.closed_form_block(blk, case["residuals"])
+        assert torch.allclose(out, case["out"], rtol=0, atol=1e-6)
+        assert torch.allclose(closed, case["out"], rtol=1e-5, atol=2e-6)
+
+
+def test_parameter_counts_match_published():
+    with torch.device("meta"):
+        unet = UNet2DConditionModel()
+        cn = ControlNetModel()
+        lora = ControlLoRAModel(SD15Config(), lora_linear_rank=32)
+        multi = om.EdgeStyleMultiControlNetModel([lora] * 6, SD15Config(), (64, 64))
+    assert count_params(unet) == 859_520_964
+    assert count_params(cn) == 361_279_120
+    assert lora.lora_param_count() == 6_354_944
+    assert sum(isinstance(m, LoRALinearLayer) for m in lora.modules()) == 82
+    assert sum(p.numel() for n, p in multi.named_parameters() if n.startswith("multi_")) == 53_902_720
+
+
+def test_residual_shape_table():
+    # /root/reference/model/edgestyle_onnx_pipeline.py:244-258
+    want = [(320, 64, 64)] * 3 + [(320, 32, 32)] + [(640, 32, 32)] * 2 + [(640, 16, 16)] + [(1280, 16, 16)] * 2 \
+        + [(1280, 8, 8)] * 3 + [(1280, 8, 8)]
+    assert om.residual_shapes(SD15Config(), 64, 64) == want
+
+
+def test_lora_fuse_equals_unfused_and_state_dict_filter():
+    m = build_models(TINY, (8, 8), rank=4)
+    inp = synthetic_inputs(TINY, 1, 8, 8)
+    x = torch.cat([inp.latents] * 2)
+    t = torch.tensor(501)
+    d0, m0 = m.lora_agnostic(x, t, inp.prompt_embeds, inp.conds[0], 1.0)
+    keys = m.lora_agnostic.state_dict().keys()
+    assert all(k.split(".")[0] not in ControlLoRAModel._skip_layers or ".lora_layer." in k for k in keys)
+    assert any(".lora_layer.down.weight" in k for k in keys)
+    # tied: same storage as the UNet
+    assert m.lora_agnostic.down_blocks[0].resnets[0].conv1.weight is m.unet.down_blocks[0].resnets[0].conv1.weight
+    m.lora_agnostic.fuse_lora()
+    d1, m1 = m.lora_agnostic(x, t, inp.prompt_embeds, inp.conds[0], 1.0)
+    for a, b in zip(d0 + [m0], d1 + [m1]):
+        assert torch.allclose(a, b, rtol=1e-3, atol=1e-4)
+
+
+def test_zero_zero_convs_make_unet_cond_independent():
+    m = build_models(TINY, (8, 8), rank=4)
+    for net in (m.lora_agnostic, m.lora_clothes, m.openpose):
+        for p in list(net.controlnet_down_blocks.parameters()) + list(net.controlnet_mid_block.parameters()):
+            p.zero_()
+    inp = synthetic_inputs(TINY, 1, 8, 8)
+    x = torch.cat([inp.latents] * 2)
+    t = torch.tensor(951)
+    e0 = fused_step(m, x, t, inp.prompt_embeds, inp.conditioning_scale, inp.conds)
+    e1 = fused_step(m, x, t, inp.prompt_embeds, inp.conditioning_scale, [c * 3 + 1 for c in inp.conds])
+    assert torch.equal(e0, e1)
+
+
+def test_ddim_schedule_constants():
+    s = DDIMScheduler()
+    ts = s.set_timesteps(20)
+    assert ts.tolist() == list(range(951, 0, -50))
+    ac = alphas_cumprod()
+    assert abs(ac[0].item() - 0.99915) < 1e-6
+    assert abs(ac[951].item() - 0.0081550) < 1e-6
+    # DDIM with eps == true noise recovers x0 direction: one step from t to t' keeps x0 fixed
+    x0 = torch.randn(1, 4, 8, 8)
+    eps = torch.randn(1, 4, 8, 8)
+    a_t, a_p = s.coefficients(951)
+    x_t = a_t.sqrt() * x0 + (1 - a_t).sqrt() * eps
+    x_p = s.step(eps, 951, x_t)
+    assert torch.allclose(x_p, a_p.sqrt() * x0 + (1 - a_p).sqrt() * eps, atol=1e-4)
+
+
+def test_unipc_consistency():
+    # with the exact eps of a fixed x0, any consistent solver must land on the analytic trajectory
+    s = UniPCMultistepScheduler()
+    ts = s.set_timesteps(10)
+    assert len(ts) == 10 and ts[0] > ts[-1]
+    x0 = torch.randn(1, 4, 4, 4)
+    noise = torch.randn(1, 4, 4, 4)
+    a0, s0 = s._alpha_sigma(s.sigmas[0])
+    x = a0 * x0 + s0 * noise
+    for i, t in enumerate(ts):
+        a, sg = s._alpha_sigma(s.sigmas[i])
+        eps = (x - a * x0) / sg
+        x = s.step(eps, t, x)
+    a, sg = s._alpha_sigma(s.sigmas[-1])
+    assert torch.allclose(x, a * x0 + sg * noise, atol=1e-3)
+
+
+def test_fp64_vs_fp32_oracle_and_cfg():
+    m = build_models(TINY, (8, 8), rank=4)
+    inp = synthetic_inputs(TINY, 1, 8, 8)
+    x = torch.cat([inp.latents] * 2)
+    t = torch.tensor(951)
+    e32 = fused_step(m, x, t, inp.prompt_embeds, inp.conditioning_scale, inp.conds)
+    m.unet.double()
+    m.controlnet.double()
+    e64 = fused_step(m, x.double(), t, inp.prompt_embeds.double(), inp.conditioning_scale,
+                     [c.double() for c in inp.conds])
+    assert (e32.double() - e64).abs().max() < 1e-4
+    g = cfg_combine(e32, 4.5)
+    u, c = e32.chunk(2)
+    assert torch.allclose(g, u + 4.5 * (c - u))
+    gv = cfg_combine(e32, torch.tensor([3.0]))
+    assert torch.allclose(gv, u + 3.0 * (c - u))
+
+
+def test_denoise_teacher_forced_equals_free_running():
+    m = build_models(TINY, (8, 8), rank=4)
+    inp = synthetic_inputs(TINY, 1, 8, 8)
+    lat, trace = denoise(m, inp, 3, 4.5, return_eps=True)
+    lat2 = denoise(m, inp, 3, 4.5, override_latents=[tr[0] for tr in trace])
+    assert torch.equal(lat, lat2)
