@@ -1,0 +1,39 @@
+// Host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/edgestyle_b200.h"
+
+namespace es {
+
+void set_error(const char* fmt, ...);
+
+#define ES_CHECK(cond, ...)        \
+  do {                             \
+    if (!(cond)) {                 \
+      ::es::set_error(__VA_ARGS__); \
+      return -1;                   \
+    }                              \
+  } while (0)
+
+#define ES_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ::es::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return -2;                                                                        \
+    }                                                                                   \
+  } while (0)
+
+// cuTensorMapEncodeTiled resolved through the runtime (no link-time dependency on libcuda).
+// dims/strides innermost first; strides in BYTES for dims 1..rank-1. 16-bit elements, SWIZZLE_128B.
+int encode_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box);
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace es

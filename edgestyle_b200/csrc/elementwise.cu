@@ -1,0 +1,313 @@
+// Small bandwidth / latency kernels around the tensor-core path: layout conversion at the NCHW
+// boundary, im2col for the stride-2 and 4-channel convs, nearest upsample, tiny-M linears (time
+// embedding), timestep sinusoid, CFG combine + DDIM update.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace es {
+
+// ---------------------------------------------------------------- NCHW fp32 <-> NHWC 16-bit
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int c, int hw, long long ldd) {
+  // grid (ceil(hw/32), ceil(ldd/32), n); block (32, 8): smem transpose tile 32 px x 32 ch
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int ch = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (ch < c && p < hw) ? src[(static_cast<long long>(n) * c + ch) * hw + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int p = p0 + i, ch = c0 + threadIdx.x;
+    if (p < hw && ch < ldd) dst[(static_cast<long long>(n) * hw + p) * ldd + ch] = Cvt<T>::from_f(tile[threadIdx.x][i]);
+  }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, long long lds, float* __restrict__ dst, int c, int hw) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int p = p0 + i, ch = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < hw && ch < c) ? Cvt<T>::to_f(src[(static_cast<long long>(n) * hw + p) * lds + ch]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int ch = c0 + i, p = p0 + threadIdx.x;
+    if (ch < c && p < hw) dst[(static_cast<long long>(n) * c + ch) * hw + p] = tile[threadIdx.x][i];
+  }
+}
+
+// ---------------------------------------------------------------- im2col 3x3 pad 1 stride s
+// out[(n, yo, xo)][tap*c + ch]; one thread per (row, tap, 8-channel vector) when c % 8 == 0, scalar otherwise.
+template <typename T>
+__global__ void im2col3x3_kernel(const T* __restrict__ src, long long lds, T* __restrict__ dst, long long ldo, int n,
+                                 int h, int w, int c, int stride, int ho, int wo) {
+  const long long rows = static_cast<long long>(n) * ho * wo;
+  if ((c & 7) == 0) {
+    const int vpt = c >> 3;
+    const long long total = rows * 9 * vpt;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const int v = static_cast<int>(i % vpt);
+      const int tap = static_cast<int>((i / vpt) % 9);
+      const long long row = i / (9 * vpt);
+      const int xo = static_cast<int>(row % wo), yo = static_cast<int>((row / wo) % ho);
+      const int img = static_cast<int>(row / (static_cast<long long>(wo) * ho));
+      const int y = yo * stride + tap / 3 - 1, x = xo * stride + tap % 3 - 1;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (y >= 0 && y < h && x >= 0 && x < w)
+        val = *reinterpret_cast<const uint4*>(src + ((static_cast<long long>(img) * h + y) * w + x) * lds + v * 8);
+      *reinterpret_cast<uint4*>(dst + row * ldo + tap * c + v * 8) = val;
+    }
+  } else {
+    const long long total = rows * ldo;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const int col = static_cast<int>(i % ldo);
+      const long long row = i / ldo;
+      T val = Cvt<T>::from_f(0.f);
+      if (col < 9 * c) {
+        const int tap = col / c, ch = col % c;
+        const int xo = static_cast<int>(row % wo), yo = static_cast<int>((row / wo) % ho);
+        const int img = static_cast<int>(row / (static_cast<long long>(wo) * ho));
+        const int y = yo * stride + tap / 3 - 1, x = xo * stride + tap % 3 - 1;
+        if (y >= 0 && y < h && x >= 0 && x < w) val = src[((static_cast<long long>(img) * h + y) * w + x) * lds + ch];
+      }
+      dst[i] = val;
+    }
+  }
+}
+
+template <typename T>
+__global__ void upsample2x_kernel(const T* __restrict__ src, long long lds, T* __restrict__ dst, long long ldd, int n,
+                                  int h, int w, int c) {
+  const int vpp = c >> 3;
+  const long long total = static_cast<long long>(n) * (2 * h) * (2 * w) * vpp;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % vpp);
+    const long long pix = i / vpp;
+    const int xo = static_cast<int>(pix % (2 * w)), yo = static_cast<int>((pix / (2 * w)) % (2 * h));
+    const int img = static_cast<int>(pix / (4ll * w * h));
+    const uint4 val =
+        *reinterpret_cast<const uint4*>(src + ((static_cast<long long>(img) * h + yo / 2) * w + xo / 2) * lds + v * 8);
+    *reinterpret_cast<uint4*>(dst + pix * ldd + v * 8) = val;
+  }
+}
+
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, long long lda, const T* __restrict__ b, long long ldb,
+                           T* __restrict__ out, long long ldo, long long rows, int c) {
+  const int vpp = c >> 3;
+  const long long total = rows * vpp;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % vpp);
+    const long long r = i / vpp;
+    const uint4 ua = *reinterpret_cast<const uint4*>(a + r * lda + v * 8);
+    const uint4 ub = *reinterpret_cast<const uint4*>(b + r * ldb + v * 8);
+    const uint32_t aa[4] = {ua.x, ua.y, ua.z, ua.w}, bb[4] = {ub.x, ub.y, ub.z, ub.w};
+    uint32_t oo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fa = Cvt<T>::unpack2(aa[j]), fb = Cvt<T>::unpack2(bb[j]);
+      oo[j] = Cvt<T>::pack2(fa.x + fb.x, fa.y + fb.y);
+    }
+    *reinterpret_cast<uint4*>(out + r * ldo + v * 8) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+  }
+}
+
+// ---------------------------------------------------------------- timestep sinusoid
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int n, int dim, float* __restrict__ out) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * half) return;
+  const int r = i / half, k = i % half;
+  const float freq = expf(-logf(10000.0f) * static_cast<float>(k) / static_cast<float>(half));
+  const float a = t[r] * freq;
+  out[r * dim + k] = cosf(a);          // flip_sin_to_cos: [cos | sin]
+  out[r * dim + half + k] = sinf(a);
+}
+
+// ---------------------------------------------------------------- tiny-M linear: one warp per output column
+template <typename T, int RC>
+__global__ void small_linear_kernel(const float* __restrict__ x, int ldx, const T* __restrict__ w,
+                                    const float* __restrict__ bias, float* __restrict__ y, int ldy, int rows, int n,
+                                    int k, int silu_in, int silu_out, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (col >= n) return;
+  const T* wr = w + static_cast<long long>(col) * k;
+  for (int r0 = 0; r0 < rows; r0 += RC) {
+    float acc[RC];
+#pragma unroll
+    for (int r = 0; r < RC; ++r) acc[r] = 0.f;
+    for (int kk = lane * 8; kk < k; kk += 256) {
+      const uint4 u = *reinterpret_cast<const uint4*>(wr + kk);
+      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+      float wf[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = Cvt<T>::unpack2(uu[j]);
+        wf[2 * j] = f.x;
+        wf[2 * j + 1] = f.y;
+      }
+#pragma unroll
+      for (int r = 0; r < RC; ++r) {
+        if (r0 + r < rows) {
+          const float* xr = x + static_cast<long long>(r0 + r) * ldx + kk;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float xv = xr[j];
+            if (silu_in) xv = silu_f(xv);
+            acc[r] += xv * wf[j];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RC; ++r) {
+      float a = acc[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0 && r0 + r < rows) {
+        if (bias) a += bias[col];
+        if (silu_out) a = silu_f(a);
+        float* yp = y + static_cast<long long>(r0 + r) * ldy + col;
+        *yp = accumulate ? (*yp + a) : a;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- CFG + DDIM
+__global__ void cfg_ddim_kernel(const float* __restrict__ eps, float* __restrict__ lat,
+                                const float* __restrict__ guidance, const float* __restrict__ coef,
+                                float* __restrict__ eps_out, int imgs, int chw) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long long>(imgs) * chw) return;
+  const int img = static_cast<int>(i / chw);
+  const float eu = eps[i];
+  const float ec = eps[i + static_cast<long long>(imgs) * chw];
+  const float e = eu + guidance[img] * (ec - eu);
+  if (eps_out) eps_out[i] = e;
+  const float sa = coef[0], s1a = coef[1], sp = coef[2], s1p = coef[3];
+  const float x = lat[i];
+  const float x0 = (x - s1a * e) / sa;
+  lat[i] = sp * x0 + s1p * e;
+}
+
+static inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148ll * 16;
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace es
+
+using namespace es;
+
+extern "C" int es_nchw_to_nhwc(int dtype, const float* src, void* dst, int n, int c, int hw, long long ldd,
+                               void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(ceil_div(hw, 32), ceil_div(static_cast<int>(ldd), 32), n), block(32, 8);
+  if (dtype == ES_DTYPE_BF16)
+    nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), c, hw, ldd);
+  else
+    nchw_to_nhwc_kernel<__half><<<grid, block, 0, s>>>(src, reinterpret_cast<__half*>(dst), c, hw, ldd);
+  ES_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int es_nhwc_to_nchw(int dtype, const void* src, long long lds, float* dst, int n, int c, int hw,
+                               void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), n), block(32, 8);
+  if (dtype == ES_DTYPE_BF16)
+    nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), lds, dst, c, hw);
+  else
+    nhwc_to_nchw_kernel<__half><<<grid, block, 0, s>>>(reinterpret_cast<const __half*>(src), lds, dst, c, hw);
+  ES_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int es_im2col3x3(int dtype, const void* src, long long lds, void* dst, long long ldo, int n, int h, int w,
+                            int c, int stride, void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  ES_CHECK(stride == 1 || stride == 2, "es_im2col3x3: stride must be 1 or 2");
+  ES_CHECK(ldo >= 9ll * c, "es_im2col3x3: ldo too small");
+  if (c % 8 == 0) ES_CHECK(lds % 8 == 0 && ldo == 9ll * c, "es_im2col3x3: vector path needs lds%%8==0 and ldo==9c");
+  const int ho = (h + 2 - 3) / stride + 1, wo = (w + 2 - 3) / stride + 1;
+  const long long total = static_cast<long long>(n) * ho * wo * ((c % 8 == 0) ? 9 * (c / 8) : ldo);
+  const int g = grid_for(total, 256);
+  if (dtype == ES_DTYPE_BF16)
+    im2col3x3_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), lds,
+                                                      reinterpret_cast<__nv_bfloat16*>(dst), ldo, n, h, w, c, stride, ho, wo);
+  else
+    im2col3x3_kernel<__half><<<g, 256, 0, s>>>(reinterpret_cast<const __half*>(src), lds, reinterpret_cast<__half*>(dst),
+                                               ldo, n, h, w, c, stride, ho, wo);
+  ES_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int es_upsample2x(int dtype, const void* src, long long lds, void* dst, long long ldd, int n, int h, int w,
+                             int c, void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  ES_CHECK(c % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0, "es_upsample2x: c and pitches must be multiples of 8");
+  const long long total = static_cast<long long>(n) * 4 * h * w * (c / 8);
+  const int g = grid_for(total, 256);
+  if (dtype == ES_DTYPE_BF16)
+    upsample2x_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), lds,
+                                                       reinterpret_cast<__nv_bfloat16*>(dst), ldd, n, h, w, c);
+  else
+    upsample2x_kernel<__half><<<g, 256, 0, s>>>(reinterpret_cast<const __half*>(src), lds, reinterpret_cast<__half*>(dst),
+                                                ldd, n, h, w, c);
+  ES_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int es_add(int dtype, const void* a, long long lda, const void* b, long long ldb, void* out, long long ldo,
+                      int rows, int c, void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  ES_CHECK(c % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 8 == 0, "es_add: c and pitches must be multiples of 8");
+  const long long total = static_cast<long long>(rows) * (c / 8);
+  const int g = grid_for(total, 256);
+  if (dtype == ES_DTYPE_BF16)
+    add_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(a), lda,
+                                                reinterpret_cast<const __nv_bfloat16*>(b), ldb,
+                                                reinterpret_cast<__nv_bfloat16*>(out), ldo, rows, c);
+  else
+    add_kernel<__half><<<g, 256, 0, s>>>(reinterpret_cast<const __half*>(a), lda, reinterpret_cast<const __half*>(b), ldb,
+                                         reinterpret_cast<__half*>(out), ldo, rows, c);
+  ES_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int es_timestep_embedding(const float* t, int n, int dim, float* out, void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  ES_CHECK(dim % 2 == 0, "es_timestep_embedding: dim must be even");
+  const int total = n * dim / 2;
+  timestep_embedding_kernel<<<ceil_div(total, 128), 128, 0, s>>>(t, n, dim, out);
+  ES_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int es_small_linear(int dtype, const float* x, int ldx, const void* w, const float* bias, float* y, int ldy,
+                               int rows, int n, int k, int silu_in, int silu_out, int accumulate, void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  ES_CHECK(k % 8 == 0 && ldx % 4 == 0, "es_small_linear: k must be a multiple of 8");
+  const int warps = 4;
+  dim3 grid(ceil_div(n, warps)), block(warps * 32);
+  if (dtype == ES_DTYPE_BF16)
+    small_linear_kernel<__nv_bfloat16, 8><<<grid, block, 0, s>>>(x, ldx, reinterpret_cast<const __nv_bfloat16*>(w), bias,
+                                                                 y, ldy, rows, n, k, silu_in, silu_out, accumulate);
+  else
+    small_linear_kernel<__half, 8><<<grid, block, 0, s>>>(x, ldx, reinterpret_cast<const __half*>(w), bias, y, ldy, rows,
+                                                          n, k, silu_in, silu_out, accumulate);
+  ES_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int es_cfg_ddim(const float* eps, float* latents, const float* guidance, const float* coef, float* eps_out,
+                           int imgs, int chw, void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = static_cast<long long>(imgs) * chw;
+  cfg_ddim_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(eps, latents, guidance, coef, eps_out, imgs, chw);
+  ES_CUDA(cudaGetLastError());
+  return 0;
+}

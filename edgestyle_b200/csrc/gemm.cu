@@ -1,0 +1,520 @@
+// es_gemm: warp-specialised tcgen05/TMEM implicit-GEMM (conv3x3 s1 / conv1x1 / Linear) for sm_100a.
+//
+//   warp 0      : TMA producer (one elected lane) -- A tile via a 4-D tensor map over the NHWC
+//                 activation (box = 64 channels x bw x bh x bn pixels; the 9 taps of a 3x3 are
+//                 shifted boxes, out-of-bounds rows are zero-filled by TMA == the conv padding),
+//                 B tile via a 3-D map over [n][tap][c].
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (128 x BLOCK_N x 16 per MMA).
+//   warps 2..5  : epilogue -- tcgen05.ld the fp32 accumulator (one row per thread), fuse
+//                 bias / per-image vector / GEGLU / alpha / residual, store 16 B vectors.
+//   smem ring   : `stages` x (A 16 KB + B BLOCK_N*128 B), SWIZZLE_128B, full/empty mbarriers.
+//
+// Replaces the cuDNN/cuBLAS dispatches listed at include/edgestyle_b200.h (es_gemm).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace es {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kGemmThreads = 192;
+
+struct GemmKParams {
+  int W, H, NI;
+  int bw, bh, bn;
+  int tiles_x, tiles_y;
+  int N;
+  int taps;
+  int kblocks1, kblocks2;
+  int nseg;
+  int seg_row_start[ES_MAX_SEG + 1];
+  int seg_tile_start[ES_MAX_SEG + 1];
+  int seg_b_noff[ES_MAX_SEG];
+  int seg_b2_noff[ES_MAX_SEG];
+  int flat;
+  const float* bias;
+  const float* rowvec;
+  int rows_per_img;
+  int rowvec_ld;
+  const void* residual;
+  long long ldr;
+  int act;
+  float alpha;
+  void* out;
+  long long ldc;
+  int out_fp32;
+  int stages;
+};
+
+template <typename T, int BLOCK_N>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+            const GemmKParams p) {
+  constexpr int kABytes = kBlockM * kBlockK * 2;
+  constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+  constexpr int kMaxStages = 8;
+
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for SWIZZLE_128B
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.stages;
+
+  // ---- tile decode -------------------------------------------------------------------------
+  const int tile_m = blockIdx.x;
+  const int n0 = blockIdx.y * BLOCK_N;
+  int x0, y0, i0, x_end, b_noff = 0, b2_noff = -1;
+  if (p.flat) {
+    int g = 0;
+#pragma unroll
+    for (int s = 1; s < ES_MAX_SEG; ++s)
+      if (s < p.nseg && tile_m >= p.seg_tile_start[s]) g = s;
+    x0 = p.seg_row_start[g] + (tile_m - p.seg_tile_start[g]) * kBlockM;
+    x_end = p.seg_row_start[g + 1];
+    y0 = 0;
+    i0 = 0;
+    b_noff = p.seg_b_noff[g];
+    b2_noff = p.seg_b2_noff[g];
+  } else {
+    const int tx = tile_m % p.tiles_x;
+    const int ty = (tile_m / p.tiles_x) % p.tiles_y;
+    const int tn = tile_m / (p.tiles_x * p.tiles_y);
+    x0 = tx * p.bw;
+    y0 = ty * p.bh;
+    i0 = tn * p.bn;
+    x_end = p.W;
+    b_noff = p.seg_b_noff[0];
+    b2_noff = p.seg_b2_noff[0];
+  }
+  const int kb1 = p.taps * p.kblocks1;
+  const int kb_total = kb1 + ((p.kblocks2 > 0 && b2_noff >= 0) ? p.kblocks2 : 0);
+
+  // ---- one-time setup ----------------------------------------------------------------------
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.kblocks2 > 0) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===========================================
+    if (lane == 0) {
+      for (int kb = 0; kb < kb_total; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * kStageBytes;
+        uint8_t* sb = sa + kABytes;
+        mbar_expect_tx(&full_bar[s], kStageBytes);
+        if (kb < kb1) {
+          const int tap = kb / p.kblocks1;
+          const int cb = kb - tap * p.kblocks1;
+          int dx = 0, dy = 0;
+          if (p.taps == 9) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+          }
+          tma_load_4d(sa, &tmA, &full_bar[s], cb * kBlockK, x0 + dx, y0 + dy, i0);
+          tma_load_3d(sb, &tmB, &full_bar[s], cb * kBlockK, tap, b_noff + n0);
+        } else {
+          const int cb = kb - kb1;
+          tma_load_4d(sa, &tmA2, &full_bar[s], cb * kBlockK, x0, y0, i0);  // centre tap (1x1)
+          tma_load_3d(sb, &tmB2, &full_bar[s], cb * kBlockK, 0, b2_noff + n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =============================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N, Cvt<T>::kFmt, 0, 0);
+      for (int kb = 0; kb < kb_total; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * kStageBytes);
+        const uint32_t sb = sa + kABytes;
+        const uint64_t adesc = smem_desc_sw128(sa, 16, 1024);
+        const uint64_t bdesc = smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          // advancing 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in the >>4 address field
+          umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
+      }
+      umma_commit(&accum_bar);  // accumulator complete
+    }
+  } else {
+    // =============================== epilogue ===============================================
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;       // row of the tile owned by this thread
+    // row -> pixel
+    int xl, yl, il;
+    if (p.flat) {
+      xl = r;
+      yl = 0;
+      il = 0;
+    } else {
+      xl = r % p.bw;
+      yl = (r / p.bw) % p.bh;
+      il = r / (p.bw * p.bh);
+    }
+    const int x = x0 + xl, y = y0 + yl, img_c = i0 + il;
+    const bool row_ok = (x < x_end) && (y < p.H) && (img_c < p.NI);
+    const long long row = (static_cast<long long>(img_c) * p.H + y) * p.W + x;
+    const int img = p.flat ? (p.rows_per_img > 0 ? x / p.rows_per_img : 0) : img_c;
+
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+    if (p.act == ES_ACT_GEGLU) {
+      constexpr int HALF = BLOCK_N / 2;
+      const int oc0 = blockIdx.y * HALF;  // output column base
+      const int n_out = p.N / 2;
+#pragma unroll 1
+      for (int c = 0; c < HALF; c += 16) {
+        uint32_t va[16], vg[16];
+        tmem_ld_x16(t_row + c, va);
+        tmem_ld_x16(t_row + HALF + c, vg);
+        tmem_ld_wait();
+        if (row_ok) {
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a = __uint_as_float(va[j]);
+            float g = __uint_as_float(vg[j]);
+            if (p.bias) {
+              a += p.bias[b_noff + n0 + c + j];
+              g += p.bias[b_noff + n0 + HALF + c + j];
+            }
+            o[j] = p.alpha * a * gelu_erf_f(g);
+          }
+          T* optr = reinterpret_cast<T*>(p.out) + row * p.ldc + oc0 + c;
+          if (oc0 + c + 16 <= n_out) {
+            uint4 w0, w1;
+            w0.x = Cvt<T>::pack2(o[0], o[1]); w0.y = Cvt<T>::pack2(o[2], o[3]);
+            w0.z = Cvt<T>::pack2(o[4], o[5]); w0.w = Cvt<T>::pack2(o[6], o[7]);
+            w1.x = Cvt<T>::pack2(o[8], o[9]); w1.y = Cvt<T>::pack2(o[10], o[11]);
+            w1.z = Cvt<T>::pack2(o[12], o[13]); w1.w = Cvt<T>::pack2(o[14], o[15]);
+            reinterpret_cast<uint4*>(optr)[0] = w0;
+            reinterpret_cast<uint4*>(optr)[1] = w1;
+          } else {
+            for (int j = 0; j < 16; ++j)
+              if (oc0 + c + j < n_out) optr[j] = Cvt<T>::from_f(o[j]);
+          }
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(t_row + c, v);
+        tmem_ld_wait();
+        if (row_ok && n0 + c < p.N) {
+          float o[16];
+          const bool full = (n0 + c + 16 <= p.N);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (full || n0 + c + j < p.N) o[j] += p.bias[b_noff + n0 + c + j];
+          }
+          if (p.rowvec) {
+            const float* rv = p.rowvec + static_cast<long long>(img) * p.rowvec_ld + n0 + c;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (full || n0 + c + j < p.N) o[j] += rv[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] *= p.alpha;
+          if (p.residual) {
+            const T* rp = reinterpret_cast<const T*>(p.residual) + row * p.ldr + n0 + c;
+            if (full) {
+              uint4 r0 = reinterpret_cast<const uint4*>(rp)[0];
+              uint4 r1 = reinterpret_cast<const uint4*>(rp)[1];
+              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float2 f = Cvt<T>::unpack2(rr[j]);
+                o[2 * j] += f.x;
+                o[2 * j + 1] += f.y;
+              }
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (n0 + c + j < p.N) o[j] += Cvt<T>::to_f(rp[j]);
+            }
+          }
+          if (p.out_fp32) {
+            float* optr = reinterpret_cast<float*>(p.out) + row * p.ldc + n0 + c;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                reinterpret_cast<float4*>(optr)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (n0 + c + j < p.N) optr[j] = o[j];
+            }
+          } else {
+            T* optr = reinterpret_cast<T*>(p.out) + row * p.ldc + n0 + c;
+            if (full) {
+              uint4 w0, w1;
+              w0.x = Cvt<T>::pack2(o[0], o[1]); w0.y = Cvt<T>::pack2(o[2], o[3]);
+              w0.z = Cvt<T>::pack2(o[4], o[5]); w0.w = Cvt<T>::pack2(o[6], o[7]);
+              w1.x = Cvt<T>::pack2(o[8], o[9]); w1.y = Cvt<T>::pack2(o[10], o[11]);
+              w1.z = Cvt<T>::pack2(o[12], o[13]); w1.w = Cvt<T>::pack2(o[14], o[15]);
+              reinterpret_cast<uint4*>(optr)[0] = w0;
+              reinterpret_cast<uint4*>(optr)[1] = w1;
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (n0 + c + j < p.N) optr[j] = Cvt<T>::from_f(o[j]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown ------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// host
+// --------------------------------------------------------------------------------------------
+template <typename T, int BLOCK_N>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
+                       const CUtensorMap& tmB2, GemmKParams& kp, int m_tiles, int n_tiles, cudaStream_t stream) {
+  constexpr int kStageBytes = kBlockM * kBlockK * 2 + BLOCK_N * kBlockK * 2;
+  int stages = (200 * 1024) / kStageBytes;
+  if (stages > 8) stages = 8;
+  const int kb_total = kp.taps * kp.kblocks1 + kp.kblocks2;
+  if (stages > kb_total) stages = kb_total < 2 ? 2 : kb_total;
+  kp.stages = stages;
+  const size_t smem = static_cast<size_t>(stages) * kStageBytes + 1024;
+  auto kern = gemm_kernel<T, BLOCK_N>;
+  static size_t attr_smem = 0;  // per instantiation
+  if (smem > attr_smem) {
+    ES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_smem = smem;
+  }
+  dim3 grid(m_tiles, n_tiles, 1);
+  kern<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, tmA2, tmB2, kp);
+  ES_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int pick_block_n(int n, int m_tiles, int act) {
+  // prefer no column waste, then enough CTAs to cover the 148 SMs
+  const int cands[5] = {256, 160, 128, 64, 32};
+  int best = 32;
+  double best_cost = 1e30;
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cands[i];
+    if (act == ES_ACT_GEGLU && (bn % 32 != 0)) continue;
+    const int nt = ceil_div(n, bn);
+    const double waste = static_cast<double>(nt) * bn / n;  // >= 1
+    const int ctas = nt * m_tiles;
+    const int waves = ceil_div(ctas, 148);
+    // time ~ waves * (per-tile time ~ bn + fixed overhead)
+    const double cost = waves * (bn + 48.0) * (0.9 + 0.1 * waste);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+template <typename T>
+static int gemm_dispatch(const EsGemm* g, cudaStream_t stream) {
+  GemmKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  const bool flat = (g->taps == 1);
+  ES_CHECK(g->taps == 1 || g->taps == 9, "es_gemm: taps must be 1 or 9 (got %d)", g->taps);
+  ES_CHECK(g->c1 > 0 && g->c1 % 8 == 0 && g->lda % 8 == 0, "es_gemm: c1/lda must be multiples of 8 (c1=%d lda=%lld)",
+           g->c1, g->lda);
+  ES_CHECK((reinterpret_cast<uintptr_t>(g->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g->b) & 15) == 0,
+           "es_gemm: a/b must be 16-byte aligned");
+  ES_CHECK(g->n > 0 && g->w > 0 && g->h > 0 && g->n_img > 0, "es_gemm: bad shape");
+  ES_CHECK(g->ldc % 8 == 0 || g->out_fp32, "es_gemm: ldc must be a multiple of 8");
+  kp.flat = flat ? 1 : 0;
+  kp.N = g->n;
+  kp.taps = g->taps;
+  kp.kblocks1 = ceil_div(g->c1, kBlockK);
+  kp.kblocks2 = 0;
+  int m_tiles;
+  int W, H, NI;
+  if (flat) {
+    // treat [n_img, h, w] as one flat row dimension
+    const long long M = static_cast<long long>(g->w) * g->h * g->n_img;
+    ES_CHECK(M < (1ll << 31), "es_gemm: M too large");
+    W = static_cast<int>(M);
+    H = 1;
+    NI = 1;
+    kp.bw = kBlockM;
+    kp.bh = 1;
+    kp.bn = 1;
+    kp.nseg = g->nseg > 0 ? g->nseg : 1;
+    ES_CHECK(kp.nseg <= ES_MAX_SEG, "es_gemm: too many segments");
+    int tiles = 0;
+    for (int s = 0; s < kp.nseg; ++s) {
+      const int r0 = g->nseg > 0 ? g->seg_row_start[s] : 0;
+      const int r1 = g->nseg > 0 ? g->seg_row_start[s + 1] : W;
+      ES_CHECK(r1 >= r0 && r1 <= W, "es_gemm: bad segment bounds");
+      kp.seg_row_start[s] = r0;
+      kp.seg_row_start[s + 1] = r1;
+      kp.seg_tile_start[s] = tiles;
+      tiles += ceil_div(r1 - r0, kBlockM);
+      kp.seg_b_noff[s] = g->nseg > 0 ? g->seg_b_noff[s] : 0;
+      kp.seg_b2_noff[s] = g->a2 ? (g->nseg > 0 ? g->seg_b2_noff[s] : 0) : -1;
+    }
+    kp.seg_tile_start[kp.nseg] = tiles;
+    m_tiles = tiles;
+    kp.tiles_x = tiles;
+    kp.tiles_y = 1;
+  } else {
+    W = g->w;
+    H = g->h;
+    NI = g->n_img;
+    int bw = W >= kBlockM ? kBlockM : W;
+    ES_CHECK(kBlockM % bw == 0, "es_gemm: conv width %d must divide 128 or be >= 128", W);
+    int bh = kBlockM / bw;
+    int bn = 1;
+    if (bh > H) {
+      // several whole images per tile (8x8 level): H must divide bh
+      int hh = 1;
+      while (hh < H) hh <<= 1;  // next pow2 >= H
+      bn = bh / hh;
+      bh = hh;
+    }
+    kp.bw = bw;
+    kp.bh = bh;
+    kp.bn = bn;
+    kp.tiles_x = ceil_div(W, bw);
+    kp.tiles_y = ceil_div(H, bh);
+    m_tiles = kp.tiles_x * kp.tiles_y * ceil_div(NI, bn);
+    kp.nseg = 1;
+    kp.seg_b_noff[0] = g->nseg > 0 ? g->seg_b_noff[0] : 0;
+    kp.seg_b2_noff[0] = g->a2 ? (g->nseg > 0 ? g->seg_b2_noff[0] : 0) : -1;
+  }
+  kp.W = W;
+  kp.H = H;
+  kp.NI = NI;
+  kp.bias = g->bias;
+  kp.rowvec = g->rowvec;
+  kp.rows_per_img = g->rows_per_img;
+  kp.rowvec_ld = g->rowvec_ld;
+  kp.residual = g->residual;
+  kp.ldr = g->ldr;
+  kp.act = g->act;
+  kp.alpha = g->alpha;
+  kp.out = g->out;
+  kp.ldc = g->ldc;
+  kp.out_fp32 = g->out_fp32;
+  if (g->residual) ES_CHECK(g->ldr % 8 == 0, "es_gemm: ldr must be a multiple of 8");
+  if (g->act == ES_ACT_GEGLU) ES_CHECK(g->n % 2 == 0 && !g->out_fp32 && !g->residual && !g->rowvec, "es_gemm: bad GEGLU config");
+
+  int bn_tile = g->block_n > 0 ? g->block_n : pick_block_n(g->n, m_tiles, g->act);
+  const int n_tiles = ceil_div(g->n, bn_tile);
+  if (g->act == ES_ACT_GEGLU) ES_CHECK(g->n % bn_tile == 0, "es_gemm: GEGLU needs n %% block_n == 0 (n=%d bn=%d)", g->n, bn_tile);
+
+  // ---- tensor maps ----------------------------------------------------------------------
+  CUtensorMap tmA, tmB, tmA2, tmB2;
+  {
+    const uint64_t pitch = static_cast<uint64_t>(g->lda) * 2;
+    uint64_t dims[4], strides[4];
+    uint32_t box[4] = {static_cast<uint32_t>(kBlockK), static_cast<uint32_t>(kp.bw), static_cast<uint32_t>(kp.bh),
+                       static_cast<uint32_t>(kp.bn)};
+    dims[0] = g->c1;
+    dims[1] = W;
+    dims[2] = H;
+    dims[3] = NI;
+    strides[1] = pitch;
+    strides[2] = pitch * W;
+    strides[3] = pitch * W * H;
+    if (encode_tmap_16b(&tmA, g->a, 4, dims, strides, box)) return -3;
+  }
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(g->c1), static_cast<uint64_t>(g->taps),
+                        static_cast<uint64_t>(g->n_total_b)};
+    uint64_t strides[3] = {0, static_cast<uint64_t>(g->c1) * 2, static_cast<uint64_t>(g->c1) * 2 * g->taps};
+    uint32_t box[3] = {static_cast<uint32_t>(kBlockK), 1u, static_cast<uint32_t>(bn_tile)};
+    ES_CHECK(g->n_total_b >= g->n, "es_gemm: n_total_b < n");
+    if (encode_tmap_16b(&tmB, g->b, 3, dims, strides, box)) return -3;
+  }
+  tmA2 = tmA;
+  tmB2 = tmB;
+  if (g->a2) {
+    ES_CHECK(g->c2 > 0 && g->c2 % 8 == 0 && g->lda2 % 8 == 0 && g->b2, "es_gemm: bad source 2");
+    kp.kblocks2 = ceil_div(g->c2, kBlockK);
+    const uint64_t pitch = static_cast<uint64_t>(g->lda2) * 2;
+    uint64_t dims[4] = {static_cast<uint64_t>(g->c2), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                        static_cast<uint64_t>(NI)};
+    uint64_t strides[4] = {0, pitch, pitch * W, pitch * W * H};
+    uint32_t box[4] = {static_cast<uint32_t>(kBlockK), static_cast<uint32_t>(kp.bw), static_cast<uint32_t>(kp.bh),
+                       static_cast<uint32_t>(kp.bn)};
+    if (encode_tmap_16b(&tmA2, g->a2, 4, dims, strides, box)) return -3;
+    uint64_t dimsb[3] = {static_cast<uint64_t>(g->c2), 1, static_cast<uint64_t>(g->n_total_b2)};
+    uint64_t stridesb[3] = {0, static_cast<uint64_t>(g->c2) * 2, static_cast<uint64_t>(g->c2) * 2};
+    uint32_t boxb[3] = {static_cast<uint32_t>(kBlockK), 1u, static_cast<uint32_t>(bn_tile)};
+    if (encode_tmap_16b(&tmB2, g->b2, 3, dimsb, stridesb, boxb)) return -3;
+  }
+
+  switch (bn_tile) {
+    case 32: return launch_gemm<T, 32>(tmA, tmB, tmA2, tmB2, kp, m_tiles, n_tiles, stream);
+    case 64: return launch_gemm<T, 64>(tmA, tmB, tmA2, tmB2, kp, m_tiles, n_tiles, stream);
+    case 128: return launch_gemm<T, 128>(tmA, tmB, tmA2, tmB2, kp, m_tiles, n_tiles, stream);
+    case 160: return launch_gemm<T, 160>(tmA, tmB, tmA2, tmB2, kp, m_tiles, n_tiles, stream);
+    case 256: return launch_gemm<T, 256>(tmA, tmB, tmA2, tmB2, kp, m_tiles, n_tiles, stream);
+    default: ES_CHECK(false, "es_gemm: unsupported block_n %d", bn_tile);
+  }
+  return 0;
+}
+
+}  // namespace es
+
+extern "C" int es_gemm(const EsGemm* g, void* stream) {
+  if (!g) {
+    es::set_error("es_gemm: null descriptor");
+    return -1;
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (g->dtype == ES_DTYPE_F16) return es::gemm_dispatch<__half>(g, s);
+  if (g->dtype == ES_DTYPE_BF16) return es::gemm_dispatch<__nv_bfloat16>(g, s);
+  es::set_error("es_gemm: unknown dtype %d", g->dtype);
+  return -1;
+}

@@ -1,0 +1,260 @@
+// Bandwidth kernels: GroupNorm(+SiLU)(+channel concat) and LayerNorm over channels-last activations.
+// fp16/bf16 in/out, fp32 statistics, 16-byte vector loads/stores, fixed channel-vector per thread so the
+// per-channel scale/shift lives in registers.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace es {
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&f)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = Cvt<T>::unpack2(u.x), b = Cvt<T>::unpack2(u.y), c = Cvt<T>::unpack2(u.z), d = Cvt<T>::unpack2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = Cvt<T>::pack2(f[0], f[1]); u.y = Cvt<T>::pack2(f[2], f[3]);
+  u.z = Cvt<T>::pack2(f[4], f[5]); u.w = Cvt<T>::pack2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// grid (chunks, n_img); block (C/8, ny)
+template <typename T>
+__global__ void gn_stats_kernel(const T* __restrict__ x0, int c0, long long ld0, const T* __restrict__ x1, int c1,
+                                long long ld1, int hw, int groups, float* __restrict__ ws) {
+  extern __shared__ float sm[];  // [C][2]
+  const int C = c0 + c1;
+  const int cpg = C / groups;
+  const int v = threadIdx.x;  // channel vector
+  const int img = blockIdx.y;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = tid; i < 2 * C; i += blockDim.x * blockDim.y) sm[i] = 0.f;
+  __syncthreads();
+  const T* src;
+  long long ld;
+  int ch = v * 8;
+  if (ch < c0) {
+    src = x0 + static_cast<long long>(img) * hw * ld0 + ch;
+    ld = ld0;
+  } else {
+    src = x1 + static_cast<long long>(img) * hw * ld1 + (ch - c0);
+    ld = ld1;
+  }
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+  const int per = (hw + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per;
+  const int p1 = min(hw, p0 + per);
+  for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+    float f[8];
+    load8<T>(src + static_cast<long long>(p) * ld, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += f[j];
+      ss[j] += f[j] * f[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sm[2 * (ch + j)], s[j]);
+    atomicAdd(&sm[2 * (ch + j) + 1], ss[j]);
+  }
+  __syncthreads();
+  for (int g = tid; g < groups; g += blockDim.x * blockDim.y) {
+    float a = 0.f, b = 0.f;
+    for (int j = 0; j < cpg; ++j) {
+      a += sm[2 * (g * cpg + j)];
+      b += sm[2 * (g * cpg + j) + 1];
+    }
+    atomicAdd(&ws[(static_cast<long long>(img) * groups + g) * 2], a);
+    atomicAdd(&ws[(static_cast<long long>(img) * groups + g) * 2 + 1], b);
+  }
+}
+
+template <typename T>
+__global__ void gn_apply_kernel(const T* __restrict__ x0, int c0, long long ld0, const T* __restrict__ x1, int c1,
+                                long long ld1, int hw, int groups, float eps, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, const float* __restrict__ ws, T* __restrict__ out,
+                                long long ldo, int silu) {
+  const int C = c0 + c1;
+  const int cpg = C / groups;
+  const int v = threadIdx.x;
+  const int img = blockIdx.y;
+  const int ch = v * 8;
+  const T* src;
+  long long ld;
+  if (ch < c0) {
+    src = x0 + static_cast<long long>(img) * hw * ld0 + ch;
+    ld = ld0;
+  } else {
+    src = x1 + static_cast<long long>(img) * hw * ld1 + (ch - c0);
+    ld = ld1;
+  }
+  float a[8], b[8];
+  const float inv_n = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (ch + j) / cpg;
+    const float sum = ws[(static_cast<long long>(img) * groups + g) * 2];
+    const float sq = ws[(static_cast<long long>(img) * groups + g) * 2 + 1];
+    const float mean = sum * inv_n;
+    const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    a[j] = rstd * gamma[ch + j];
+    b[j] = beta[ch + j] - mean * a[j];
+  }
+  T* dst = out + static_cast<long long>(img) * hw * ldo + ch;
+  const int per = (hw + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per;
+  const int p1 = min(hw, p0 + per);
+  for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+    float f[8];
+    load8<T>(src + static_cast<long long>(p) * ld, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = f[j] * a[j] + b[j];
+      f[j] = silu ? silu_f(y) : y;
+    }
+    store8<T>(dst + static_cast<long long>(p) * ldo, f);
+  }
+}
+
+static int gn_check(const EsGroupNorm* g) {
+  ES_CHECK(g && g->x0 && g->ws, "es_groupnorm: null pointer");
+  const int C = g->c0 + g->c1;
+  ES_CHECK(g->c0 % 8 == 0 && g->c1 % 8 == 0 && g->ld0 % 8 == 0 && (g->c1 == 0 || g->ld1 % 8 == 0),
+           "es_groupnorm: channels and pitches must be multiples of 8");
+  ES_CHECK(C % g->groups == 0 && C / 8 <= 1024, "es_groupnorm: bad channel count %d", C);
+  ES_CHECK(g->c1 == 0 || g->x1, "es_groupnorm: c1 > 0 but x1 is null");
+  return 0;
+}
+
+static void gn_geometry(const EsGroupNorm* g, dim3& grid, dim3& block) {
+  const int vpp = (g->c0 + g->c1) / 8;
+  int ny = 256 / vpp;
+  if (ny < 1) ny = 1;
+  if (ny > g->hw) ny = g->hw;
+  block = dim3(vpp, ny, 1);
+  int chunks = (4 * 148 + g->n_img - 1) / g->n_img;
+  const int max_chunks = (g->hw + ny * 4 - 1) / (ny * 4);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  grid = dim3(chunks, g->n_img, 1);
+}
+
+template <typename T>
+static int gn_stats_t(const EsGroupNorm* g, cudaStream_t s) {
+  dim3 grid, block;
+  gn_geometry(g, grid, block);
+  const size_t smem = static_cast<size_t>(g->c0 + g->c1) * 2 * sizeof(float);
+  gn_stats_kernel<T><<<grid, block, smem, s>>>(reinterpret_cast<const T*>(g->x0), g->c0, g->ld0,
+                                               reinterpret_cast<const T*>(g->x1), g->c1, g->ld1, g->hw, g->groups,
+                                               g->ws);
+  ES_CUDA(cudaGetLastError());
+  return 0;
+}
+template <typename T>
+static int gn_apply_t(const EsGroupNorm* g, cudaStream_t s) {
+  dim3 grid, block;
+  gn_geometry(g, grid, block);
+  ES_CHECK(g->out && g->ldo % 8 == 0 && g->gamma && g->beta, "es_groupnorm_apply: bad output/affine");
+  gn_apply_kernel<T><<<grid, block, 0, s>>>(reinterpret_cast<const T*>(g->x0), g->c0, g->ld0,
+                                            reinterpret_cast<const T*>(g->x1), g->c1, g->ld1, g->hw, g->groups, g->eps,
+                                            g->gamma, g->beta, g->ws, reinterpret_cast<T*>(g->out), g->ldo, g->silu);
+  ES_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------- LayerNorm: one warp per row
+template <typename T, int MAXV>
+__global__ void layernorm_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ out, long long ldo,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int c,
+                                 float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = c >> 3;
+  const T* src = x + static_cast<long long>(row) * ldx;
+  float f[MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nv) {
+      load8<T>(src + v * 8, f[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[i][j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / c;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = f[i][j] - mean;
+        q += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / c + eps);
+  T* dst = out + static_cast<long long>(row) * ldo;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nv) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * gamma[v * 8 + j] + beta[v * 8 + j];
+      store8<T>(dst + v * 8, o);
+    }
+  }
+}
+
+template <typename T>
+static int layernorm_t(const void* x, long long ldx, void* out, long long ldo, const float* gamma, const float* beta,
+                       int rows, int c, float eps, cudaStream_t s) {
+  ES_CHECK(c % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && c <= 8 * 32 * 8, "es_layernorm: unsupported c=%d", c);
+  const int warps = 8;
+  dim3 grid((rows + warps - 1) / warps), block(warps * 32);
+  const int nv = c / 8;
+  if (nv <= 32 * 2)
+    layernorm_kernel<T, 2><<<grid, block, 0, s>>>(reinterpret_cast<const T*>(x), ldx, reinterpret_cast<T*>(out), ldo,
+                                                  gamma, beta, rows, c, eps);
+  else if (nv <= 32 * 5)
+    layernorm_kernel<T, 5><<<grid, block, 0, s>>>(reinterpret_cast<const T*>(x), ldx, reinterpret_cast<T*>(out), ldo,
+                                                  gamma, beta, rows, c, eps);
+  else
+    layernorm_kernel<T, 8><<<grid, block, 0, s>>>(reinterpret_cast<const T*>(x), ldx, reinterpret_cast<T*>(out), ldo,
+                                                  gamma, beta, rows, c, eps);
+  ES_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace es
+
+extern "C" int es_groupnorm_stats(const EsGroupNorm* g, void* stream) {
+  if (es::gn_check(g)) return -1;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return g->dtype == ES_DTYPE_BF16 ? es::gn_stats_t<__nv_bfloat16>(g, s) : es::gn_stats_t<__half>(g, s);
+}
+extern "C" int es_groupnorm_apply(const EsGroupNorm* g, void* stream) {
+  if (es::gn_check(g)) return -1;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return g->dtype == ES_DTYPE_BF16 ? es::gn_apply_t<__nv_bfloat16>(g, s) : es::gn_apply_t<__half>(g, s);
+}
+extern "C" int es_layernorm(int dtype, const void* x, long long ldx, void* out, long long ldo, const float* gamma,
+                            const float* beta, int rows, int c, float eps, void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return dtype == ES_DTYPE_BF16 ? es::layernorm_t<__nv_bfloat16>(x, ldx, out, ldo, gamma, beta, rows, c, eps, s)
+                                : es::layernorm_t<__half>(x, ldx, out, ldo, gamma, beta, rows, c, eps, s);
+}

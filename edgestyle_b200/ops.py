@@ -1,0 +1,214 @@
+"""Tensor-level wrappers over the C-ABI (torch is only the allocator / stream provider).
+
+All activations are channels-last 2-D views [rows, channels] (rows = images * H * W) in fp16/bf16.
+Every function enqueues on torch's current CUDA stream and returns its output tensor.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import ext
+from .ext import ACT_GEGLU, ACT_NONE, EsAttention, EsGemm, EsGroupNorm, EsMerge, check, load
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float16:
+        return ext.DTYPE_F16
+    if t.dtype == torch.bfloat16:
+        return ext.DTYPE_BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise ext.EdgeStyleNativeError("edgestyle_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: int = 1, whn=None, bias=None,
+         rowvec=None, rows_per_img: int = 0, residual=None, act: int = ACT_NONE, alpha: float = 1.0,
+         a2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None, segs=None, block_n: int = 0,
+         c1: Optional[int] = None):
+    """out[m, :n] = epilogue(A (*) B^T).  a: [M, >=c1] (pitch = a.stride(0)); b: [n_total, taps*c1].
+
+    whn=(w, h, n_img) for taps == 9.  segs = list of (row_start, b_noff, b2_noff) + final row end via segs_end.
+    """
+    _need_cuda(a, b, out)
+    g = EsGemm()
+    g.dtype = _dt(a)
+    g.a = a.data_ptr()
+    g.c1 = c1 if c1 is not None else a.shape[1]
+    g.lda = a.stride(0)
+    M = a.shape[0]
+    if taps == 1:
+        g.w, g.h, g.n_img = M, 1, 1
+    else:
+        g.w, g.h, g.n_img = whn
+        assert g.w * g.h * g.n_img == M
+    g.taps = taps
+    assert b.is_contiguous() and b.shape[1] == taps * g.c1, (b.shape, taps, g.c1)
+    g.b = b.data_ptr()
+    g.n_total_b = b.shape[0]
+    if a2 is not None:
+        assert b2 is not None and b2.is_contiguous() and a2.shape[0] == M
+        g.a2, g.c2, g.lda2 = a2.data_ptr(), a2.shape[1], a2.stride(0)
+        g.b2, g.n_total_b2 = b2.data_ptr(), b2.shape[0]
+    g.n = n
+    if segs:
+        rows, noff, noff2 = segs
+        g.nseg = len(noff)
+        for i, r in enumerate(rows):
+            g.seg_row_start[i] = r
+        for i in range(g.nseg):
+            g.seg_b_noff[i] = noff[i]
+            g.seg_b2_noff[i] = noff2[i] if noff2 is not None else 0
+    g.bias = _p(bias)
+    g.rowvec = _p(rowvec)
+    g.rows_per_img = rows_per_img
+    g.rowvec_ld = rowvec.stride(0) if rowvec is not None else 0
+    g.residual = _p(residual)
+    g.ldr = residual.stride(0) if residual is not None else 0
+    g.act = act
+    g.alpha = alpha
+    g.out = out.data_ptr()
+    g.ldc = out.stride(0)
+    g.out_fp32 = 1 if out.dtype == torch.float32 else 0
+    g.block_n = block_n
+    check(load().es_gemm(C.byref(g), _stream()), "es_gemm")
+    return out
+
+
+def attention(q, k, v, out, batch: int, heads: int, nq: int, nkv: int, scale: Optional[float] = None):
+    """q/out: [batch*nq, heads*d] views, k/v: [batch*nkv, heads*d] views (row pitch = stride(0))."""
+    _need_cuda(q, k, v, out)
+    d = q.shape[1] // heads
+    a = EsAttention()
+    a.dtype = _dt(q)
+    a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.ldq, a.ldk, a.ldv, a.ldo = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
+    a.bsq, a.bsk, a.bsv, a.bso = nq * q.stride(0), nkv * k.stride(0), nkv * v.stride(0), nq * out.stride(0)
+    a.batch, a.heads, a.d, a.nq, a.nkv = batch, heads, d, nq, nkv
+    a.scale = scale if scale is not None else d ** -0.5
+    check(load().es_attention(C.byref(a), _stream()), "es_attention")
+    return out
+
+
+def groupnorm(x0, out, gamma, beta, ws, n_img: int, hw: int, groups: int, eps: float, silu: bool, x1=None):
+    """GroupNorm(+SiLU) over [n_img*hw, c0(+c1)]; ws: fp32 [n_img, groups, 2] scratch (zeroed here)."""
+    _need_cuda(x0, out, ws)
+    g = EsGroupNorm()
+    g.dtype = _dt(x0)
+    g.x0, g.c0, g.ld0 = x0.data_ptr(), x0.shape[1], x0.stride(0)
+    if x1 is not None:
+        g.x1, g.c1, g.ld1 = x1.data_ptr(), x1.shape[1], x1.stride(0)
+    g.n_img, g.hw, g.groups, g.eps = n_img, hw, groups, eps
+    g.gamma, g.beta = gamma.data_ptr(), beta.data_ptr()
+    g.ws = ws.data_ptr()
+    g.out, g.ldo = out.data_ptr(), out.stride(0)
+    g.silu = 1 if silu else 0
+    ws.zero_()
+    lib = load()
+    check(lib.es_groupnorm_stats(C.byref(g), _stream()), "es_groupnorm_stats")
+    check(lib.es_groupnorm_apply(C.byref(g), _stream()), "es_groupnorm_apply")
+    return out
+
+
+def layernorm(x, out, gamma, beta, eps: float = 1e-5):
+    _need_cuda(x, out)
+    check(load().es_layernorm(_dt(x), x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), gamma.data_ptr(),
+                              beta.data_ptr(), x.shape[0], x.shape[1], eps, _stream()), "es_layernorm")
+    return out
+
+
+def merge(res: Sequence[torch.Tensor], scale: Sequence[float], prm: dict, stats, z, B: int, hw: int, Cc: int, dst,
+          skip=None):
+    """EdgeStyle ControlNetBlock over six [B*hw, C] residual slabs; dst = skip + block(res)."""
+    m = EsMerge()
+    m.dtype = _dt(res[0])
+    for i in range(6):
+        m.res[i] = res[i].data_ptr()
+        m.scale[i] = float(scale[i])
+    m.B, m.hw, m.C = B, hw, Cc
+    for k in ("w1", "b1", "w2", "b2", "w3", "b3", "g1", "be1", "g2", "be2"):
+        setattr(m, k, prm[k].data_ptr())
+    m.stats, m.z = stats.data_ptr(), z.data_ptr()
+    if skip is not None:
+        m.skip, m.lds = skip.data_ptr(), skip.stride(0)
+    m.dst, m.ldd = dst.data_ptr(), dst.stride(0)
+    stats.zero_()
+    lib = load()
+    for ph in (1, 2, 3):
+        check(lib.es_merge_phase(C.byref(m), ph, _stream()), f"es_merge_phase({ph})")
+    return dst
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, out: torch.Tensor):
+    check(load().es_timestep_embedding(t.data_ptr(), t.shape[0], dim, out.data_ptr(), _stream()),
+          "es_timestep_embedding")
+    return out
+
+
+def small_linear(x, w, bias, y, *, silu_in=False, silu_out=False, accumulate=False):
+    """y[r, :] (+)= act_out(act_in(x[r, :]) @ w^T + bias); x, y fp32; w fp16/bf16 [n, k]."""
+    rows, k = x.shape
+    n = w.shape[0]
+    assert w.shape[1] == k and w.is_contiguous()
+    check(load().es_small_linear(_dt(w), x.data_ptr(), x.stride(0), w.data_ptr(), _p(bias), y.data_ptr(), y.stride(0),
+                                 rows, n, k, int(silu_in), int(silu_out), int(accumulate), _stream()),
+          "es_small_linear")
+    return y
+
+
+def nchw_to_nhwc(src: torch.Tensor, dst: torch.Tensor):
+    """src fp32 [n, c, h, w] contiguous -> dst [n*h*w, ld] (channels zero-padded to ld)."""
+    n, c, h, w = src.shape
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    check(load().es_nchw_to_nhwc(_dt(dst), src.data_ptr(), dst.data_ptr(), n, c, h * w, dst.stride(0), _stream()),
+          "es_nchw_to_nhwc")
+    return dst
+
+
+def nhwc_to_nchw(src: torch.Tensor, dst: torch.Tensor):
+    n, c, h, w = dst.shape
+    assert dst.dtype == torch.float32 and dst.is_contiguous()
+    check(load().es_nhwc_to_nchw(_dt(src), src.data_ptr(), src.stride(0), dst.data_ptr(), n, c, h * w, _stream()),
+          "es_nhwc_to_nchw")
+    return dst
+
+
+def im2col3x3(src, dst, n: int, h: int, w: int, c: int, stride: int):
+    check(load().es_im2col3x3(_dt(src), src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), n, h, w, c,
+                              stride, _stream()), "es_im2col3x3")
+    return dst
+
+
+def upsample2x(src, dst, n: int, h: int, w: int):
+    c = src.shape[1]
+    check(load().es_upsample2x(_dt(src), src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), n, h, w, c,
+                               _stream()), "es_upsample2x")
+    return dst
+
+
+def add(a, b, out):
+    check(load().es_add(_dt(a), a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0),
+                        a.shape[0], a.shape[1], _stream()), "es_add")
+    return out
+
+
+def cfg_ddim(eps, latents, guidance, coef, eps_out=None):
+    imgs = latents.shape[0]
+    chw = latents[0].numel()
+    check(load().es_cfg_ddim(eps.data_ptr(), latents.data_ptr(), guidance.data_ptr(), coef.data_ptr(), _p(eps_out),
+                             imgs, chw, _stream()), "es_cfg_ddim")
+    return latents

@@ -1,0 +1,186 @@
+/* edgestyle_b200 -- C ABI of the B200 (sm_100a) kernels behind the EdgeStyle denoise hot path.
+ *
+ * The reference (andrei-ace/EdgeStyle) has no FFI of its own for this path: its boundary is the
+ * Python `forward` of three classes, and everything below them is ATen library kernels
+ * (SURVEY.md 2.1).  Each entry point here therefore cites the reference call site(s) whose
+ * library dispatch it replaces.  All pointers are DEVICE pointers owned by the caller (PyTorch);
+ * nothing allocates, nothing synchronises; every call enqueues on `stream` (a cudaStream_t passed
+ * as void*).  Return value: 0 on success, negative on error; `es_last_error()` gives the text.
+ * Thread-compatible: no global mutable state except the lazily resolved driver entry point.
+ *
+ * Activations are channels-last ("NHWC" == [tokens, channels]) fp16 or bf16 (`dtype`), all
+ * accumulation and statistics are fp32.
+ */
+#ifndef EDGESTYLE_B200_H
+#define EDGESTYLE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ES_DTYPE_F16 0
+#define ES_DTYPE_BF16 1
+
+#define ES_ACT_NONE 0
+#define ES_ACT_GEGLU 1 /* out[:, j] = v[:, j'] * gelu_erf(v[:, j' + tile/2]); weights pre-permuted per tile */
+
+#define ES_MAX_SEG 4
+
+const char* es_last_error(void);
+int es_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * es_gemm: tcgen05/TMEM implicit-GEMM for conv3x3(stride 1, pad 1) / conv1x1 / Linear.
+ *   replaces: every cuDNN conv and cuBLAS GEMM under UNet2DConditionModel.forward
+ *   (/root/reference/model/edgestyle_pipeline.py:500-510) and CachedControlNetModel.forward
+ *   (/root/reference/model/controllora.py:197-254): ResnetBlock2D conv1/conv2/shortcut,
+ *   Transformer2DModel proj_in/out, attention to_q/k/v/out, GEGLU FF, zero-convs; and the
+ *   LoRACompatibleLinear low-rank update (controllora.py:578-593) as a K-extension of the same
+ *   accumulator (source 2 = x @ down^T, B2 = up).
+ *
+ *   out[m, n] = alpha * act( sum_{tap, c} A[pixel(m) + tap, c] * B[noff + n, tap, c]
+ *                            + sum_{c2} A2[m, c2] * B2[noff2 + n, c2] + bias[noff + n] + rowvec[img(m), n] )
+ *               + residual[m, n]
+ *
+ *   A is [n_img, h, w, c1] with pixel pitch `lda` elements (flat GEMM: w = M, h = n_img = 1).
+ *   Row segments (flat only): rows [seg_row_start[g], seg_row_start[g+1]) use weight-row offset
+ *   seg_b_noff[g] in B/bias and seg_b2_noff[g] in B2 (-1: no source 2 for that segment).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct EsGemm {
+  int dtype;
+  const void* a;
+  int c1;
+  long long lda;
+  int w, h, n_img;
+  int taps; /* 1 or 9 */
+  const void* b; /* [n_total_b][taps][c1] */
+  int n_total_b;
+  const void* a2; /* optional [same pixels as A][c2], pitch lda2 (1x1 / centre tap) */
+  int c2;
+  long long lda2;
+  const void* b2; /* [n_total_b2][c2] */
+  int n_total_b2;
+  int n; /* GEMM N (columns of the accumulator) */
+  int nseg;
+  int seg_row_start[ES_MAX_SEG + 1];
+  int seg_b_noff[ES_MAX_SEG];
+  int seg_b2_noff[ES_MAX_SEG];
+  const float* bias;   /* fp32, indexed noff + n; may be NULL */
+  const float* rowvec; /* fp32 [imgs][rowvec_ld]; may be NULL */
+  int rows_per_img;    /* flat mode: img(m) = m / rows_per_img */
+  int rowvec_ld;
+  const void* residual; /* same dtype as A; may be NULL */
+  long long ldr;
+  int act;
+  float alpha;
+  void* out;
+  long long ldc;
+  int out_fp32;
+  int block_n; /* 0 = auto */
+} EsGemm;
+int es_gemm(const EsGemm* g, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * es_attention: flash-style softmax(Q K^T * scale) V on tcgen05/TMEM tiles fed by TMA.
+ *   replaces: F.scaled_dot_product_attention under diffusers Attention (AttnProcessor2_0) in every
+ *   BasicTransformerBlock attn1/attn2 (reached from controllora.py:205-238 and
+ *   edgestyle_pipeline.py:500).
+ *   q: [batch, nq, heads*d] pitch ldq; k, v: [batch, nkv, heads*d] pitch ldk / ldv; out like q.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct EsAttention {
+  int dtype;
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  long long ldq, ldk, ldv, ldo; /* elements between consecutive tokens */
+  long long bsq, bsk, bsv, bso; /* elements between consecutive batch items */
+  int batch, heads, d, nq, nkv;
+  float scale; /* d^-0.5 */
+} EsAttention;
+int es_attention(const EsAttention* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GroupNorm(32 groups, affine) [+ SiLU] over NHWC, optionally over the channel concat of two sources.
+ *   replaces: nn.GroupNorm + SiLU + torch.cat in ResnetBlock2D / Transformer2DModel.norm / conv_norm_out.
+ *   stats: ws[img][group][2] (sum, sumsq) fp32, zeroed by the caller.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct EsGroupNorm {
+  int dtype;
+  const void* x0; /* [n_img, hw, c0] pitch ld0 */
+  int c0;
+  long long ld0;
+  const void* x1; /* optional second source (channel concat) */
+  int c1;
+  long long ld1;
+  int n_img, hw, groups;
+  float eps;
+  const float* gamma; /* [c0+c1] */
+  const float* beta;
+  float* ws; /* [n_img][groups][2] */
+  void* out; /* [n_img, hw, c0+c1] pitch ldo */
+  long long ldo;
+  int silu;
+} EsGroupNorm;
+int es_groupnorm_stats(const EsGroupNorm* g, void* stream);
+int es_groupnorm_apply(const EsGroupNorm* g, void* stream);
+
+/* LayerNorm over the channel dim of [rows, c] (eps 1e-5, affine): BasicTransformerBlock.norm1/2/3. */
+int es_layernorm(int dtype, const void* x, long long ldx, void* out, long long ldo, const float* gamma,
+                 const float* beta, int rows, int c, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * EdgeStyle merge (ControlNetBlock, /root/reference/model/edgestyle_multicontrolnet.py:23-63 with
+ * the interleave of :160-164,479-514 folded into indexing; closed form in SURVEY.md A.9).
+ *   res[k]  : residual of net k, [B, hw, C] (zero-conv outputs, NOT yet scaled); k = 0..5
+ *   scale[k]: conditioning_scale (controllora.py:267-270)
+ *   params (repacked channels-last by the host): w1 [C][3][2], b1 [C][3], g1/be1 [hw][3][C] (dtype),
+ *           w2 [C][3], b2 [C], g2/be2 [hw][C] (dtype), w3 [C], b3 [C]
+ *   phase 1: sums of u  -> stats[b][0..1];  phase 2: z (fp32, [B,hw,C]) + sums of z -> stats[b][2..3];
+ *   phase 3: dst[b,p,c] = skip[b,p,c] + w3*SiLU(LN(z))+b3   (skip may be NULL; dst pitch ldd)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct EsMerge {
+  int dtype;
+  const void* res[6];
+  float scale[6];
+  int B, hw, C;
+  const float *w1, *b1, *w2, *b2, *w3, *b3;
+  const void *g1, *be1, *g2, *be2;
+  double* stats; /* [B][4], zeroed by the caller */
+  float* z;      /* [B][hw][C] */
+  const void* skip;
+  long long lds;
+  void* dst;
+  long long ldd;
+} EsMerge;
+int es_merge_phase(const EsMerge* m, int phase, void* stream);
+
+/* ------------------------------------------------------------------------------------------ misc */
+/* sinusoidal timestep embedding (flip_sin_to_cos, freq_shift 0): out fp32 [n][dim]; controllora.py:150 */
+int es_timestep_embedding(const float* t, int n, int dim, float* out, void* stream);
+/* y[r][n] = act_out( sum_k act_in(x[r][k]) * W[n][k] + bias[n] ) (+ y if accumulate); tiny-M linears:
+ * time_embedding.linear_1/2, resnet time_emb_proj, and their LoRA down/up.  W in `dtype`, x/y fp32. */
+int es_small_linear(int dtype, const float* x, int ldx, const void* w, const float* bias, float* y, int ldy, int rows,
+                    int n, int k, int silu_in, int silu_out, int accumulate, void* stream);
+/* NCHW fp32 [n,c,h,w] -> NHWC dtype [n,h,w,c_pad] (zero padded channels), and back. */
+int es_nchw_to_nhwc(int dtype, const float* src, void* dst, int n, int c, int hw, long long ldd, void* stream);
+int es_nhwc_to_nchw(int dtype, const void* src, long long lds, float* dst, int n, int c, int hw, void* stream);
+/* im2col for 3x3 pad 1 stride s over NHWC: out [n*ho*wo][ldo] with column = tap*c + ch (zero padded to ldo). */
+int es_im2col3x3(int dtype, const void* src, long long lds, void* dst, long long ldo, int n, int h, int w, int c,
+                 int stride, void* stream);
+/* nearest-neighbour x2 upsample NHWC (Upsample2D before its conv). */
+int es_upsample2x(int dtype, const void* src, long long lds, void* dst, long long ldd, int n, int h, int w, int c,
+                  void* stream);
+/* y = a + b elementwise over [rows, c] with pitches (skip + residual etc.). */
+int es_add(int dtype, const void* a, long long lda, const void* b, long long ldb, void* out, long long ldo, int rows,
+           int c, void* stream);
+/* CFG combine + DDIM update (edgestyle_pipeline.py:513-522): eps NCHW fp32 [2*imgs, c, hw] (uncond rows first),
+ * latents fp32 [imgs, c, hw] updated in place; guidance per image; coef = {sqrt(a_t), sqrt(1-a_t), sqrt(a_prev),
+ * sqrt(1-a_prev)}.  eps_out (optional) receives the guided eps. */
+int es_cfg_ddim(const float* eps, float* latents, const float* guidance, const float* coef, float* eps_out, int imgs,
+                int chw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

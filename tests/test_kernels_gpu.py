@@ -1,0 +1,355 @@
+"""Op-level parity of every CUDA kernel against fp32 PyTorch references / the oracle (run on the B200)."""
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib():
+    from edgestyle_b200 import build, ext
+
+    if not os.path.exists(ext.LIB_PATH):
+        build.build()
+    ext.load()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def _rand(*shape, dtype=torch.float16, scale=1.0, seed=None):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed if seed is not None else (hash(shape) & 0xFFFF))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+def _close(got, want, atol, rtol, what=""):
+    got = got.float()
+    want = want.float()
+    err = (got - want).abs()
+    tol = atol + rtol * want.abs()
+    bad = (err > tol).sum().item()
+    assert bad == 0, f"{what}: {bad} / {err.numel()} elements off, max err {err.max().item():.4g}"
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K,bn", [(256, 320, 320, 0), (300, 640, 960, 160), (128, 64, 64, 64), (4096, 320, 1280, 0),
+                                      (77, 1280, 768, 256), (1000, 96, 40, 32), (130, 200, 72, 128)])
+def test_gemm_flat(M, N, K, bn, dtype):
+    from edgestyle_b200 import ops
+
+    a = _rand(M, K, dtype=dtype, seed=1)
+    b = _rand(N, K, dtype=dtype, scale=K ** -0.5, seed=2)
+    bias = _rand(N, dtype=torch.float32, seed=3)
+    res = _rand(M, N, dtype=dtype, seed=4)
+    out = torch.empty(M, N, device=DEV, dtype=dtype)
+    ops.gemm(a, b, N, out=out, bias=bias, residual=res, block_n=bn)
+    want = a.float() @ b.float().t() + bias + res.float()
+    tol = 2e-2 if dtype == torch.bfloat16 else 4e-3
+    _close(out, want, tol, tol, f"gemm {M}x{N}x{K}")
+
+
+def test_gemm_strided_views_fp32_out_rowvec_alpha():
+    from edgestyle_b200 import ops
+
+    M, N, K = 512, 192, 128
+    abuf = _rand(M, K + 64, seed=5)
+    a = abuf[:, 32:32 + K]  # pitch K+64, offset 32 (64-byte aligned)
+    b = _rand(N, K, scale=K ** -0.5, seed=6)
+    rowvec = _rand(4, N, dtype=torch.float32, seed=7)
+    obuf = torch.zeros(M, N + 64, device=DEV, dtype=torch.float32)
+    out = obuf[:, 16:16 + N]
+    ops.gemm(a, b, N, out=out, rowvec=rowvec, rows_per_img=128, alpha=0.5)
+    want = 0.5 * (a.float() @ b.float().t() + rowvec.repeat_interleave(128, 0))
+    _close(out, want, 3e-3, 3e-3, "gemm strided")
+    assert obuf[:, :16].abs().max() == 0 and obuf[:, 16 + N:].abs().max() == 0
+
+
+def test_gemm_geglu():
+    from edgestyle_b200 import ops
+
+    M, C, bn = 384, 320, 160
+    a = _rand(M, C, seed=8)
+    w = _rand(8 * C, C, scale=C ** -0.5, seed=9)  # rows [0,4C) = value, [4C,8C) = gate
+    bias = _rand(8 * C, dtype=torch.float32, seed=10)
+    half = bn // 2
+    idx = []
+    for t in range(8 * C // bn):
+        idx += list(range(t * half, (t + 1) * half)) + list(range(4 * C + t * half, 4 * C + (t + 1) * half))
+    idx = torch.tensor(idx, device=DEV)
+    out = torch.empty(M, 4 * C, device=DEV, dtype=torch.float16)
+    ops.gemm(a, w[idx].contiguous(), 8 * C, out=out, bias=bias[idx].contiguous(), act=1, block_n=bn)
+    u = a.float() @ w.float().t() + bias
+    want = u[:, :4 * C] * F.gelu(u[:, 4 * C:])
+    _close(out, want, 6e-3, 6e-3, "geglu")
+
+
+def test_gemm_segments_and_lora_k_extension():
+    """Row segments pick different weight slabs; source 2 = (x @ down^T) extends K with the LoRA up matrix."""
+    from edgestyle_b200 import ops
+
+    K, N, r = 320, 320, 32
+    rows = [0, 200, 456, 1000]  # three segments: no LoRA, LoRA A, LoRA B
+    M = rows[-1]
+    x = _rand(M, K, seed=11)
+    w = _rand(N, K, scale=K ** -0.5, seed=12)
+    downs = [_rand(r, K, scale=K ** -0.5, seed=13 + i) for i in range(2)]
+    ups = [_rand(N, r, scale=0.1, seed=15 + i) for i in range(2)]
+    # t = x @ down_g^T per segment (segment 0 unused)
+    dstack = torch.cat(downs, 0)  # [2r, K]
+    t = torch.zeros(M, 64, device=DEV, dtype=torch.float16)
+    ops.gemm(x, dstack, r, out=t, segs=(rows, [0, 0, r], None))
+    for s, d in ((1, downs[0]), (2, downs[1])):
+        want_t = x[rows[s]:rows[s + 1]].float() @ d.float().t()
+        _close(t[rows[s]:rows[s + 1], :r], want_t, 4e-3, 4e-3, "lora down")
+    ustack = torch.zeros(2 * N, 64, device=DEV, dtype=torch.float16)
+    ustack[:N, :r] = ups[0]
+    ustack[N:, :r] = ups[1]
+    out = torch.empty(M, N, device=DEV, dtype=torch.float16)
+    ops.gemm(x, w, N, out=out, a2=t, b2=ustack, segs=(rows, [0, 0, 0], [-1, 0, N]))
+    base = x.float() @ w.float().t()
+    want = base.clone()
+    for s in (1, 2):
+        sl = slice(rows[s], rows[s + 1])
+        want[sl] += t[sl, :r].float() @ ups[s - 1].float().t()
+    _close(out, want, 5e-3, 5e-3, "lora k-extension")
+
+
+@pytest.mark.parametrize("n_img,h,w,cin,cout", [(2, 64, 64, 320, 320), (3, 32, 32, 64, 128), (2, 16, 16, 640, 320),
+                                                (4, 8, 8, 128, 64), (1, 12, 16, 64, 64), (3, 4, 4, 32, 32),
+                                                (2, 2, 2, 32, 32), (1, 24, 128, 64, 32)])
+def test_conv3x3(n_img, h, w, cin, cout):
+    from edgestyle_b200 import ops
+
+    x = _rand(n_img, cin, h, w, dtype=torch.float32, seed=20)
+    wt = _rand(cout, cin, 3, 3, dtype=torch.float32, scale=(9 * cin) ** -0.5, seed=21)
+    bias = _rand(cout, dtype=torch.float32, seed=22)
+    rowvec = _rand(n_img, cout, dtype=torch.float32, seed=23)
+    x_nhwc = x.permute(0, 2, 3, 1).reshape(-1, cin).half().contiguous()
+    w_pack = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).half().contiguous()  # [cout][tap][cin]
+    out = torch.empty(n_img * h * w, cout, device=DEV, dtype=torch.float16)
+    ops.gemm(x_nhwc, w_pack, cout, out=out, taps=9, whn=(w, h, n_img), bias=bias, rowvec=rowvec, c1=cin)
+    want = F.conv2d(x_nhwc.float().view(n_img, h, w, cin).permute(0, 3, 1, 2), w_pack.float().view(cout, 3, 3, cin)
+                    .permute(0, 3, 1, 2), bias, padding=1) + rowvec[:, :, None, None]
+    want = want.permute(0, 2, 3, 1).reshape(-1, cout)
+    _close(out, want, 5e-3, 5e-3, "conv3x3")
+
+
+def test_conv3x3_with_fused_1x1_shortcut():
+    """ResnetBlock2D tail: conv2(3x3) + conv_shortcut(1x1 on the block input) in one accumulator."""
+    from edgestyle_b200 import ops
+
+    n_img, h, w, cin, cout, cx = 2, 16, 16, 128, 64, 192
+    g = _rand(n_img * h * w, cin, seed=24)
+    x = _rand(n_img * h * w, cx, seed=25)
+    w2 = _rand(cout, 9 * cin, scale=(9 * cin) ** -0.5, seed=26)
+    wsc = _rand(cout, cx, scale=cx ** -0.5, seed=27)
+    bias = _rand(cout, dtype=torch.float32, seed=28)
+    out = torch.empty(n_img * h * w, cout, device=DEV, dtype=torch.float16)
+    ops.gemm(g, w2, cout, out=out, taps=9, whn=(w, h, n_img), bias=bias, a2=x, b2=wsc)
+    conv = F.conv2d(g.float().view(n_img, h, w, cin).permute(0, 3, 1, 2),
+                    w2.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2), bias, padding=1)
+    want = conv.permute(0, 2, 3, 1).reshape(-1, cout) + x.float() @ wsc.float().t()
+    _close(out, want, 5e-3, 5e-3, "conv3x3 + shortcut")
+
+
+# ------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("batch,heads,d,nq,nkv", [(2, 8, 40, 4096, 4096), (2, 8, 80, 1024, 1024), (3, 8, 160, 256, 256),
+                                                  (2, 8, 160, 64, 64), (2, 8, 40, 4096, 77), (2, 8, 80, 1024, 77),
+                                                  (1, 8, 160, 64, 77), (2, 4, 8, 200, 300), (1, 2, 16, 130, 129),
+                                                  (1, 8, 32, 64, 16)])
+def test_attention(batch, heads, d, nq, nkv, dtype):
+    from edgestyle_b200 import ops
+
+    C = heads * d
+    q = _rand(batch * nq, C, dtype=dtype, seed=30)
+    k = _rand(batch * nkv, C, dtype=dtype, seed=31)
+    v = _rand(batch * nkv, C, dtype=dtype, seed=32)
+    out = torch.empty(batch * nq, C, device=DEV, dtype=dtype)
+    ops.attention(q, k, v, out, batch, heads, nq, nkv)
+    qf = q.float().view(batch, nq, heads, d).transpose(1, 2)
+    kf = k.float().view(batch, nkv, heads, d).transpose(1, 2)
+    vf = v.float().view(batch, nkv, heads, d).transpose(1, 2)
+    want = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(batch * nq, C)
+    tol = 2e-2 if dtype == torch.bfloat16 else 4e-3
+    _close(out, want, tol, tol, f"attention d={d} nq={nq} nkv={nkv}")
+
+
+def test_attention_fused_qkv_views():
+    """q, k, v as column slices of one [M, 3C] projection output (how the engine calls it)."""
+    from edgestyle_b200 import ops
+
+    batch, heads, d, n = 2, 8, 40, 1024
+    C = heads * d
+    qkv = _rand(batch * n, 3 * C, seed=33)
+    out = torch.empty(batch * n, C, device=DEV, dtype=torch.float16)
+    ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], out, batch, heads, n, n)
+    qf, kf, vf = [t.float().reshape(batch, n, heads, d).transpose(1, 2) for t in qkv.split(C, dim=1)]
+    want = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(batch * n, C)
+    _close(out, want, 4e-3, 4e-3, "attention qkv views")
+
+
+# ------------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("n_img,hw,c0,c1,silu", [(2, 4096, 320, 0, True), (3, 1024, 640, 320, True),
+                                                 (2, 64, 1280, 1280, True), (2, 256, 1280, 640, False),
+                                                 (4, 16, 32, 0, True), (2, 100, 64, 32, True)])
+def test_groupnorm(n_img, hw, c0, c1, silu):
+    from edgestyle_b200 import ops
+
+    x0 = _rand(n_img * hw, c0, seed=40) * 2 + 0.5
+    x1 = _rand(n_img * hw, c1, seed=41) if c1 else None
+    C = c0 + c1
+    gamma = _rand(C, dtype=torch.float32, seed=42) * 0.1 + 1
+    beta = _rand(C, dtype=torch.float32, seed=43) * 0.1
+    ws = torch.empty(n_img, 32, 2, device=DEV, dtype=torch.float32)
+    out = torch.empty(n_img * hw, C, device=DEV, dtype=torch.float16)
+    ops.groupnorm(x0, out, gamma, beta, ws, n_img, hw, 32, 1e-5, silu, x1=x1)
+    x = x0 if x1 is None else torch.cat([x0, x1], 1)
+    xn = x.float().view(n_img, hw, C).permute(0, 2, 1)
+    want = F.group_norm(xn, 32, gamma, beta, 1e-5)
+    if silu:
+        want = F.silu(want)
+    want = want.permute(0, 2, 1).reshape(-1, C)
+    _close(out, want, 4e-3, 4e-3, "groupnorm")
+
+
+@pytest.mark.parametrize("rows,c", [(8192, 320), (2048, 640), (512, 1280), (77, 32), (5, 2048)])
+def test_layernorm(rows, c):
+    from edgestyle_b200 import ops
+
+    x = _rand(rows, c, seed=44) * 3 + 1
+    gamma = _rand(c, dtype=torch.float32, seed=45) * 0.1 + 1
+    beta = _rand(c, dtype=torch.float32, seed=46) * 0.1
+    out = torch.empty_like(x)
+    ops.layernorm(x, out, gamma, beta)
+    want = F.layer_norm(x.float(), (c,), gamma, beta, 1e-5)
+    _close(out, want, 4e-3, 4e-3, "layernorm")
+
+
+# ------------------------------------------------------------------------------------------ merge
+def _pack_merge(blk, C, h, w, dtype):
+    """Host repack of a ControlNetBlock's parameters to the channels-last layout the kernel reads."""
+    from edgestyle_b200.engine import pack_merge_block
+
+    return pack_merge_block({k: v for k, v in blk.state_dict().items()}, C, h, w, dtype, DEV)
+
+
+@pytest.mark.parametrize("C,h,w,B", [(320, 64, 64, 2), (640, 16, 16, 2), (1280, 8, 8, 3), (32, 4, 4, 2)])
+def test_merge_vs_oracle(C, h, w, B):
+    from edgestyle_b200 import ops
+    from oracle.merge import ControlNetBlock, interleave_tensors
+
+    torch.manual_seed(C + h)
+    blk = ControlNetBlock(C, (h, w), 6)
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.add_(torch.randn_like(p) * 0.1)
+    blk = blk.to(DEV)
+    res = [_rand(B, C, h, w, dtype=torch.float32, seed=50 + i) for i in range(6)]
+    scale = [1.0, 0.5, 1.5, 1.0, 0.25, 2.0]
+    res16 = [r.permute(0, 2, 3, 1).reshape(-1, C).half().contiguous() for r in res]
+    skip = _rand(B * h * w, C, seed=60)
+    with torch.no_grad():
+        want = blk(interleave_tensors([r16.float().view(B, h, w, C).permute(0, 3, 1, 2) * s
+                                       for r16, s in zip(res16, scale)]))
+    want = want.permute(0, 2, 3, 1).reshape(-1, C) + skip.float()
+    prm = _pack_merge(blk, C, h, w, torch.float16)
+    stats = torch.empty(B, 4, device=DEV, dtype=torch.float64)
+    z = torch.empty(B * h * w, C, device=DEV, dtype=torch.float32)
+    dst = torch.empty(B * h * w, C, device=DEV, dtype=torch.float16)
+    ops.merge(res16, scale, prm, stats, z, B, h * w, C, dst, skip=skip)
+    _close(dst, want, 6e-3, 6e-3, "merge")
+
+
+def test_merge_golden_fixture():
+    """The committed outputs of the reference's own ControlNetBlock code (tests/golden/make_golden.py)."""
+    from edgestyle_b200 import ops
+    from edgestyle_b200.engine import pack_merge_block
+
+    cases = torch.load(os.path.join(os.path.dirname(__file__), "golden", "merge_block_golden.pt"))
+    for case in cases:
+        C, h, w, B = case["shape"]
+        prm = pack_merge_block(case["state_dict"], C, h, w, torch.float16, DEV)
+        res16 = [r.to(DEV).permute(0, 2, 3, 1).reshape(-1, C).half().contiguous() for r in case["residuals"]]
+        stats = torch.empty(B, 4, device=DEV, dtype=torch.float64)
+        z = torch.empty(B * h * w, C, device=DEV, dtype=torch.float32)
+        dst = torch.empty(B * h * w, C, device=DEV, dtype=torch.float16)
+        ops.merge(res16, [1.0] * 6, prm, stats, z, B, h * w, C, dst)
+        want = case["out"].to(DEV).permute(0, 2, 3, 1).reshape(-1, C)
+        _close(dst, want, 1e-2, 1e-2, "merge golden")
+
+
+# ------------------------------------------------------------------------------------------ misc
+def test_layout_im2col_upsample_add():
+    from edgestyle_b200 import ops
+
+    x = _rand(2, 4, 16, 16, dtype=torch.float32, seed=70)
+    nhwc = torch.empty(2 * 256, 8, device=DEV, dtype=torch.float16)
+    ops.nchw_to_nhwc(x, nhwc)
+    assert torch.equal(nhwc[:, :4], x.permute(0, 2, 3, 1).reshape(-1, 4).half())
+    assert nhwc[:, 4:].abs().max() == 0
+    back = torch.empty(2, 4, 16, 16, device=DEV, dtype=torch.float32)
+    ops.nhwc_to_nchw(nhwc, back)
+    assert torch.equal(back, x.half().float())
+    # im2col, scalar path (c = 4 padded to 64 columns)
+    col = torch.empty(2 * 256, 64, device=DEV, dtype=torch.float16)
+    ops.im2col3x3(nhwc, col, 2, 16, 16, 4, 1)
+    want = F.unfold(x.half().float(), 3, padding=1).view(2, 4, 9, 256).permute(0, 3, 2, 1).reshape(-1, 36)
+    assert torch.equal(col[:, :36].float(), want) and col[:, 36:].abs().max() == 0
+    # im2col, vector path stride 2
+    y = _rand(2, 64, 16, 16, dtype=torch.float32, seed=71)
+    y16 = y.permute(0, 2, 3, 1).reshape(-1, 64).half().contiguous()
+    col2 = torch.empty(2 * 64, 9 * 64, device=DEV, dtype=torch.float16)
+    ops.im2col3x3(y16, col2, 2, 16, 16, 64, 2)
+    want2 = F.unfold(y.half().float(), 3, padding=1, stride=2).view(2, 64, 9, 64).permute(0, 3, 2, 1).reshape(-1, 576)
+    assert torch.equal(col2.float(), want2)
+    up = torch.empty(2 * 1024, 64, device=DEV, dtype=torch.float16)
+    ops.upsample2x(y16, up, 2, 16, 16)
+    wantu = F.interpolate(y.half().float(), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1).reshape(-1, 64)
+    assert torch.equal(up.float(), wantu)
+    s = torch.empty_like(y16)
+    ops.add(y16, y16, s)
+    assert torch.equal(s, y16 + y16)
+
+
+def test_time_embedding_small_linear_cfg_ddim():
+    from edgestyle_b200 import ops
+    from oracle.schedulers import DDIMScheduler
+    from oracle.sd15 import timestep_sinusoid
+
+    t = torch.tensor([951.0, 951.0, 1.0, 501.0], device=DEV)
+    emb = torch.empty(4, 320, device=DEV)
+    ops.timestep_embedding(t, 320, emb)
+    _close(emb, timestep_sinusoid(t, 320), 2e-4, 0, "sinusoid")
+    w = _rand(1280, 320, scale=320 ** -0.5, seed=80)
+    b = _rand(1280, dtype=torch.float32, seed=81)
+    y = torch.empty(4, 1280, device=DEV)
+    ops.small_linear(emb, w, b, y, silu_out=True)
+    _close(y, F.silu(emb @ w.float().t() + b), 1e-3, 1e-3, "small_linear")
+    y2 = y.clone()
+    w2 = _rand(1280, 1280, scale=1280 ** -0.5, seed=82)
+    ops.small_linear(y, w2, None, y2, silu_in=True, accumulate=True)
+    _close(y2, y + F.silu(y) @ w2.float().t(), 2e-3, 2e-3, "small_linear acc")
+    # CFG + DDIM
+    sch = DDIMScheduler()
+    sch.set_timesteps(20)
+    eps = _rand(4, 4, 8, 8, dtype=torch.float32, seed=83)
+    lat = _rand(2, 4, 8, 8, dtype=torch.float32, seed=84)
+    g = torch.tensor([4.5, 7.5], device=DEV)
+    a_t, a_p = sch.coefficients(951)
+    coef = torch.tensor([a_t.sqrt(), (1 - a_t).sqrt(), a_p.sqrt(), (1 - a_p).sqrt()], device=DEV)
+    u, c = eps.chunk(2)
+    e = u + g.view(-1, 1, 1, 1) * (c - u)
+    want = sch.step(e.cpu(), 951, lat.cpu()).to(DEV)
+    got = lat.clone()
+    eo = torch.empty_like(lat)
+    ops.cfg_ddim(eps, got, g, coef, eo)
+    _close(eo, e, 1e-6, 1e-6, "cfg")
+    _close(got, want, 1e-4, 1e-5, "ddim")
