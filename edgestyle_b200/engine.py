@@ -268,7 +268,7 @@ class DenoiseEngine:
         self.use_graph = use_graph
         self._bufs: Dict[str, torch.Tensor] = {}
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
-        self.launches = 0
+        self.launches_per_step = 0
         for i, c in enumerate(cfg.block_out_channels):
             if c % 8 or c % cfg.norm_num_groups or (c // cfg.num_heads) % 8:
                 raise ValueError(f"channel count {c} unsupported (needs %8, %groups, head_dim %8)")
@@ -427,7 +427,6 @@ class DenoiseEngine:
     def _gn(self, x, out, g, b, imgs, hw, silu, eps=None):
         ops.groupnorm(x, out, g, b, self.gn_ws[:imgs], imgs, hw, self.cfg.norm_num_groups,
                       self.cfg.norm_eps if eps is None else eps, silu)
-        self.launches += 3
         return out
 
     def _lin(self, L: Lin, a, out, rows_per_img: int, lora_seg_imgs: Optional[Sequence[int]], tag: str, **ep):
@@ -439,10 +438,8 @@ class DenoiseEngine:
             ops.gemm(a[n0:], L.down, L.rp, out=t[n0:], segs=([0, n1, n1 + n2], [0, L.rp], None))
             ops.gemm(a, L.w, L.n, out=out, bias=L.bias, a2=t, b2=L.up, block_n=L.block_n,
                      segs=([0, n0, n0 + n1, n0 + n1 + n2], [0, 0, 0], [-1, 0, L.n]), **ep)
-            self.launches += 2
         else:
             ops.gemm(a, L.w, L.n, out=out, bias=L.bias, block_n=L.block_n, **ep)
-            self.launches += 1
         return out
 
     def _resnet(self, R: Res, x, imgs, H, W, temb, out, tag):
@@ -458,7 +455,6 @@ class DenoiseEngine:
             ops.gemm(g2, R.w2, R.cout, out=out, taps=9, whn=(W, H, imgs), bias=R.b2, a2=x, b2=R.wsc, c1=R.cout)
         else:
             ops.gemm(g2, R.w2, R.cout, out=out, taps=9, whn=(W, H, imgs), bias=R.b2, residual=x, c1=R.cout)
-        self.launches += 2
         return out
 
     def _transformer(self, T: Tfm, x, imgs, H, W, ctx, out, tag, seg):
@@ -491,7 +487,6 @@ class DenoiseEngine:
         self._lin(T.ff1, ln, u, hw, seg, tag + ".o", act=ACT_GEGLU)
         self._lin(T.ff2, u, hcur, hw, seg, tag + ".ff2", residual=hcur)
         self._lin(T.proj_out, hcur, out, hw, None, tag, residual=x)
-        self.launches += 5
         return out
 
     def _time_path(self, E: EncoderW, groups: Sequence[Tuple[int, int]], tag: str, ncols: Sequence[int]):
@@ -512,8 +507,6 @@ class DenoiseEngine:
             for rep in range(n // B):
                 ops.small_linear(e2, E.temb_w[gi][:nc], E.temb_b[gi][:nc], temb[r0:r0 + B, :nc], silu_in=True)
                 r0 += B
-                self.launches += 1
-            self.launches += 2
         return temb
 
     def _encoder(self, E: EncoderW, x, imgs, temb, ctx, seg, tag):
@@ -542,7 +535,6 @@ class DenoiseEngine:
                 ops.im2col3x3(x, col, imgs, H, W, c, 2)
                 out = self.buf(f"{tag}.skip{len(skips)}", imgs * Hn * Wn, c)
                 ops.gemm(col, E.down_conv[i][0], c, out=out, bias=E.down_conv[i][1])
-                self.launches += 2
                 x = out
                 skips.append(x)
         H, W = self.levels[-1]
@@ -557,7 +549,9 @@ class DenoiseEngine:
         return skips, mid
 
     # ------------------------------------------------------------------------------------ the step
-    def _run_step(self, cond_scale: Sequence[float]):
+    def _run_step(self, cond_scale: Sequence[float], mode: str = "step"):
+        """mode 'step': full fused step -> eps_out.  mode 'residuals': stop after the merge and leave the 13
+        merged residuals (what EdgeStyleMultiControlNetModel.forward returns) in self.res_out."""
         cfg, B = self.cfg, self.B
         h, w = self.h, self.w
         hw = h * w
@@ -570,7 +564,6 @@ class DenoiseEngine:
         col = self.buf("sample_col", B * hw, 64)
         ops.im2col3x3(s16, col, B, h, w, cfg.in_channels, 1)
         ops.timestep_embedding(self.t_in, c0, self.buf("t_sin", B, c0, torch.float32))
-        self.launches += 3
         Eb, Ep = self.enc_base, self.enc_pose
         enc_cols = Eb.temb_cols
         temb_base = self._time_path(Eb, [(0, B), (1, B), (2, 2 * B)], "base",
@@ -585,7 +578,6 @@ class DenoiseEngine:
         xp = self.buf("pose.x0", 3 * B * hw, c0)
         for slot, k in ((0, 1), (1, 3), (2, 5)):
             ops.gemm(col, Ep.conv_in, c0, out=xp[slot * B * hw:(slot + 1) * B * hw], bias=Ep.conv_in_b, residual=cond(k))
-        self.launches += 7
         # -- the two batched encoder passes
         skips_b, mid_b = self._encoder(Eb, xb, 4 * B, temb_base, self.ctx_base, (B, B, 2 * B), "base")
         skips_p, mid_p = self._encoder(Ep, xp, 3 * B, temb_pose, self.ctx_pose, None, "pose")
@@ -616,13 +608,18 @@ class DenoiseEngine:
             ops.gemm(all_p[li], self.zero_pose[li][0], c, out=rp, bias=self.zero_pose[li][1])
             res = [rb[:n], rp[:n], rb[n:2 * n], rp[n:2 * n], rb[2 * n:], rp[2 * n:]]
             z = self.buf(f"merge_z{li}", n, c, torch.float32)
+            if mode == "residuals":
+                dst = self.buf(f"res_out{li}", n, c)
+                ops.merge(res, scale, self.merge[li], self.merge_stats, z, B, H * W, c, dst, skip=None)
+                continue
             if li < len(self.res_shapes) - 1:
                 cbuf, xc = cat_of_skip[li]
                 dst = cbuf[:, xc:]
             else:  # mid: becomes the x half of the first decoder concat
                 dst = cats[(0, 0)][0][:, :c]
             ops.merge(res, scale, self.merge[li], self.merge_stats, z, B, H * W, c, dst, skip=all_b[li][:n])
-            self.launches += 6
+        if mode == "residuals":
+            return
         # -- UNet decoder
         for i in range(len(boc)):
             H, W = self.levels[len(boc) - 1 - i]
@@ -651,7 +648,6 @@ class DenoiseEngine:
                 ops.upsample2x(self.buf(f"dec{i}.out", M, cout), up, B, H, W)
                 ops.gemm(up, self.up_conv[i][0], cout, out=cats[(i + 1, 0)][0][:, :cout], taps=9, whn=(Wn, Hn, B),
                          bias=self.up_conv[i][1], c1=cout)
-                self.launches += 2
         # -- conv_norm_out + SiLU + conv_out
         fin = self.buf("dec.final", B * hw, c0)
         g = self.buf("dec.gn_out", B * hw, c0)
@@ -660,7 +656,6 @@ class DenoiseEngine:
         ops.gemm(g, self.conv_out[0], cfg.out_channels, out=o, taps=9, whn=(w, h, B), bias=self.conv_out[1], c1=c0,
                  block_n=32)
         self._nhwc32_to_nchw(o, self.eps_out)
-        self.launches += 2
 
     def _nhwc32_to_nchw(self, o, dst):
         # [B*hw, 16] fp32 (first out_channels valid) -> [B, c, h, w]; tiny (64 KB): a strided copy kernel of torch
@@ -672,27 +667,88 @@ class DenoiseEngine:
     def step(self, sample: torch.Tensor, timestep, cond_scale: Sequence[float] = (1.0,) * 6) -> torch.Tensor:
         """noise_pred = UNet(sample, t, ehs, residuals(6 ControlNets + merge)) -- the fused single-step form the
         reference defines at /root/reference/export_onnx.py:43-74.  Returns a view of the static output buffer."""
-        self.sample_in.copy_(sample.to(device=self.dev, dtype=torch.float32))
-        if not torch.is_tensor(timestep):
-            timestep = torch.tensor([float(timestep)])
-        t = timestep.to(device=self.dev, dtype=torch.float32).reshape(-1)
-        self.t_in.copy_(t.expand(self.B) if t.numel() == 1 else t)
+        self._load_sample_t(sample, timestep)
         key = tuple(float(s) for s in cond_scale)
         if not self.use_graph:
-            self.launches = 0
+            n0 = ops.LAUNCHES
             self._run_step(key)
+            self.launches_per_step = ops.LAUNCHES - n0
             return self.eps_out
         gph = self._graphs.get(key)
         if gph is None:
             self._run_step(key)  # eager warm-up: allocates every buffer, sets kernel attributes
             torch.cuda.synchronize()
             gph = torch.cuda.CUDAGraph()
-            self.launches = 0
+            n0 = ops.LAUNCHES
             with torch.cuda.graph(gph):
                 self._run_step(key)
+            self.launches_per_step = ops.LAUNCHES - n0
             self._graphs[key] = gph
         gph.replay()
         return self.eps_out
+
+    def _load_sample_t(self, sample, timestep):
+        self.sample_in.copy_(sample.to(device=self.dev, dtype=torch.float32))
+        if not torch.is_tensor(timestep):
+            timestep = torch.tensor([float(timestep)])
+        t = timestep.to(device=self.dev, dtype=torch.float32).reshape(-1)
+        self.t_in.copy_(t.expand(self.B) if t.numel() == 1 else t)
+
+    @torch.no_grad()
+    def residuals(self, sample, timestep, cond_scale: Sequence[float]) -> Tuple[List[torch.Tensor], torch.Tensor]:
+        """EdgeStyleMultiControlNetModel.forward (edgestyle_multicontrolnet.py:116-171): 12 merged down residuals +
+        mid as fresh NCHW fp32 tensors."""
+        self._load_sample_t(sample, timestep)
+        self._run_step(tuple(float(s) for s in cond_scale), mode="residuals")
+        outs = []
+        for li, (c, H, W) in enumerate(self.res_shapes):
+            dst = torch.empty(self.B, c, H, W, device=self.dev, dtype=torch.float32)
+            ops.nhwc_to_nchw(self.buf(f"res_out{li}", self.B * H * W, c), dst)
+            outs.append(dst)
+        return outs[:-1], outs[-1]
+
+    @torch.no_grad()
+    def single_controlnet(self, group: Optional[int], sample, timestep, prompt_embeds, cond, conditioning_scale: float,
+                          guess_mode: bool = False) -> Tuple[List[torch.Tensor], torch.Tensor]:
+        """CachedControlNetModel.forward (controllora.py:59-287) for ONE net: group 0/1 = ControlLoRA sets (UNet base
+        weights + that LoRA), None = the plain (openpose) ControlNet.  Returns NCHW fp32 residuals x scale."""
+        cfg, B, h, w = self.cfg, self.B, self.h, self.w
+        hw, c0, nt = h * w, cfg.block_out_channels[0], self.n_text
+        self._load_sample_t(sample, timestep)
+        s16 = self.buf("sample16", B * hw, 8)
+        ops.nchw_to_nhwc(self.sample_in, s16)
+        col = self.buf("sample_col", B * hw, 64)
+        ops.im2col3x3(s16, col, B, h, w, cfg.in_channels, 1)
+        ops.timestep_embedding(self.t_in, c0, self.buf("t_sin", B, c0, torch.float32))
+        E = self.enc_pose if group is None else self.enc_base
+        gi = 0 if group is None else group + 1
+        temb = self._time_path(E, [(gi, B)], "single", [E.temb_cols])
+        cond16 = self.buf("single.cond", B * hw, c0)
+        ops.nchw_to_nhwc(cond.to(device=self.dev, dtype=torch.float32).contiguous(), cond16)
+        x0 = self.buf("single.x0", B * hw, c0)
+        ops.gemm(col, E.conv_in, c0, out=x0, bias=E.conv_in_b, residual=cond16)
+        ctx = self.buf("single.ctx", B * nt, cfg.cross_attention_dim)
+        ctx.copy_(prompt_embeds.to(device=self.dev, dtype=self.dtype).reshape(B * nt, -1))
+        seg = None if group is None else ((0, B, 0) if group == 0 else (0, 0, B))
+        skips, mid = self._encoder(E, x0, B, temb, ctx, seg, "single")
+        n_res = len(self.res_shapes)
+        if guess_mode:  # controllora.py:257-265
+            scales = (torch.logspace(-1, 0, n_res) * conditioning_scale).tolist()
+        else:
+            scales = [conditioning_scale] * n_res
+        outs = []
+        for li, ((c, H, W), src) in enumerate(zip(self.res_shapes, skips + [mid])):
+            n = B * H * W
+            r = self.buf(f"single.z{li}", n, c)
+            if group is None:
+                ops.gemm(src, self.zero_pose[li][0], c, out=r, bias=self.zero_pose[li][1], alpha=scales[li])
+            else:
+                zw, zb = self.zero_base[li]
+                ops.gemm(src, zw, c, out=r, bias=zb, alpha=scales[li], segs=([0, n], [group * c], None))
+            dst = torch.empty(B, c, H, W, device=self.dev, dtype=torch.float32)
+            ops.nhwc_to_nchw(r, dst)
+            outs.append(dst)
+        return outs[:-1], outs[-1]
 
     @torch.no_grad()
     def cfg_ddim_update(self, latents: torch.Tensor, a_t: float, a_prev: float, guidance=None):

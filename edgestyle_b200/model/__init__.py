@@ -1,0 +1,5 @@
+"""Host-side mirrors of the reference's model/ package for the denoise hot path (same class names,
+forward signatures and state-dict semantics; arithmetic in edgestyle_b200.engine)."""
+from .controllora import CachedControlNetModel, ControlLoRAModel, ControlNetOutput, UNet2DConditionModel  # noqa: F401
+from .edgestyle_multicontrolnet import EdgeStyleMultiControlNetModel  # noqa: F401
+from .edgestyle_pipeline import EdgeStyleStableDiffusionControlNetPipeline, StableDiffusionPipelineOutput  # noqa: F401

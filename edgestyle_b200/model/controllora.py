@@ -1,0 +1,162 @@
+"""Host mirror of /root/reference/model/controllora.py for the denoise hot path.
+
+Same class names, `forward` signature (:59-75), `preprocess_image` (:289-290), `from_unet` (:644-725),
+`tie_weights` (:623-632), `state_dict` / `load_state_dict` filter semantics (:600-614) and `fuse_lora`
+(:728-737).  The classes are weight containers (diffusers-layout state dicts); the arithmetic
+runs in the CUDA engine that the owning EdgeStyleMultiControlNetModel builds.  There is no CPU path.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import Any, Dict, List, Mapping, Optional, Tuple, Union
+
+import torch
+
+from .. import config as C
+
+_SKIP_LAYERS = ["conv_in", "time_proj", "time_embedding", "class_embedding", "down_blocks", "mid_block"]
+
+
+@dataclass
+class ControlNetOutput:
+    down_block_res_samples: Tuple[torch.Tensor, ...]
+    mid_block_res_sample: torch.Tensor
+
+
+def _check_spec(sd: Mapping[str, torch.Tensor], spec: Dict[str, Tuple[int, ...]], what: str, allow_extra=()):
+    missing = [k for k in spec if k not in sd]
+    if missing:
+        raise KeyError(f"{what}: missing {len(missing)} keys, e.g. {missing[:3]}")
+    for k, shape in spec.items():
+        if tuple(sd[k].shape) != tuple(shape):
+            raise ValueError(f"{what}: {k} has shape {tuple(sd[k].shape)}, expected {shape}")
+    extra = [k for k in sd if k not in spec and not any(k.startswith(p) for p in allow_extra)]
+    if extra:
+        raise KeyError(f"{what}: unexpected keys, e.g. {extra[:3]}")
+
+
+class UNet2DConditionModel:
+    """Weight container for the SD1.5 UNet (diffusers key names)."""
+
+    def __init__(self, config: C.UNetConfig, state_dict: Mapping[str, torch.Tensor]):
+        self.config = C.UNetConfig.from_any(config)
+        _check_spec(state_dict, C.unet_spec(self.config), "UNet2DConditionModel")
+        self._sd = OrderedDict(state_dict)
+
+    def state_dict(self):
+        return self._sd
+
+
+class CachedControlNetModel:
+    """ControlNet whose conditioning embedder is skipped when `controlnet_cond` is already latent-sized
+    (controllora.py:199-201) -- the only mode the hot path uses (conds are cached by the pipeline)."""
+
+    uses_lora = False
+
+    def __init__(self, config: C.UNetConfig, state_dict: Mapping[str, torch.Tensor]):
+        self.config = C.UNetConfig.from_any(config)
+        spec = dict(C.encoder_spec(self.config))
+        spec.update(C.controlnet_extra_spec(self.config, with_embedder=False))
+        _check_spec(state_dict, spec, type(self).__name__, allow_extra=("controlnet_cond_embedding.",))
+        self._sd = OrderedDict(state_dict)
+        self._owner = None  # set by EdgeStyleMultiControlNetModel
+        self._slots: List[int] = []
+        self.controlnet_conditioning_channel_order = "rgb"
+
+    def state_dict(self):
+        return self._sd
+
+    # -- reference surface -------------------------------------------------------------------
+    def forward(self, sample, timestep, encoder_hidden_states, controlnet_cond, conditioning_scale: float = 1.0,
+                class_labels=None, timestep_cond=None, attention_mask=None, added_cond_kwargs=None,
+                cross_attention_kwargs=None, guess_mode: bool = False, return_dict: bool = True
+                ) -> Union[ControlNetOutput, Tuple]:
+        if self.controlnet_conditioning_channel_order not in ("rgb", "bgr"):  # controllora.py:115-126
+            raise ValueError(f"unknown `controlnet_conditioning_channel_order`: {self.controlnet_conditioning_channel_order}")
+        for name, val in (("class_labels", class_labels), ("timestep_cond", timestep_cond),
+                          ("attention_mask", attention_mask), ("added_cond_kwargs", added_cond_kwargs)):
+            if val is not None:
+                raise NotImplementedError(f"{name} is not used by SD1.5 and not implemented")
+        if cross_attention_kwargs and cross_attention_kwargs.get("scale", 1.0) != 1.0:
+            raise NotImplementedError('cross_attention_kwargs["scale"] != 1')
+        if self._owner is None:
+            raise RuntimeError("register this net in an EdgeStyleMultiControlNetModel before calling forward "
+                               "(the CUDA engine is built per multi-ControlNet model)")
+        if tuple(controlnet_cond.shape[2:]) != tuple(sample.shape[2:]):
+            raise NotImplementedError("raw-image conditioning (the embedder runs every step, controllora.py:199-201) "
+                                      "is row N4 of SURVEY.md 8(f); pass the cached embedding from preprocess_image")
+        down, mid = self._owner._single_forward(self, sample, timestep, encoder_hidden_states, controlnet_cond,
+                                                float(conditioning_scale), guess_mode)
+        if not return_dict:
+            return down, mid
+        return ControlNetOutput(tuple(down), mid)
+
+    __call__ = forward
+
+    def preprocess_image(self, image):
+        raise NotImplementedError("the per-call precompute stage (VAE / openpose embedder) is row N2 of SURVEY.md 8(f)")
+
+
+class ControlLoRAModel(CachedControlNetModel):
+    """ControlNet whose conv_in / time_embedding / down_blocks / mid_block ARE the UNet's parameters
+    (tie_weights) plus a rank-r LoRA on every Linear under `_skip_layers` (controllora.py:443-450,529-593).
+
+    `state_dict()` holds only LoRA tensors and the non-tied tensors (zero-convs), exactly like :600-606."""
+
+    _skip_layers = _SKIP_LAYERS
+    uses_lora = True
+
+    def __init__(self, config: C.UNetConfig, state_dict: Mapping[str, torch.Tensor], lora_linear_rank: int = 4,
+                 lora_conv2d_rank: int = 0, unet: Optional[UNet2DConditionModel] = None):
+        self.config = C.UNetConfig.from_any(config)
+        if lora_conv2d_rank > 0:
+            raise NotImplementedError("lora_conv2d_rank > 0 (conv LoRA, controllora.py:561-575) is not implemented")
+        self.lora_linear_rank, self.lora_conv2d_rank = lora_linear_rank, lora_conv2d_rank
+        spec = dict(C.lora_spec(self.config, lora_linear_rank))
+        spec.update(C.controlnet_extra_spec(self.config, with_embedder=False))
+        filtered = OrderedDict((k, v) for k, v in state_dict.items()
+                               if k.split(".")[0] not in self._skip_layers or ".lora_layer." in k)
+        _check_spec(filtered, spec, "ControlLoRAModel", allow_extra=("controlnet_cond_embedding.",))
+        self._sd = filtered
+        self._unet = unet
+        self._owner = None
+        self._slots = []
+        self.controlnet_conditioning_channel_order = "rgb"
+
+    @classmethod
+    def from_unet(cls, unet: UNet2DConditionModel, conditioning_channels: int = 3,
+                  controlnet_conditioning_channel_order: str = "rgb",
+                  conditioning_embedding_out_channels=(16, 32, 96, 256), lora_linear_rank: int = 4,
+                  lora_conv2d_rank: int = 0, autoencoder=None, generator: Optional[torch.Generator] = None):
+        """Fresh LoRA (down ~ N(0, 1/r^2), up = 0) and zero zero-convs, tied to `unet` (controllora.py:644-725)."""
+        cfg = unet.config
+        sd = OrderedDict()
+        for k, shape in C.lora_spec(cfg, lora_linear_rank).items():
+            if k.endswith("down.weight"):
+                sd[k] = torch.randn(shape, generator=generator) / lora_linear_rank
+            else:
+                sd[k] = torch.zeros(shape)
+        for k, shape in C.controlnet_extra_spec(cfg, with_embedder=False).items():
+            sd[k] = torch.zeros(shape)
+        net = cls(cfg, sd, lora_linear_rank, lora_conv2d_rank, unet)
+        net.controlnet_conditioning_channel_order = controlnet_conditioning_channel_order
+        return net
+
+    def tie_weights(self, unet: UNet2DConditionModel):
+        self._unet = unet
+
+    def set_autoencoder(self, autoencoder):
+        self.autoencoder = autoencoder
+
+    def load_state_dict(self, state_dict: Mapping[str, Any], strict: bool = True):
+        for k, v in state_dict.items():
+            if k in self._sd:
+                self._sd[k] = v
+            elif strict and (k.split(".")[0] not in self._skip_layers) and not k.startswith("controlnet_cond_embedding."):
+                raise KeyError(k)
+
+    def fuse_lora(self, lora_scale: float = 1.0, safe_fusing: bool = False):
+        raise NotImplementedError(
+            "fusing would un-tie the base weights from the UNet and forfeit the batched base pass; the engine "
+            "applies the LoRA update inside the GEMM instead (es_gemm source 2)")

@@ -1,0 +1,108 @@
+"""Host mirror of /root/reference/model/edgestyle_multicontrolnet.py: EdgeStyleMultiControlNetModel.
+
+Same constructor shape (`controlnets` list -> `.nets`), same `forward` signature and return convention
+(:116-171: always a `(down_block_res_samples, mid_block_res_sample)` tuple, `return_dict` ignored), merge-block
+state dict under `multi_controlnet_down_blocks.* / multi_controlnet_mid_block.*` (:173-193).  The six
+sequential ControlNet calls + interleave + 13 ControlNetBlocks of the reference become two batched encoder
+passes + a fused merge kernel in `edgestyle_b200.engine.DenoiseEngine`.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Any, Dict, List, Mapping, Optional, Sequence, Tuple
+
+import torch
+
+from .. import config as C
+from ..engine import SUPPORTED_PATTERN, DenoiseEngine
+from .controllora import CachedControlNetModel, ControlLoRAModel, UNet2DConditionModel, _check_spec
+
+
+class EdgeStyleMultiControlNetModel:
+    def __init__(self, controlnets: Sequence[CachedControlNetModel], merge_state_dict: Optional[Mapping] = None,
+                 latent_hw: Tuple[int, int] = (64, 64), dtype=torch.float16, n_text: int = 77):
+        self.nets: List[CachedControlNetModel] = list(controlnets)
+        if len(self.nets) != 6:
+            raise NotImplementedError("EdgeStyle uses exactly six control branches (app.py:86-94)")
+        a, p0, c0, p1, c1, p2 = self.nets
+        ok = (isinstance(a, ControlLoRAModel) and isinstance(c0, ControlLoRAModel) and c0 is c1 and a is not c0
+              and p0 is p1 is p2 and not isinstance(p0, ControlLoRAModel))
+        if not ok:
+            raise NotImplementedError(
+                f"only the reference's net pattern {SUPPORTED_PATTERN} = [loraA, pose, loraB, pose, loraB, pose] with "
+                "shared module objects (app.py:40,86-94) is supported")
+        self.config = a.config
+        self.latent_hw = tuple(latent_hw)
+        self.dtype, self.n_text = dtype, n_text
+        spec = C.merge_spec(self.config, *self.latent_hw)
+        if merge_state_dict is None:  # nn.Conv2d / nn.LayerNorm default init, as the reference's constructor
+            g = torch.Generator().manual_seed(0)
+            merge_state_dict = OrderedDict()
+            for k, shape in spec.items():
+                if "normalization" in k:
+                    merge_state_dict[k] = torch.ones(shape) if k.endswith("weight") else torch.zeros(shape)
+                else:
+                    fan_in = 2 if "first_conv" in k else (3 if "second_conv" in k else 1)
+                    merge_state_dict[k] = (torch.rand(shape, generator=g) * 2 - 1) / fan_in ** 0.5
+        _check_spec(merge_state_dict, spec, "EdgeStyleMultiControlNetModel")
+        self._merge_sd = OrderedDict(merge_state_dict)
+        for slot, net in enumerate(self.nets):
+            net._owner = self
+            if slot not in net._slots:
+                net._slots.append(slot)
+        self._engines: Dict[tuple, DenoiseEngine] = {}
+
+    # ---------------------------------------------------------------------------------------
+    def state_dict(self):
+        return self._merge_sd
+
+    def unet(self) -> UNet2DConditionModel:
+        u = self.nets[0]._unet
+        if u is None or self.nets[2]._unet is not u:
+            raise RuntimeError("call net.tie_weights(unet) on both ControlLoRA nets first (app.py:95-97)")
+        return u
+
+    def engine(self, rows: int, h: int, w: int, use_graph: bool = False) -> DenoiseEngine:
+        if (h, w) != self.latent_hw:
+            raise ValueError(f"merge blocks were built for latent {self.latent_hw}, got {(h, w)} "
+                             "(LayerNorm([C,H,W]) ties the model to one resolution, SURVEY.md F7)")
+        key = (rows, h, w, use_graph)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = DenoiseEngine(self.config, self.unet().state_dict(),
+                                [self.nets[0].state_dict(), self.nets[2].state_dict()], self.nets[1].state_dict(),
+                                self._merge_sd, rows=rows, h=h, w=w, dtype=self.dtype, n_text=self.n_text,
+                                use_graph=use_graph)
+            self._engines[key] = eng
+        return eng
+
+    # -- reference surface ----------------------------------------------------------------------
+    def forward(self, sample, timestep, encoder_hidden_states, controlnet_cond: List[torch.Tensor],
+                conditioning_scale: List[float], class_labels=None, timestep_cond=None, attention_mask=None,
+                added_cond_kwargs=None, cross_attention_kwargs=None, guess_mode: bool = False,
+                return_dict: bool = True):
+        for name, val in (("class_labels", class_labels), ("timestep_cond", timestep_cond),
+                          ("attention_mask", attention_mask), ("added_cond_kwargs", added_cond_kwargs)):
+            if val is not None:
+                raise NotImplementedError(f"{name} is not used by SD1.5 and not implemented")
+        if guess_mode:
+            raise NotImplementedError("guess_mode through the batched path (row N4 of SURVEY.md 8(f))")
+        if len(controlnet_cond) != 6 or len(conditioning_scale) != 6:
+            raise ValueError("expected six conditioning tensors and six scales")
+        B, _, h, w = sample.shape
+        eng = self.engine(B, h, w)
+        eng.set_prompt(encoder_hidden_states)
+        eng.set_conditioning(controlnet_cond)
+        down, mid = eng.residuals(sample, timestep, conditioning_scale)
+        return down, mid
+
+    __call__ = forward
+
+    def _single_forward(self, net, sample, timestep, ehs, cond, scale, guess_mode):
+        B, _, h, w = sample.shape
+        eng = self.engine(B, h, w)
+        group = None if not net.uses_lora else (0 if net is self.nets[0] else 1)
+        return eng.single_controlnet(group, sample, timestep, ehs, cond, scale, guess_mode)
+
+    def fuse(self):
+        raise NotImplementedError("see ControlLoRAModel.fuse_lora: LoRA is applied inside the GEMM")

@@ -1,0 +1,149 @@
+"""Host mirror of /root/reference/model/edgestyle_pipeline.py: EdgeStyleStableDiffusionControlNetPipeline.
+
+`__call__` keeps the reference's keyword surface (:92-120).  The hot-path subset is implemented
+(`prompt_embeds` / `negative_prompt_embeds` / `latents` / cached conditioning embeddings / `guidance_scale`
+/ `num_inference_steps` / `controlnet_conditioning_scale` / `control_guidance_start|end` / `generator` /
+`output_type="latent"` / `callback_on_step_end`); everything outside the denoise loop (CLIP text encoding, VAE,
+PIL post-processing -- SURVEY.md 8(f) rows N2) raises NotImplementedError instead of being silently ignored.
+
+Per step (reference loop body :434-543): CFG duplicate -> 6 ControlNets + merge -> UNet -> CFG combine ->
+scheduler.step.  Here: one captured CUDA graph (DenoiseEngine.step) + one es_cfg_ddim launch.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Callable, Dict, List, Optional, Sequence, Union
+
+import torch
+
+from ..schedulers import DDIMScheduler
+from .controllora import UNet2DConditionModel
+from .edgestyle_multicontrolnet import EdgeStyleMultiControlNetModel
+
+
+@dataclass
+class StableDiffusionPipelineOutput:
+    images: Any
+    nsfw_content_detected: Optional[List[bool]]
+
+
+class EdgeStyleStableDiffusionControlNetPipeline:
+    def __init__(self, vae=None, text_encoder=None, tokenizer=None, unet: UNet2DConditionModel = None,
+                 controlnet: EdgeStyleMultiControlNetModel = None, scheduler=None, safety_checker=None,
+                 feature_extractor=None, image_encoder=None, requires_safety_checker: bool = True,
+                 use_graph: bool = True):
+        if unet is None or controlnet is None:
+            raise ValueError("unet and controlnet are required")
+        if controlnet.unet() is not unet:
+            raise ValueError("the ControlLoRA nets must be tied to this pipeline's unet (app.py:95-97)")
+        self.vae, self.text_encoder, self.tokenizer = vae, text_encoder, tokenizer
+        self.unet, self.controlnet = unet, controlnet
+        self.scheduler = scheduler or DDIMScheduler()
+        self.use_graph = use_graph
+        self._guidance_scale = 7.5
+        self.h2d_bytes = 0  # bytes copied host->device / device->host by the last __call__ (bench.py e2e accounting)
+        self.d2h_bytes = 0
+
+    @property
+    def guidance_scale(self):
+        return self._guidance_scale
+
+    @property
+    def do_classifier_free_guidance(self):
+        g = self._guidance_scale
+        return bool((g > 1).all()) if torch.is_tensor(g) else g > 1
+
+    def _to_dev(self, t: torch.Tensor, dev) -> torch.Tensor:
+        if t.device.type != "cuda":
+            self.h2d_bytes += t.numel() * t.element_size()
+            return t.to(dev, non_blocking=True)
+        return t
+
+    @torch.no_grad()
+    def __call__(self, prompt=None, image=None, height=None, width=None, num_inference_steps: int = 50,
+                 timesteps=None, guidance_scale=7.5, negative_prompt=None, num_images_per_prompt: int = 1,
+                 eta: float = 0.0, generator=None, latents=None, prompt_embeds=None, negative_prompt_embeds=None,
+                 ip_adapter_image=None, output_type: str = "pil", return_dict: bool = True,
+                 cross_attention_kwargs=None, controlnet_conditioning_scale: Union[float, List[float]] = 1.0,
+                 guess_mode: bool = False, control_guidance_start: Union[float, List[float]] = 0.0,
+                 control_guidance_end: Union[float, List[float]] = 1.0, clip_skip=None,
+                 callback_on_step_end: Optional[Callable] = None,
+                 callback_on_step_end_tensor_inputs: List[str] = ["latents"], **kwargs):
+        # ---- arguments outside the hot path: explicit errors, never silently ignored ----
+        if prompt is not None or negative_prompt is not None:
+            raise NotImplementedError("text encoding is outside the hot path: pass prompt_embeds / negative_prompt_embeds")
+        if prompt_embeds is None:
+            raise ValueError("prompt_embeds is required")
+        if output_type != "latent":
+            raise NotImplementedError('VAE decode / PIL output is outside the hot path: use output_type="latent"')
+        for name, val in (("ip_adapter_image", ip_adapter_image), ("clip_skip", clip_skip), ("timesteps", timesteps)):
+            if val is not None:
+                raise NotImplementedError(f"{name} is not implemented")
+        if guess_mode:
+            raise NotImplementedError("guess_mode is not implemented")
+        if eta != 0.0:
+            raise NotImplementedError("eta != 0 (stochastic DDIM) is not implemented")
+        if cross_attention_kwargs and cross_attention_kwargs.get("scale", 1.0) != 1.0:
+            raise NotImplementedError('cross_attention_kwargs["scale"] != 1')
+        if num_images_per_prompt != 1:
+            raise NotImplementedError("num_images_per_prompt != 1: batch the prompt_embeds instead")
+        if not isinstance(image, (list, tuple)) or len(image) != 6:
+            raise ValueError("`image` must be the list of six conditioning tensors")
+        self.h2d_bytes = self.d2h_bytes = 0
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._guidance_scale = guidance_scale
+        cfg_on = self.do_classifier_free_guidance
+        if not cfg_on:
+            raise NotImplementedError("guidance_scale <= 1 (no CFG) is not implemented")
+        n_img = prompt_embeds.shape[0]
+        if negative_prompt_embeds is None:
+            raise ValueError("negative_prompt_embeds is required when guidance_scale > 1")
+        B = 2 * n_img
+        nets = 6
+        # align control guidance (edgestyle_pipeline.py:264-283)
+        if not isinstance(control_guidance_start, list):
+            control_guidance_start = [control_guidance_start] * nets
+        if not isinstance(control_guidance_end, list):
+            control_guidance_end = [control_guidance_end] * nets
+        if isinstance(controlnet_conditioning_scale, (int, float)):
+            controlnet_conditioning_scale = [float(controlnet_conditioning_scale)] * nets
+        # ---- inputs -> device ----
+        pe = torch.cat([self._to_dev(negative_prompt_embeds, dev), self._to_dev(prompt_embeds, dev)])  # :330
+        conds = []
+        for c in image:
+            c = self._to_dev(c, dev)
+            if c.shape[0] == n_img:  # CFG duplication of the cached embedding (:657-658)
+                c = torch.cat([c] * 2)
+            conds.append(c)
+        h, w = conds[0].shape[-2:]
+        if tuple(conds[0].shape[1:]) != (self.unet.config.block_out_channels[0], h, w):
+            raise NotImplementedError("raw control images need the per-call precompute stage (SURVEY.md 8(f) N2): pass the "
+                                      "cached conditioning embeddings [B, 320, h, w]")
+        eng = self.controlnet.engine(B, h, w, use_graph=self.use_graph)
+        eng.set_prompt(pe)
+        eng.set_conditioning(conds)
+        sch = self.scheduler
+        ts = sch.set_timesteps(num_inference_steps)
+        if latents is None:
+            latents = torch.randn((n_img, self.unet.config.in_channels, h, w), generator=generator,
+                                  device=generator.device if generator is not None else "cpu")
+        latents = self._to_dev(latents, dev).to(torch.float32).clone() * sch.init_noise_sigma
+        g = guidance_scale if torch.is_tensor(guidance_scale) else torch.full((n_img,), float(guidance_scale))
+        eng.guidance.copy_(self._to_dev(g.to(torch.float32), dev).reshape(-1).expand(n_img))
+        self.h2d_bytes += 0 if torch.is_tensor(guidance_scale) else 4 * n_img
+        n_t = len(ts)
+        for i, t in enumerate(ts):
+            keeps = [1.0 - float(i / n_t < s or (i + 1) / n_t > e)
+                     for s, e in zip(control_guidance_start, control_guidance_end)]  # :418-427
+            cond_scale = [c * k for c, k in zip(controlnet_conditioning_scale, keeps)]
+            x = sch.scale_model_input(torch.cat([latents] * 2), t)  # :443-450
+            eng.step(x, float(t), cond_scale)
+            a_t, a_prev = sch.coefficients(int(t))
+            eng.cfg_ddim_update(latents, a_t, a_prev)
+            self.h2d_bytes += 4 + 16  # timestep + 4 scheduler coefficients
+            if callback_on_step_end is not None:
+                out = callback_on_step_end(self, i, t, {k: locals()[k] for k in callback_on_step_end_tensor_inputs})
+                latents = out.pop("latents", latents) if out else latents
+        if not return_dict:
+            return (latents, None)
+        return StableDiffusionPipelineOutput(images=latents, nsfw_content_detected=None)

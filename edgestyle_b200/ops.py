@@ -14,6 +14,14 @@ from . import ext
 from .ext import ACT_GEGLU, ACT_NONE, EsAttention, EsGemm, EsGroupNorm, EsMerge, check, load
 
 
+LAUNCHES = 0  # native kernel launches issued through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n: int = 1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def _dt(t: torch.Tensor) -> int:
     if t.dtype == torch.float16:
         return ext.DTYPE_F16
@@ -85,6 +93,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: i
     g.ldc = out.stride(0)
     g.out_fp32 = 1 if out.dtype == torch.float32 else 0
     g.block_n = block_n
+    _count()
     check(load().es_gemm(C.byref(g), _stream()), "es_gemm")
     return out
 
@@ -100,6 +109,7 @@ def attention(q, k, v, out, batch: int, heads: int, nq: int, nkv: int, scale: Op
     a.bsq, a.bsk, a.bsv, a.bso = nq * q.stride(0), nkv * k.stride(0), nkv * v.stride(0), nq * out.stride(0)
     a.batch, a.heads, a.d, a.nq, a.nkv = batch, heads, d, nq, nkv
     a.scale = scale if scale is not None else d ** -0.5
+    _count()
     check(load().es_attention(C.byref(a), _stream()), "es_attention")
     return out
 
@@ -119,6 +129,7 @@ def groupnorm(x0, out, gamma, beta, ws, n_img: int, hw: int, groups: int, eps: f
     g.silu = 1 if silu else 0
     ws.zero_()
     lib = load()
+    _count(2)  # stats + apply (the workspace memset is torch's)
     check(lib.es_groupnorm_stats(C.byref(g), _stream()), "es_groupnorm_stats")
     check(lib.es_groupnorm_apply(C.byref(g), _stream()), "es_groupnorm_apply")
     return out
@@ -126,6 +137,7 @@ def groupnorm(x0, out, gamma, beta, ws, n_img: int, hw: int, groups: int, eps: f
 
 def layernorm(x, out, gamma, beta, eps: float = 1e-5):
     _need_cuda(x, out)
+    _count()
     check(load().es_layernorm(_dt(x), x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), gamma.data_ptr(),
                               beta.data_ptr(), x.shape[0], x.shape[1], eps, _stream()), "es_layernorm")
     return out
@@ -148,12 +160,14 @@ def merge(res: Sequence[torch.Tensor], scale: Sequence[float], prm: dict, stats,
     m.dst, m.ldd = dst.data_ptr(), dst.stride(0)
     stats.zero_()
     lib = load()
+    _count(3)  # three phases (the stats memset is torch's)
     for ph in (1, 2, 3):
         check(lib.es_merge_phase(C.byref(m), ph, _stream()), f"es_merge_phase({ph})")
     return dst
 
 
 def timestep_embedding(t: torch.Tensor, dim: int, out: torch.Tensor):
+    _count()
     check(load().es_timestep_embedding(t.data_ptr(), t.shape[0], dim, out.data_ptr(), _stream()),
           "es_timestep_embedding")
     return out
@@ -164,6 +178,7 @@ def small_linear(x, w, bias, y, *, silu_in=False, silu_out=False, accumulate=Fal
     rows, k = x.shape
     n = w.shape[0]
     assert w.shape[1] == k and w.is_contiguous()
+    _count()
     check(load().es_small_linear(_dt(w), x.data_ptr(), x.stride(0), w.data_ptr(), _p(bias), y.data_ptr(), y.stride(0),
                                  rows, n, k, int(silu_in), int(silu_out), int(accumulate), _stream()),
           "es_small_linear")
@@ -174,6 +189,7 @@ def nchw_to_nhwc(src: torch.Tensor, dst: torch.Tensor):
     """src fp32 [n, c, h, w] contiguous -> dst [n*h*w, ld] (channels zero-padded to ld)."""
     n, c, h, w = src.shape
     assert src.dtype == torch.float32 and src.is_contiguous()
+    _count()
     check(load().es_nchw_to_nhwc(_dt(dst), src.data_ptr(), dst.data_ptr(), n, c, h * w, dst.stride(0), _stream()),
           "es_nchw_to_nhwc")
     return dst
@@ -182,12 +198,14 @@ def nchw_to_nhwc(src: torch.Tensor, dst: torch.Tensor):
 def nhwc_to_nchw(src: torch.Tensor, dst: torch.Tensor):
     n, c, h, w = dst.shape
     assert dst.dtype == torch.float32 and dst.is_contiguous()
+    _count()
     check(load().es_nhwc_to_nchw(_dt(src), src.data_ptr(), src.stride(0), dst.data_ptr(), n, c, h * w, _stream()),
           "es_nhwc_to_nchw")
     return dst
 
 
 def im2col3x3(src, dst, n: int, h: int, w: int, c: int, stride: int):
+    _count()
     check(load().es_im2col3x3(_dt(src), src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), n, h, w, c,
                               stride, _stream()), "es_im2col3x3")
     return dst
@@ -195,12 +213,14 @@ def im2col3x3(src, dst, n: int, h: int, w: int, c: int, stride: int):
 
 def upsample2x(src, dst, n: int, h: int, w: int):
     c = src.shape[1]
+    _count()
     check(load().es_upsample2x(_dt(src), src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), n, h, w, c,
                                _stream()), "es_upsample2x")
     return dst
 
 
 def add(a, b, out):
+    _count()
     check(load().es_add(_dt(a), a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0),
                         a.shape[0], a.shape[1], _stream()), "es_add")
     return out
@@ -209,6 +229,7 @@ def add(a, b, out):
 def cfg_ddim(eps, latents, guidance, coef, eps_out=None):
     imgs = latents.shape[0]
     chw = latents[0].numel()
+    _count()
     check(load().es_cfg_ddim(eps.data_ptr(), latents.data_ptr(), guidance.data_ptr(), coef.data_ptr(), _p(eps_out),
                              imgs, chw, _stream()), "es_cfg_ddim")
     return latents
