@@ -44,6 +44,9 @@ struct GemmKParams {
   long long ldc;
   int out_fp32;
   int stages;
+  int splits;            // split-K factor (grid.z)
+  float* ws_partial;     // [splits][tiles][128][BLOCK_N] fp32 partial accumulators
+  int* ws_counter;       // [tiles] arrival counters (zero on entry, reset by the finishing CTA)
 };
 
 template <typename T, int BLOCK_N>
@@ -64,6 +67,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ int splitk_last;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -97,6 +101,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   const int kb1 = p.taps * p.kblocks1;
   const int kb_total = kb1 + ((p.kblocks2 > 0 && b2_noff >= 0) ? p.kblocks2 : 0);
+  // split-K: this CTA owns k-blocks [kb_begin, kb_end)
+  const int kb_per = (kb_total + p.splits - 1) / p.splits;
+  const int kb_begin = blockIdx.z * kb_per;
+  const int kb_end = min(kb_total, kb_begin + kb_per);
+  const bool has_work = kb_end > kb_begin;
 
   // ---- one-time setup ----------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
@@ -125,9 +134,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0) {
     // =============================== TMA producer ===========================================
     if (lane == 0) {
-      for (int kb = 0; kb < kb_total; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (kb / stages) & 1;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int it = kb - kb_begin;
+        const int s = it % stages;
+        const uint32_t ph = (it / stages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sa = smem + s * kStageBytes;
         uint8_t* sb = sa + kABytes;
@@ -153,9 +163,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // =============================== MMA issuer =============================================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N, Cvt<T>::kFmt, 0, 0);
-      for (int kb = 0; kb < kb_total; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (kb / stages) & 1;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int it = kb - kb_begin;
+        const int s = it % stages;
+        const uint32_t ph = (it / stages) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * kStageBytes);
@@ -165,11 +176,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
           // advancing 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in the >>4 address field
-          umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
         }
         umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
       }
-      umma_commit(&accum_bar);  // accumulator complete
+      if (has_work) umma_commit(&accum_bar);  // accumulator complete
+      else mbar_arrive(&accum_bar);
     }
   } else {
     // =============================== epilogue ===============================================
@@ -195,112 +207,157 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_after();
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 
-    if (p.act == ES_ACT_GEGLU) {
-      constexpr int HALF = BLOCK_N / 2;
-      const int oc0 = blockIdx.y * HALF;  // output column base
-      const int n_out = p.N / 2;
-#pragma unroll 1
-      for (int c = 0; c < HALF; c += 16) {
-        uint32_t va[16], vg[16];
-        tmem_ld_x16(t_row + c, va);
-        tmem_ld_x16(t_row + HALF + c, vg);
-        tmem_ld_wait();
-        if (row_ok) {
-          float o[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float a = __uint_as_float(va[j]);
-            float g = __uint_as_float(vg[j]);
-            if (p.bias) {
-              a += p.bias[b_noff + n0 + c + j];
-              g += p.bias[b_noff + n0 + HALF + c + j];
-            }
-            o[j] = p.alpha * a * gelu_erf_f(g);
-          }
-          T* optr = reinterpret_cast<T*>(p.out) + row * p.ldc + oc0 + c;
-          if (oc0 + c + 16 <= n_out) {
-            uint4 w0, w1;
-            w0.x = Cvt<T>::pack2(o[0], o[1]); w0.y = Cvt<T>::pack2(o[2], o[3]);
-            w0.z = Cvt<T>::pack2(o[4], o[5]); w0.w = Cvt<T>::pack2(o[6], o[7]);
-            w1.x = Cvt<T>::pack2(o[8], o[9]); w1.y = Cvt<T>::pack2(o[10], o[11]);
-            w1.z = Cvt<T>::pack2(o[12], o[13]); w1.w = Cvt<T>::pack2(o[14], o[15]);
-            reinterpret_cast<uint4*>(optr)[0] = w0;
-            reinterpret_cast<uint4*>(optr)[1] = w1;
-          } else {
-            for (int j = 0; j < 16; ++j)
-              if (oc0 + c + j < n_out) optr[j] = Cvt<T>::from_f(o[j]);
-          }
-        }
-      }
-    } else {
+    // ---- split-K: publish this CTA's partial tile; only the last arriver continues to the epilogue ----
+    const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+    const long long tiles = static_cast<long long>(gridDim.x) * gridDim.y;
+    bool from_ws = false;
+    if (p.splits > 1) {
+      // layout [split][tile][BLOCK_N/4][128 rows] float4: a warp's 32 rows store 512 contiguous bytes
+      float4* wp = reinterpret_cast<float4*>(p.ws_partial) +
+                   (static_cast<long long>(blockIdx.z) * tiles + tile_id) * (kBlockM * BLOCK_N / 4) + r;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 16) {
         uint32_t v[16];
         tmem_ld_x16(t_row + c, v);
         tmem_ld_wait();
-        if (row_ok && n0 + c < p.N) {
-          float o[16];
-          const bool full = (n0 + c + 16 <= p.N);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 f = has_work ? make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          __stcg(wp + static_cast<long long>(c / 4 + j) * kBlockM, f);
+        }
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        const int old = atomicAdd(p.ws_counter + tile_id, 1);
+        splitk_last = (old == p.splits - 1) ? 1 : 0;
+        if (splitk_last) p.ws_counter[tile_id] = 0;  // self-reset for the next launch
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (!splitk_last) goto epilogue_done;
+      __threadfence();
+      from_ws = true;
+    }
+    {
+      // accumulator columns [c, c+16) of this thread's row: from TMEM, or the deterministic sum of all partials
+      auto load_cols = [&](int c, float (&o)[16]) {
+        if (!from_ws) {
+          uint32_t v[16];
+          tmem_ld_x16(t_row + c, v);
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]);
-          if (p.bias) {
+        } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (full || n0 + c + j < p.N) o[j] += p.bias[b_noff + n0 + c + j];
+          for (int j = 0; j < 16; ++j) o[j] = 0.f;
+          for (int sp = 0; sp < p.splits; ++sp) {
+            const float4* wp = reinterpret_cast<const float4*>(p.ws_partial) +
+                               (static_cast<long long>(sp) * tiles + tile_id) * (kBlockM * BLOCK_N / 4) +
+                               static_cast<long long>(c / 4) * kBlockM + r;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 f = __ldcg(wp + j * kBlockM);
+              o[4 * j] += f.x; o[4 * j + 1] += f.y; o[4 * j + 2] += f.z; o[4 * j + 3] += f.w;
+            }
           }
-          if (p.rowvec) {
-            const float* rv = p.rowvec + static_cast<long long>(img) * p.rowvec_ld + n0 + c;
+        }
+      };
+      auto store16 = [&](T* optr, const float (&o)[16], int valid) {
+        if (valid >= 16) {
+          uint4 w0, w1;
+          w0.x = Cvt<T>::pack2(o[0], o[1]); w0.y = Cvt<T>::pack2(o[2], o[3]);
+          w0.z = Cvt<T>::pack2(o[4], o[5]); w0.w = Cvt<T>::pack2(o[6], o[7]);
+          w1.x = Cvt<T>::pack2(o[8], o[9]); w1.y = Cvt<T>::pack2(o[10], o[11]);
+          w1.z = Cvt<T>::pack2(o[12], o[13]); w1.w = Cvt<T>::pack2(o[14], o[15]);
+          reinterpret_cast<uint4*>(optr)[0] = w0;
+          reinterpret_cast<uint4*>(optr)[1] = w1;
+        } else {
+          for (int j = 0; j < 16; ++j)
+            if (j < valid) optr[j] = Cvt<T>::from_f(o[j]);
+        }
+      };
+
+      if (p.act == ES_ACT_GEGLU) {
+        constexpr int HALF = BLOCK_N / 2;
+        const int oc0 = blockIdx.y * HALF;  // output column base
+        const int n_out = p.N / 2;
+#pragma unroll 1
+        for (int c = 0; c < HALF; c += 16) {
+          float a[16], g[16];
+          load_cols(c, a);
+          load_cols(HALF + c, g);
+          if (row_ok) {
+            float o[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (full || n0 + c + j < p.N) o[j] += rv[j];
+            for (int j = 0; j < 16; ++j) {
+              float av = a[j], gv = g[j];
+              if (p.bias) {
+                av += p.bias[b_noff + n0 + c + j];
+                gv += p.bias[b_noff + n0 + HALF + c + j];
+              }
+              o[j] = p.alpha * av * gelu_erf_f(gv);
+            }
+            store16(reinterpret_cast<T*>(p.out) + row * p.ldc + oc0 + c, o, n_out - (oc0 + c));
           }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 16) {
+          float o[16];
+          load_cols(c, o);
+          if (row_ok && n0 + c < p.N) {
+            const int valid = p.N - (n0 + c);
+            const bool full = valid >= 16;
+            if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] *= p.alpha;
-          if (p.residual) {
-            const T* rp = reinterpret_cast<const T*>(p.residual) + row * p.ldr + n0 + c;
-            if (full) {
-              uint4 r0 = reinterpret_cast<const uint4*>(rp)[0];
-              uint4 r1 = reinterpret_cast<const uint4*>(rp)[1];
-              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+              for (int j = 0; j < 16; ++j)
+                if (full || j < valid) o[j] += p.bias[b_noff + n0 + c + j];
+            }
+            if (p.rowvec) {
+              const float* rv = p.rowvec + static_cast<long long>(img) * p.rowvec_ld + n0 + c;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float2 f = Cvt<T>::unpack2(rr[j]);
-                o[2 * j] += f.x;
-                o[2 * j + 1] += f.y;
+              for (int j = 0; j < 16; ++j)
+                if (full || j < valid) o[j] += rv[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] *= p.alpha;
+            if (p.residual) {
+              const T* rp = reinterpret_cast<const T*>(p.residual) + row * p.ldr + n0 + c;
+              if (full) {
+                uint4 r0 = reinterpret_cast<const uint4*>(rp)[0];
+                uint4 r1 = reinterpret_cast<const uint4*>(rp)[1];
+                const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float2 f = Cvt<T>::unpack2(rr[j]);
+                  o[2 * j] += f.x;
+                  o[2 * j + 1] += f.y;
+                }
+              } else {
+                for (int j = 0; j < 16; ++j)
+                  if (j < valid) o[j] += Cvt<T>::to_f(rp[j]);
+              }
+            }
+            if (p.out_fp32) {
+              float* optr = reinterpret_cast<float*>(p.out) + row * p.ldc + n0 + c;
+              if (full) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  reinterpret_cast<float4*>(optr)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              } else {
+                for (int j = 0; j < 16; ++j)
+                  if (j < valid) optr[j] = o[j];
               }
             } else {
-              for (int j = 0; j < 16; ++j)
-                if (n0 + c + j < p.N) o[j] += Cvt<T>::to_f(rp[j]);
-            }
-          }
-          if (p.out_fp32) {
-            float* optr = reinterpret_cast<float*>(p.out) + row * p.ldc + n0 + c;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                reinterpret_cast<float4*>(optr)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-            } else {
-              for (int j = 0; j < 16; ++j)
-                if (n0 + c + j < p.N) optr[j] = o[j];
-            }
-          } else {
-            T* optr = reinterpret_cast<T*>(p.out) + row * p.ldc + n0 + c;
-            if (full) {
-              uint4 w0, w1;
-              w0.x = Cvt<T>::pack2(o[0], o[1]); w0.y = Cvt<T>::pack2(o[2], o[3]);
-              w0.z = Cvt<T>::pack2(o[4], o[5]); w0.w = Cvt<T>::pack2(o[6], o[7]);
-              w1.x = Cvt<T>::pack2(o[8], o[9]); w1.y = Cvt<T>::pack2(o[10], o[11]);
-              w1.z = Cvt<T>::pack2(o[12], o[13]); w1.w = Cvt<T>::pack2(o[14], o[15]);
-              reinterpret_cast<uint4*>(optr)[0] = w0;
-              reinterpret_cast<uint4*>(optr)[1] = w1;
-            } else {
-              for (int j = 0; j < 16; ++j)
-                if (n0 + c + j < p.N) optr[j] = Cvt<T>::from_f(o[j]);
+              store16(reinterpret_cast<T*>(p.out) + row * p.ldc + n0 + c, o, valid);
             }
           }
         }
       }
     }
+  epilogue_done:;
   }
 
   // ---- teardown ------------------------------------------------------------------------------
@@ -317,12 +374,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // --------------------------------------------------------------------------------------------
 template <typename T, int BLOCK_N>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
-                       const CUtensorMap& tmB2, GemmKParams& kp, int m_tiles, int n_tiles, cudaStream_t stream) {
+                       const CUtensorMap& tmB2, GemmKParams& kp, int m_tiles, int n_tiles, const EsGemm* g,
+                       cudaStream_t stream) {
   constexpr int kStageBytes = kBlockM * kBlockK * 2 + BLOCK_N * kBlockK * 2;
-  int stages = (200 * 1024) / kStageBytes;
-  if (stages > 8) stages = 8;
   const int kb_total = kp.taps * kp.kblocks1 + kp.kblocks2;
-  if (stages > kb_total) stages = kb_total < 2 ? 2 : kb_total;
+  const int tiles = m_tiles * n_tiles;
+  // ---- split-K: small-M layers have too few output tiles to cover 148 SMs; stream K over several CTAs
+  int splits = 1;
+  if (g->workspace && g->split_k != 1) {
+    if (g->split_k > 1) {
+      splits = g->split_k;
+    } else if (tiles <= 96 && kb_total >= 16) {
+      splits = (2 * 148 + tiles - 1) / tiles;
+      if (splits > kb_total / 6) splits = kb_total / 6;
+      if (splits > 32) splits = 32;
+      if (splits < 1) splits = 1;
+    }
+    const long long need = 65536 + static_cast<long long>(splits) * tiles * kBlockM * BLOCK_N * 4;
+    if (splits > 1 && (need > g->workspace_bytes || tiles > 16384)) splits = 1;
+  }
+  kp.splits = splits;
+  kp.ws_counter = reinterpret_cast<int*>(g->workspace);
+  kp.ws_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(g->workspace) + 65536);
+  // ---- pipeline depth: default leaves room for two CTAs per SM so one CTA's epilogue overlaps the other's MMAs
+  const int kb_cta = (kb_total + splits - 1) / splits;
+  int stages = g->stages > 0 ? g->stages : (108 * 1024) / kStageBytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  if (stages > kb_cta) stages = kb_cta < 2 ? 2 : kb_cta;
   kp.stages = stages;
   const size_t smem = static_cast<size_t>(stages) * kStageBytes + 1024;
   auto kern = gemm_kernel<T, BLOCK_N>;
@@ -331,7 +410,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     ES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr_smem = smem;
   }
-  dim3 grid(m_tiles, n_tiles, 1);
+  dim3 grid(m_tiles, n_tiles, splits);
   kern<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, tmA2, tmB2, kp);
   ES_CUDA(cudaGetLastError());
   return 0;
@@ -495,11 +574,11 @@ static int gemm_dispatch(const EsGemm* g, cudaStream_t stream) {
   }
 
   switch (bn_tile) {
-    case 32: return launch_gemm<T, 32>(tmA, tmB, tmA2, tmB2, kp, m_tiles, n_tiles, stream);
-    case 64: return launch_gemm<T, 64>(tmA, tmB, tmA2, tmB2, kp, m_tiles, n_tiles, stream);
-    case 128: return launch_gemm<T, 128>(tmA, tmB, tmA2, tmB2, kp, m_tiles, n_tiles, stream);
-    case 160: return launch_gemm<T, 160>(tmA, tmB, tmA2, tmB2, kp, m_tiles, n_tiles, stream);
-    case 256: return launch_gemm<T, 256>(tmA, tmB, tmA2, tmB2, kp, m_tiles, n_tiles, stream);
+    case 32: return launch_gemm<T, 32>(tmA, tmB, tmA2, tmB2, kp, m_tiles, n_tiles, g, stream);
+    case 64: return launch_gemm<T, 64>(tmA, tmB, tmA2, tmB2, kp, m_tiles, n_tiles, g, stream);
+    case 128: return launch_gemm<T, 128>(tmA, tmB, tmA2, tmB2, kp, m_tiles, n_tiles, g, stream);
+    case 160: return launch_gemm<T, 160>(tmA, tmB, tmA2, tmB2, kp, m_tiles, n_tiles, g, stream);
+    case 256: return launch_gemm<T, 256>(tmA, tmB, tmA2, tmB2, kp, m_tiles, n_tiles, g, stream);
     default: ES_CHECK(false, "es_gemm: unsupported block_n %d", bn_tile);
   }
   return 0;

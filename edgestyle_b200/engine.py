@@ -272,6 +272,7 @@ class DenoiseEngine:
         for i, c in enumerate(cfg.block_out_channels):
             if c % 8 or c % cfg.norm_num_groups or (c // cfg.num_heads) % 8:
                 raise ValueError(f"channel count {c} unsupported (needs %8, %groups, head_dim %8)")
+        ops.set_gemm_workspace(256 << 20, self.dev)  # split-K scratch shared by all GEMM launches of the stream
         self._pack(unet_sd, lora_sds, pose_sd, merge_sd)
         self._alloc_static()
 

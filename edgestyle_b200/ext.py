@@ -26,7 +26,8 @@ class EsGemm(C.Structure):
         ("seg_row_start", C.c_int * (ES_MAX_SEG + 1)), ("seg_b_noff", C.c_int * ES_MAX_SEG),
         ("seg_b2_noff", C.c_int * ES_MAX_SEG), ("bias", vp), ("rowvec", vp), ("rows_per_img", C.c_int),
         ("rowvec_ld", C.c_int), ("residual", vp), ("ldr", ll), ("act", C.c_int), ("alpha", C.c_float),
-        ("out", vp), ("ldc", ll), ("out_fp32", C.c_int), ("block_n", C.c_int),
+        ("out", vp), ("ldc", ll), ("out_fp32", C.c_int), ("block_n", C.c_int), ("stages", C.c_int),
+        ("split_k", C.c_int), ("workspace", vp), ("workspace_bytes", ll),
     ]
 
 

@@ -14,6 +14,17 @@ from . import ext
 from .ext import ACT_GEGLU, ACT_NONE, EsAttention, EsGemm, EsGroupNorm, EsMerge, check, load
 
 
+GEMM_WORKSPACE: Optional[torch.Tensor] = None  # default split-K scratch (zero-initialised uint8 tensor), see EsGemm
+
+
+def set_gemm_workspace(nbytes: int = 256 << 20, device="cuda") -> torch.Tensor:
+    """Allocate (once) the zeroed split-K workspace used by every gemm() call that does not pass its own."""
+    global GEMM_WORKSPACE
+    if GEMM_WORKSPACE is None or GEMM_WORKSPACE.numel() < nbytes or not GEMM_WORKSPACE.is_cuda:
+        GEMM_WORKSPACE = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    return GEMM_WORKSPACE
+
+
 LAUNCHES = 0  # native kernel launches issued through this module (bench.py reports it as gpu_launches)
 
 
@@ -47,7 +58,7 @@ def _need_cuda(*ts):
 def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: int = 1, whn=None, bias=None,
          rowvec=None, rows_per_img: int = 0, residual=None, act: int = ACT_NONE, alpha: float = 1.0,
          a2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None, segs=None, block_n: int = 0,
-         c1: Optional[int] = None):
+         c1: Optional[int] = None, stages: int = 0, split_k: int = 0, workspace: Optional[torch.Tensor] = None):
     """out[m, :n] = epilogue(A (*) B^T).  a: [M, >=c1] (pitch = a.stride(0)); b: [n_total, taps*c1].
 
     whn=(w, h, n_img) for taps == 9.  segs = list of (row_start, b_noff, b2_noff) + final row end via segs_end.
@@ -93,6 +104,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: i
     g.ldc = out.stride(0)
     g.out_fp32 = 1 if out.dtype == torch.float32 else 0
     g.block_n = block_n
+    g.stages = stages
+    g.split_k = split_k
+    ws = workspace if workspace is not None else GEMM_WORKSPACE
+    if ws is not None:
+        g.workspace = ws.data_ptr()
+        g.workspace_bytes = ws.numel() * ws.element_size()
     _count()
     check(load().es_gemm(C.byref(g), _stream()), "es_gemm")
     return out

@@ -77,6 +77,11 @@ typedef struct EsGemm {
   long long ldc;
   int out_fp32;
   int block_n; /* 0 = auto */
+  int stages;  /* smem pipeline depth, 0 = auto */
+  int split_k; /* 0 = auto, 1 = off, >1 = forced; needs `workspace` */
+  void* workspace; /* optional split-K scratch: first 64 KiB = tile counters (zero-initialised ONCE by the caller,
+                      self-resetting), rest = fp32 partial tiles.  Must not be shared by concurrent launches. */
+  long long workspace_bytes;
 } EsGemm;
 int es_gemm(const EsGemm* g, void* stream);
 

@@ -121,6 +121,39 @@ def test_gemm_segments_and_lora_k_extension():
     _close(out, want, 5e-3, 5e-3, "lora k-extension")
 
 
+@pytest.mark.parametrize("split_k", [0, 2, 5, 16])
+@pytest.mark.parametrize("M,N,K,bn", [(128, 1280, 2304, 128), (512, 640, 11520, 64), (300, 200, 1000, 256)])
+def test_gemm_split_k(M, N, K, bn, split_k):
+    """Split-K partial tiles + last-arriver epilogue must equal the single-pass result (and self-reset counters)."""
+    from edgestyle_b200 import ops
+
+    ops.set_gemm_workspace(256 << 20)
+    a = _rand(M, K, seed=90)
+    b = _rand(N, K, scale=K ** -0.5, seed=91)
+    bias = _rand(N, dtype=torch.float32, seed=92)
+    res = _rand(M, N, seed=93)
+    want = a.float() @ b.float().t() + bias + res.float()
+    for _ in range(2):  # second launch re-uses the self-reset counters
+        out = torch.zeros(M, N, device=DEV, dtype=torch.float16)
+        ops.gemm(a, b, N, out=out, bias=bias, residual=res, block_n=bn, split_k=split_k)
+        _close(out, want, 6e-3, 6e-3, f"split_k={split_k}")
+
+
+def test_conv3x3_split_k_small_m():
+    from edgestyle_b200 import ops
+
+    ops.set_gemm_workspace(256 << 20)
+    n_img, h, w, cin, cout = 2, 8, 8, 256, 128
+    x = _rand(n_img * h * w, cin, seed=94)
+    wt = _rand(cout, 9 * cin, scale=(9 * cin) ** -0.5, seed=95)
+    bias = _rand(cout, dtype=torch.float32, seed=96)
+    out = torch.empty(n_img * h * w, cout, device=DEV, dtype=torch.float16)
+    ops.gemm(x, wt, cout, out=out, taps=9, whn=(w, h, n_img), bias=bias, split_k=6, block_n=64)
+    want = F.conv2d(x.float().view(n_img, h, w, cin).permute(0, 3, 1, 2), wt.float().view(cout, 3, 3, cin)
+                    .permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, cout)
+    _close(out, want, 5e-3, 5e-3, "conv split-k")
+
+
 @pytest.mark.parametrize("n_img,h,w,cin,cout", [(2, 64, 64, 320, 320), (3, 32, 32, 64, 128), (2, 16, 16, 640, 320),
                                                 (4, 8, 8, 128, 64), (1, 12, 16, 64, 64), (3, 4, 4, 32, 32),
                                                 (2, 2, 2, 32, 32), (1, 24, 128, 64, 32)])
