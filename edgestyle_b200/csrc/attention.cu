@@ -29,6 +29,28 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float y;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
+
+// Optional event trace (clock64 stamps of one CTA) for pipeline analysis: build with -DES_ATT_TRACE.
+#ifdef ES_ATT_TRACE
+__device__ long long g_att_trace[4][64];
+#define ATT_TRACE(role, slot)                                                            \
+  do {                                                                                   \
+    if (blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && (slot) < 64) g_att_trace[role][slot] = clock64(); \
+  } while (0)
+#else
+#define ATT_TRACE(role, slot) do {} while (0)
+#endif
+
 struct AttParams {
   int d, dN, nq, nkv;
   float scale_log2;
@@ -105,9 +127,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int kq = (p.d + 15) / 16;  // MMAs along the head dim
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
       mbar_wait(&q_full, 0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const uint32_t ph = j & 1;
-        mbar_wait(&k_full, ph);
+      auto issue_qk = [&](int j) {
+        mbar_wait(&k_full, j & 1);
         tc_fence_after();
         for (int k = 0; k < kq; ++k) {
           const uint64_t ad = smem_desc_sw128(aQ + (k >> 2) * kAtomBytes, 16, 1024) + 2 * (k & 3);
@@ -116,7 +137,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         umma_commit(&k_empty);
         umma_commit(&s_full);
-        mbar_wait(&p_full, ph);  // P in smem, S consumed, O rescaled
+      };
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const uint32_t ph = j & 1;
+        ATT_TRACE(0, 4 * j + 1);
+        mbar_wait(&p_full, ph);  // P(j) in smem and S(j) consumed
+        ATT_TRACE(0, 4 * j + 2);
+        // S is free again: start the next tile's scores first so its softmax can begin while PV(j) runs
+        if (j + 1 < n_tiles) issue_qk(j + 1);
+        ATT_TRACE(0, 4 * j + 0);
         mbar_wait(&v_full, ph);
         tc_fence_after();
 #pragma unroll
@@ -128,80 +158,142 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         umma_commit(&v_empty);
         umma_commit(&o_done);
+        ATT_TRACE(0, 4 * j + 3);
       }
     }
   } else {
     const int qd = warp & 3;
     const int r = qd * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_run = -INFINITY;  // row max estimate used as the softmax shift, in scaled (log2) units
+    float l_run = 0.f;        // running row sum of P (fp32)
+    const float sl2 = p.scale_log2;
+    // Softmax is shift-invariant, so the shift only has to stay within 2^kSlack of the true running max
+    // (P <= 2^kSlack fits 16-bit floats).  Tiles after the first are therefore processed in ONE pass with
+    // the previous shift; a warp re-does its 32 rows (and rescales O) only when some row's max grew by
+    // more than kSlack -- rare once the first tiles have been seen.
+    constexpr float kSlack = 8.0f;
+
+    // writes P for columns [c, c+32) of this thread's row from raw scores v, with shift -neg_m
+    auto emit_p = [&](const uint32_t (&v)[32], int c, float neg_m, int kv_valid, bool full_tile, float& sum) {
+      uint32_t pk[16];
+      float s0 = 0.f, s1 = 0.f;
+      if (full_tile) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, neg_m));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, neg_m));
+          s0 += p0;
+          s1 += p1;
+          pk[i >> 1] = Cvt<T>::pack2(p0, p1);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = (c + i < kv_valid) ? ex2_approx(fmaf(__uint_as_float(v[i]), sl2, neg_m)) : 0.f;
+          const float p1 = (c + i + 1 < kv_valid) ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, neg_m)) : 0.f;
+          s0 += p0;
+          s1 += p1;
+          pk[i >> 1] = Cvt<T>::pack2(p0, p1);
+        }
+      }
+      sum += s0 + s1;
+      uint8_t* prow = sP + (c >> 6) * kAtomBytes + r * 128;
+      const int cc0 = (c & 63) >> 3;  // first 16 B chunk of this 32-column group inside the atom
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int chunk = (cc0 + q4) ^ (r & 7);
+        *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+      }
+    };
+    auto tile_max = [&](const uint32_t (&v)[32], int c, int kv_valid, bool full_tile, float mx) {
+      if (full_tile) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      return mx;
+    };
+
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t ph = j & 1;
       const int kv_valid = min(128, p.nkv - j * 128);
+      const bool full_tile = kv_valid == 128;
+      if (threadIdx.x == 64) ATT_TRACE(1, 4 * j + 0);
       mbar_wait(&s_full, ph);
+      if (threadIdx.x == 64) ATT_TRACE(1, 4 * j + 1);
+      if (j > 0) mbar_wait(&o_done, ph ^ 1);  // PV(j-1) retired: P may be overwritten, O may be touched
       tc_fence_after();
-      // pass 1: row max
-      float m_new = m_run;
-#pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(t_row + c, v);
+      if (threadIdx.x == 64) ATT_TRACE(1, 4 * j + 2);
+      float mx = -INFINITY;
+      uint32_t va[32], vb[32];
+      if (j == 0) {
+        // first tile: a max pass to establish the shift (TMEM loads software-pipelined against the math)
+        tmem_ld_x32(t_row, va);
         tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c + i < kv_valid) m_new = fmaxf(m_new, __uint_as_float(v[i]) * p.scale_log2);
+        tmem_ld_x32(t_row + 32, vb);
+        mx = tile_max(va, 0, kv_valid, full_tile, mx);
+        tmem_ld_wait();
+        tmem_ld_x32(t_row + 64, va);
+        mx = tile_max(vb, 32, kv_valid, full_tile, mx);
+        tmem_ld_wait();
+        tmem_ld_x32(t_row + 96, vb);
+        mx = tile_max(va, 64, kv_valid, full_tile, mx);
+        tmem_ld_wait();
+        mx = tile_max(vb, 96, kv_valid, full_tile, mx);
+        m_run = mx * sl2;
       }
-      const float alpha = exp2f(m_run - m_new);  // 0 on the first tile (m_run = -inf)
-      // previous PV must have retired before P is overwritten / O is touched
-      if (j > 0) {
-        mbar_wait(&o_done, ph ^ 1);
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll 1
-          for (int c = 0; c < p.dN; c += 16) {
-            uint32_t o[16];
-            tmem_ld_x16(t_row + kOCol + c, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_x16(t_row + kOCol + c, o);
-          }
-          tmem_st_wait();
-        }
-      }
-      // pass 2: P = exp2(s - m), row sum, write P (K-major SW128: row r, 16 B chunk index XOR (r & 7))
+      bool redo = false;
       float sum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(t_row + c, v);
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        const float neg_m = -m_run;
+        sum = 0.f;
+        tmem_ld_x32(t_row, va);
         tmem_ld_wait();
-        uint32_t pk[16];
+        tmem_ld_x32(t_row + 32, vb);
+        if (j > 0 && attempt == 0) mx = tile_max(va, 0, kv_valid, full_tile, mx);
+        emit_p(va, 0, neg_m, kv_valid, full_tile, sum);
+        tmem_ld_wait();
+        tmem_ld_x32(t_row + 64, va);
+        if (j > 0 && attempt == 0) mx = tile_max(vb, 32, kv_valid, full_tile, mx);
+        emit_p(vb, 32, neg_m, kv_valid, full_tile, sum);
+        tmem_ld_wait();
+        tmem_ld_x32(t_row + 96, vb);
+        if (j > 0 && attempt == 0) mx = tile_max(va, 64, kv_valid, full_tile, mx);
+        emit_p(va, 64, neg_m, kv_valid, full_tile, sum);
+        tmem_ld_wait();
+        if (j > 0 && attempt == 0) mx = tile_max(vb, 96, kv_valid, full_tile, mx);
+        emit_p(vb, 96, neg_m, kv_valid, full_tile, sum);
+        if (j == 0 || attempt == 1) break;
+        const float m_tile = mx * sl2;
+        redo = __any_sync(0xffffffffu, m_tile > m_run + kSlack);
+        if (!redo) break;
+        // rare path: raise the shift of the rows that need it, rescale their O / row-sum columns, redo P
+        const float m_new = fmaxf(m_run, m_tile);
+        const float alpha = ex2_approx(m_run - m_new);
+#pragma unroll 1
+        for (int c = 0; c < p.dN; c += 16) {
+          uint32_t o[16];
+          tmem_ld_x16(t_row + kOCol + c, o);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = (c + i < kv_valid) ? exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_new) : 0.f;
-          float p1 = (c + i + 1 < kv_valid) ? exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - m_new) : 0.f;
-          pk[i >> 1] = Cvt<T>::pack2(p0, p1);
-          // accumulate the ROUNDED probabilities so that numerator and denominator match
-          const float2 pr = Cvt<T>::unpack2(pk[i >> 1]);
-          sum += pr.x + pr.y;
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_x16(t_row + kOCol + c, o);
         }
-        uint8_t* prow = sP + (c >> 6) * kAtomBytes + r * 128;
-        const int cc0 = (c & 63) >> 3;  // first 16 B chunk of this 32-column group inside the atom
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int chunk = (cc0 + q4) ^ (r & 7);
-          *reinterpret_cast<uint4*>(prow + chunk * 16) =
-              make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
-        }
+        tmem_st_wait();
+        l_run *= alpha;
+        m_run = m_new;
       }
-      l_run = l_run * alpha + sum;
-      m_run = m_new;
+      l_run += sum;
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       tc_fence_before();
       mbar_arrive(&p_full);
+      if (threadIdx.x == 64) ATT_TRACE(1, 4 * j + 3);
     }
-    // epilogue: O / l
+    // epilogue: O / l   (l = row sum accumulated by the tensor core in the columns right after O)
     mbar_wait(&o_done, (n_tiles - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
@@ -288,6 +380,12 @@ static int attention_dispatch(const EsAttention* a, cudaStream_t s) {
 }
 
 }  // namespace es
+
+#ifdef ES_ATT_TRACE
+extern "C" int es_attention_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, es::g_att_trace, sizeof(es::g_att_trace)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int es_attention(const EsAttention* a, void* stream) {
   if (!a) {
