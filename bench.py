@@ -181,8 +181,9 @@ def run_ours(args):
             lat.copy_(host["latents"], non_blocking=True)  # a new image starts every 20 steps
         one_step(i)
     if world > 1:  # the only collective on the path: gather final latents (32 KB per row)
-        gathered = [torch.empty_like(lat) for _ in range(world)]
-        dist.all_gather(gathered, lat)
+        from edgestyle_b200.dist import gather_latents
+
+        gathered = gather_latents(lat, world * images, rank, world)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)

@@ -8,8 +8,11 @@ import numpy as np
 
 
 def alphas_cumprod(num_train: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012) -> np.ndarray:
-    betas = np.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train, dtype=np.float32) ** 2
-    return np.cumprod(1.0 - betas, dtype=np.float32)
+    """scaled_linear betas, fp32 torch.cumprod -- the same arithmetic (and rounding) as diffusers."""
+    import torch
+
+    betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train, dtype=torch.float32) ** 2
+    return torch.cumprod(1.0 - betas, dim=0).numpy()
 
 
 class DDIMScheduler:

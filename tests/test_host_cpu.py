@@ -1,0 +1,130 @@
+"""Host-side logic that needs no GPU: parameter specs vs the oracle, weight packing, schedulers, the
+reference-surface error behaviour of the model mirrors."""
+import pytest
+import torch
+
+from edgestyle_b200 import config as C
+from edgestyle_b200.schedulers import DDIMScheduler
+from oracle.schedulers import DDIMScheduler as OracleDDIM
+from oracle.sd15 import SD15Config
+from oracle.step import build_models
+
+TINY = SD15Config(block_out_channels=(64, 128, 128, 128), cross_attention_dim=64)
+
+
+@pytest.fixture(scope="module")
+def models():
+    return build_models(TINY, (8, 8), rank=4)
+
+
+def test_specs_match_oracle_state_dicts(models):
+    cfg = C.UNetConfig.from_any(TINY)
+    usd = models.unet.state_dict()
+    spec = C.unet_spec(cfg)
+    assert set(spec) == set(usd) and all(tuple(usd[k].shape) == v for k, v in spec.items())
+    lsd = models.lora_agnostic.state_dict()
+    ls = dict(C.lora_spec(cfg, 4))
+    ls.update(C.controlnet_extra_spec(cfg, False))
+    assert set(ls) <= set(lsd) and all(tuple(lsd[k].shape) == v for k, v in ls.items())
+    assert all(k.startswith("controlnet_cond_embedding.") for k in set(lsd) - set(ls))
+    psd = models.openpose.state_dict()
+    ps = dict(C.encoder_spec(cfg))
+    ps.update(C.controlnet_extra_spec(cfg, True))
+    assert set(ps) == set(psd)
+    msd = models.controlnet.merge_state_dict()
+    ms = C.merge_spec(cfg, 8, 8)
+    assert set(ms) == set(msd) and all(tuple(msd[k].shape) == v for k, v in ms.items())
+    assert len(C.lora_linear_names(C.UNetConfig())) == 82  # the reference's 82 LoRA'd Linear layers
+
+
+def test_full_size_spec_parameter_counts():
+    cfg = C.UNetConfig()
+    n = lambda spec: sum(int(torch.tensor(s).prod()) for s in spec.values())
+    assert n(C.unet_spec(cfg)) == 859_520_964
+    cn = dict(C.encoder_spec(cfg))
+    cn.update(C.controlnet_extra_spec(cfg, True))
+    assert n(cn) == 361_279_120
+    assert n(C.lora_spec(cfg, 32)) == 6_354_944
+    assert n(C.merge_spec(cfg, 64, 64)) == 53_902_720
+    assert C.residual_shapes(cfg, 64, 64)[3] == (320, 32, 32) and C.residual_shapes(cfg, 96, 128)[-1] == (1280, 12, 16)
+
+
+def test_ddim_host_tables_match_oracle():
+    a, b = DDIMScheduler(), OracleDDIM()
+    for n in (20, 25, 50):
+        ta, tb = a.set_timesteps(n), b.set_timesteps(n)
+        assert ta.tolist() == tb.tolist()
+        for t in ta:
+            ca, cb = a.coefficients(int(t)), b.coefficients(int(t))
+            assert abs(ca[0] - float(cb[0])) < 1e-7 and abs(ca[1] - float(cb[1])) < 1e-7
+
+
+def test_merge_block_repack_is_a_pure_permutation(models):
+    from edgestyle_b200.engine import pack_merge_block
+
+    blk = models.controlnet.multi_controlnet_down_blocks[4]
+    sd = blk.state_dict()
+    c = blk.third_conv.weight.shape[0]
+    h, w = blk.second_normalization.weight.shape[1:]
+    p = pack_merge_block(sd, c, h, w, torch.float32, "cpu")
+    g1 = sd["first_normalization.weight"]  # [3C, H, W], channel index c*3 + pair
+    assert torch.equal(p["g1"][5, 2, 7], g1[7 * 3 + 2].reshape(-1)[5])
+    assert torch.equal(p["w1"][3, 1], sd["first_conv.weight"][3 * 3 + 1, :, 0, 0])
+    assert torch.equal(p["g2"][6, 9], sd["second_normalization.weight"][9].reshape(-1)[6])
+
+
+def test_model_mirrors_reference_surface(models):
+    from edgestyle_b200.model import (CachedControlNetModel, ControlLoRAModel, EdgeStyleMultiControlNetModel,
+                                      UNet2DConditionModel)
+
+    cfg = C.UNetConfig.from_any(TINY)
+    unet = UNet2DConditionModel(cfg, models.unet.state_dict())
+    agn = ControlLoRAModel(cfg, models.lora_agnostic.state_dict(), lora_linear_rank=4)
+    clo = ControlLoRAModel(cfg, models.lora_clothes.state_dict(), lora_linear_rank=4)
+    pose = CachedControlNetModel(cfg, models.openpose.state_dict())
+    # state_dict filter semantics of controllora.py:600-606
+    assert all(k.split(".")[0] not in ControlLoRAModel._skip_layers or ".lora_layer." in k for k in agn.state_dict())
+    with pytest.raises(NotImplementedError):
+        EdgeStyleMultiControlNetModel([agn, pose, clo, pose, agn, pose], latent_hw=(8, 8))  # nets 2/4 must be one object
+    multi = EdgeStyleMultiControlNetModel([agn, pose, clo, pose, clo, pose], models.controlnet.merge_state_dict(), (8, 8))
+    with pytest.raises(RuntimeError):
+        multi.unet()  # not tied yet (app.py:95-97)
+    agn.tie_weights(unet)
+    clo.tie_weights(unet)
+    assert multi.unet() is unet
+    with pytest.raises(NotImplementedError):
+        ControlLoRAModel(cfg, models.lora_agnostic.state_dict(), lora_linear_rank=4, lora_conv2d_rank=4)
+    fresh = ControlLoRAModel.from_unet(unet, lora_linear_rank=4)
+    assert all(v.abs().max() == 0 for k, v in fresh.state_dict().items() if k.endswith("up.weight"))
+    with pytest.raises(KeyError):
+        CachedControlNetModel(cfg, {})
+    x = torch.zeros(2, 4, 8, 8)
+    with pytest.raises(ValueError):
+        multi.forward(x, 1, torch.zeros(2, 77, 64), [x] * 5, [1.0] * 5)
+    # no CUDA here: the engine must refuse to run rather than fall back
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            multi.forward(x, 1, torch.zeros(2, 77, 64), [torch.zeros(2, 64, 8, 8)] * 6, [1.0] * 6)
+
+
+def test_pipeline_rejects_out_of_scope_arguments(models):
+    from edgestyle_b200.model import (CachedControlNetModel, ControlLoRAModel, EdgeStyleMultiControlNetModel,
+                                      EdgeStyleStableDiffusionControlNetPipeline, UNet2DConditionModel)
+
+    cfg = C.UNetConfig.from_any(TINY)
+    unet = UNet2DConditionModel(cfg, models.unet.state_dict())
+    agn = ControlLoRAModel(cfg, models.lora_agnostic.state_dict(), 4, unet=unet)
+    clo = ControlLoRAModel(cfg, models.lora_clothes.state_dict(), 4, unet=unet)
+    pose = CachedControlNetModel(cfg, models.openpose.state_dict())
+    multi = EdgeStyleMultiControlNetModel([agn, pose, clo, pose, clo, pose], models.controlnet.merge_state_dict(), (8, 8))
+    pipe = EdgeStyleStableDiffusionControlNetPipeline(unet=unet, controlnet=multi)
+    pe = torch.zeros(1, 77, 64)
+    conds = [torch.zeros(2, 64, 8, 8)] * 6
+    with pytest.raises(NotImplementedError):
+        pipe(prompt="a photo", image=conds, prompt_embeds=pe, negative_prompt_embeds=pe, output_type="latent")
+    with pytest.raises(NotImplementedError):
+        pipe(image=conds, prompt_embeds=pe, negative_prompt_embeds=pe, output_type="pil")
+    with pytest.raises(NotImplementedError):
+        pipe(image=conds, prompt_embeds=pe, negative_prompt_embeds=pe, output_type="latent", guess_mode=True)
+    with pytest.raises(ValueError):
+        pipe(image=conds[:4], prompt_embeds=pe, negative_prompt_embeds=pe, output_type="latent")
