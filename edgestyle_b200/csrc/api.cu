@@ -62,7 +62,15 @@ int encode_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t
   return 0;
 }
 
+static int g_pdl = 0;
+bool pdl_enabled() { return g_pdl != 0; }
+
 }  // namespace es
 
+extern "C" int es_set_pdl(int enabled) {
+  const int old = es::g_pdl;
+  es::g_pdl = enabled ? 1 : 0;
+  return old;
+}
 extern "C" const char* es_last_error(void) { return es::g_err; }
 extern "C" int es_abi_version(void) { return 1; }

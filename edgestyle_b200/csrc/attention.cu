@@ -73,6 +73,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __shared__ __align__(8) uint64_t q_full, k_full, v_full, k_empty, v_empty, s_full, p_full, o_done;
   __shared__ uint32_t tmem_base_smem;
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128;
@@ -102,6 +103,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // PDL: everything above (barrier init, TMEM alloc, descriptor prefetch) overlaps the previous kernel's tail;
+  // global memory written by it may only be touched after this point.
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -362,7 +366,7 @@ static int launch_attention(const EsAttention* a, cudaStream_t stream) {
     attr_smem = smem;
   }
   dim3 grid((a->nq + 127) / 128, a->heads, a->batch);
-  kern<<<grid, kAttThreads, smem, stream>>>(tmQ, tmK, tmV, p);
+  ES_CUDA(launch_kernel(kern, dim3(grid), dim3(kAttThreads), smem, stream, tmQ, tmK, tmV, p));
   ES_CUDA(cudaGetLastError());
   return 0;
 }

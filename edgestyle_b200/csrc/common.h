@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/edgestyle_b200.h"
 
@@ -35,5 +36,32 @@ int encode_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t
                     const uint32_t* box);
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Programmatic dependent launch (PDL): when enabled, every kernel of this library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs may be scheduled (and run their prologue:
+// barrier init, TMEM alloc, tensor-map prefetch) while the previous kernel in the stream drains; each kernel
+// executes griddepcontrol.wait before its first global-memory access.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  int n = 0;
+  if (pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    n = 1;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 }  // namespace es

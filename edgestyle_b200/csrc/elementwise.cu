@@ -9,6 +9,8 @@ namespace es {
 // ---------------------------------------------------------------- NCHW fp32 <-> NHWC 16-bit
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int c, int hw, long long ldd) {
+  pdl_launch_dependents();
+  pdl_wait();  // PDL: inputs are produced by the preceding kernel
   // grid (ceil(hw/32), ceil(ldd/32), n); block (32, 8): smem transpose tile 32 px x 32 ch
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
@@ -25,6 +27,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict
 }
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, long long lds, float* __restrict__ dst, int c, int hw) {
+  pdl_launch_dependents();
+  pdl_wait();  // PDL: inputs are produced by the preceding kernel
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -44,6 +48,8 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, long long lds, fl
 template <typename T>
 __global__ void im2col3x3_kernel(const T* __restrict__ src, long long lds, T* __restrict__ dst, long long ldo, int n,
                                  int h, int w, int c, int stride, int ho, int wo) {
+  pdl_launch_dependents();
+  pdl_wait();  // PDL: inputs are produced by the preceding kernel
   const long long rows = static_cast<long long>(n) * ho * wo;
   if ((c & 7) == 0) {
     const int vpt = c >> 3;
@@ -83,6 +89,8 @@ __global__ void im2col3x3_kernel(const T* __restrict__ src, long long lds, T* __
 template <typename T>
 __global__ void upsample2x_kernel(const T* __restrict__ src, long long lds, T* __restrict__ dst, long long ldd, int n,
                                   int h, int w, int c) {
+  pdl_launch_dependents();
+  pdl_wait();  // PDL: inputs are produced by the preceding kernel
   const int vpp = c >> 3;
   const long long total = static_cast<long long>(n) * (2 * h) * (2 * w) * vpp;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -100,6 +108,8 @@ __global__ void upsample2x_kernel(const T* __restrict__ src, long long lds, T* _
 template <typename T>
 __global__ void add_kernel(const T* __restrict__ a, long long lda, const T* __restrict__ b, long long ldb,
                            T* __restrict__ out, long long ldo, long long rows, int c) {
+  pdl_launch_dependents();
+  pdl_wait();  // PDL: inputs are produced by the preceding kernel
   const int vpp = c >> 3;
   const long long total = rows * vpp;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -121,6 +131,8 @@ __global__ void add_kernel(const T* __restrict__ a, long long lda, const T* __re
 
 // ---------------------------------------------------------------- timestep sinusoid
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int n, int dim, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();  // PDL: inputs are produced by the preceding kernel
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * half) return;
@@ -136,6 +148,8 @@ template <typename T, int RC>
 __global__ void small_linear_kernel(const float* __restrict__ x, int ldx, const T* __restrict__ w,
                                     const float* __restrict__ bias, float* __restrict__ y, int ldy, int rows, int n,
                                     int k, int silu_in, int silu_out, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();  // PDL: inputs are produced by the preceding kernel
   const int lane = threadIdx.x & 31;
   const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (col >= n) return;
@@ -186,6 +200,8 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int ldx, const 
 __global__ void cfg_ddim_kernel(const float* __restrict__ eps, float* __restrict__ lat,
                                 const float* __restrict__ guidance, const float* __restrict__ coef,
                                 float* __restrict__ eps_out, int imgs, int chw) {
+  pdl_launch_dependents();
+  pdl_wait();  // PDL: inputs are produced by the preceding kernel
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(imgs) * chw) return;
   const int img = static_cast<int>(i / chw);
@@ -214,9 +230,9 @@ extern "C" int es_nchw_to_nhwc(int dtype, const float* src, void* dst, int n, in
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(ceil_div(hw, 32), ceil_div(static_cast<int>(ldd), 32), n), block(32, 8);
   if (dtype == ES_DTYPE_BF16)
-    nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), c, hw, ldd);
+    ES_CUDA(launch_kernel(nchw_to_nhwc_kernel<__nv_bfloat16>, dim3(grid), dim3(block), 0, s, src, reinterpret_cast<__nv_bfloat16*>(dst), c, hw, ldd));
   else
-    nchw_to_nhwc_kernel<__half><<<grid, block, 0, s>>>(src, reinterpret_cast<__half*>(dst), c, hw, ldd);
+    ES_CUDA(launch_kernel(nchw_to_nhwc_kernel<__half>, dim3(grid), dim3(block), 0, s, src, reinterpret_cast<__half*>(dst), c, hw, ldd));
   ES_CUDA(cudaGetLastError());
   return 0;
 }
@@ -225,9 +241,9 @@ extern "C" int es_nhwc_to_nchw(int dtype, const void* src, long long lds, float*
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), n), block(32, 8);
   if (dtype == ES_DTYPE_BF16)
-    nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), lds, dst, c, hw);
+    ES_CUDA(launch_kernel(nhwc_to_nchw_kernel<__nv_bfloat16>, dim3(grid), dim3(block), 0, s, reinterpret_cast<const __nv_bfloat16*>(src), lds, dst, c, hw));
   else
-    nhwc_to_nchw_kernel<__half><<<grid, block, 0, s>>>(reinterpret_cast<const __half*>(src), lds, dst, c, hw);
+    ES_CUDA(launch_kernel(nhwc_to_nchw_kernel<__half>, dim3(grid), dim3(block), 0, s, reinterpret_cast<const __half*>(src), lds, dst, c, hw));
   ES_CUDA(cudaGetLastError());
   return 0;
 }
@@ -241,11 +257,11 @@ extern "C" int es_im2col3x3(int dtype, const void* src, long long lds, void* dst
   const long long total = static_cast<long long>(n) * ho * wo * ((c % 8 == 0) ? 9 * (c / 8) : ldo);
   const int g = grid_for(total, 256);
   if (dtype == ES_DTYPE_BF16)
-    im2col3x3_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), lds,
-                                                      reinterpret_cast<__nv_bfloat16*>(dst), ldo, n, h, w, c, stride, ho, wo);
+    ES_CUDA(launch_kernel(im2col3x3_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, s, reinterpret_cast<const __nv_bfloat16*>(src), lds,
+                                                      reinterpret_cast<__nv_bfloat16*>(dst), ldo, n, h, w, c, stride, ho, wo));
   else
-    im2col3x3_kernel<__half><<<g, 256, 0, s>>>(reinterpret_cast<const __half*>(src), lds, reinterpret_cast<__half*>(dst),
-                                               ldo, n, h, w, c, stride, ho, wo);
+    ES_CUDA(launch_kernel(im2col3x3_kernel<__half>, dim3(g), dim3(256), 0, s, reinterpret_cast<const __half*>(src), lds, reinterpret_cast<__half*>(dst),
+                                               ldo, n, h, w, c, stride, ho, wo));
   ES_CUDA(cudaGetLastError());
   return 0;
 }
@@ -256,11 +272,11 @@ extern "C" int es_upsample2x(int dtype, const void* src, long long lds, void* ds
   const long long total = static_cast<long long>(n) * 4 * h * w * (c / 8);
   const int g = grid_for(total, 256);
   if (dtype == ES_DTYPE_BF16)
-    upsample2x_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), lds,
-                                                       reinterpret_cast<__nv_bfloat16*>(dst), ldd, n, h, w, c);
+    ES_CUDA(launch_kernel(upsample2x_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, s, reinterpret_cast<const __nv_bfloat16*>(src), lds,
+                                                       reinterpret_cast<__nv_bfloat16*>(dst), ldd, n, h, w, c));
   else
-    upsample2x_kernel<__half><<<g, 256, 0, s>>>(reinterpret_cast<const __half*>(src), lds, reinterpret_cast<__half*>(dst),
-                                                ldd, n, h, w, c);
+    ES_CUDA(launch_kernel(upsample2x_kernel<__half>, dim3(g), dim3(256), 0, s, reinterpret_cast<const __half*>(src), lds, reinterpret_cast<__half*>(dst),
+                                                ldd, n, h, w, c));
   ES_CUDA(cudaGetLastError());
   return 0;
 }
@@ -271,12 +287,12 @@ extern "C" int es_add(int dtype, const void* a, long long lda, const void* b, lo
   const long long total = static_cast<long long>(rows) * (c / 8);
   const int g = grid_for(total, 256);
   if (dtype == ES_DTYPE_BF16)
-    add_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(a), lda,
+    ES_CUDA(launch_kernel(add_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, s, reinterpret_cast<const __nv_bfloat16*>(a), lda,
                                                 reinterpret_cast<const __nv_bfloat16*>(b), ldb,
-                                                reinterpret_cast<__nv_bfloat16*>(out), ldo, rows, c);
+                                                reinterpret_cast<__nv_bfloat16*>(out), ldo, rows, c));
   else
-    add_kernel<__half><<<g, 256, 0, s>>>(reinterpret_cast<const __half*>(a), lda, reinterpret_cast<const __half*>(b), ldb,
-                                         reinterpret_cast<__half*>(out), ldo, rows, c);
+    ES_CUDA(launch_kernel(add_kernel<__half>, dim3(g), dim3(256), 0, s, reinterpret_cast<const __half*>(a), lda, reinterpret_cast<const __half*>(b), ldb,
+                                         reinterpret_cast<__half*>(out), ldo, rows, c));
   ES_CUDA(cudaGetLastError());
   return 0;
 }
@@ -284,7 +300,7 @@ extern "C" int es_timestep_embedding(const float* t, int n, int dim, float* out,
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   ES_CHECK(dim % 2 == 0, "es_timestep_embedding: dim must be even");
   const int total = n * dim / 2;
-  timestep_embedding_kernel<<<ceil_div(total, 128), 128, 0, s>>>(t, n, dim, out);
+  ES_CUDA(launch_kernel(timestep_embedding_kernel, dim3(ceil_div(total, 128)), dim3(128), 0, s, t, n, dim, out));
   ES_CUDA(cudaGetLastError());
   return 0;
 }
@@ -295,11 +311,11 @@ extern "C" int es_small_linear(int dtype, const float* x, int ldx, const void* w
   const int warps = 4;
   dim3 grid(ceil_div(n, warps)), block(warps * 32);
   if (dtype == ES_DTYPE_BF16)
-    small_linear_kernel<__nv_bfloat16, 8><<<grid, block, 0, s>>>(x, ldx, reinterpret_cast<const __nv_bfloat16*>(w), bias,
-                                                                 y, ldy, rows, n, k, silu_in, silu_out, accumulate);
+    ES_CUDA(launch_kernel(small_linear_kernel<__nv_bfloat16, 8>, dim3(grid), dim3(block), 0, s, x, ldx, reinterpret_cast<const __nv_bfloat16*>(w), bias,
+                                                                 y, ldy, rows, n, k, silu_in, silu_out, accumulate));
   else
-    small_linear_kernel<__half, 8><<<grid, block, 0, s>>>(x, ldx, reinterpret_cast<const __half*>(w), bias, y, ldy, rows,
-                                                          n, k, silu_in, silu_out, accumulate);
+    ES_CUDA(launch_kernel(small_linear_kernel<__half, 8>, dim3(grid), dim3(block), 0, s, x, ldx, reinterpret_cast<const __half*>(w), bias, y, ldy, rows,
+                                                          n, k, silu_in, silu_out, accumulate));
   ES_CUDA(cudaGetLastError());
   return 0;
 }
@@ -307,7 +323,7 @@ extern "C" int es_cfg_ddim(const float* eps, float* latents, const float* guidan
                            int imgs, int chw, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const long long total = static_cast<long long>(imgs) * chw;
-  cfg_ddim_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(eps, latents, guidance, coef, eps_out, imgs, chw);
+  ES_CUDA(launch_kernel(cfg_ddim_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, s, eps, latents, guidance, coef, eps_out, imgs, chw));
   ES_CUDA(cudaGetLastError());
   return 0;
 }

@@ -69,6 +69,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __shared__ uint32_t tmem_base_smem;
   __shared__ int splitk_last;
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
@@ -130,6 +131,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // PDL: everything above (barrier init, TMEM alloc, descriptor prefetch) overlaps the previous kernel's tail;
+  // global memory written by it may only be touched after this point.
+  pdl_wait();
 
   if (warp == 0) {
     // =============================== TMA producer ===========================================
@@ -303,10 +307,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       } else {
+        // software pipeline: the residual (global) and accumulator (TMEM) loads of chunk c+1 are in flight while
+        // chunk c is converted and stored
+        const bool res_vec = p.residual != nullptr && row_ok;
+        const T* rbase = reinterpret_cast<const T*>(p.residual) + (res_vec ? row * p.ldr + n0 : 0);
+        uint4 rn0 = make_uint4(0, 0, 0, 0), rn1 = make_uint4(0, 0, 0, 0);
+        auto fetch_res = [&](int c) {
+          if (res_vec && n0 + c + 16 <= p.N) {
+            rn0 = reinterpret_cast<const uint4*>(rbase + c)[0];
+            rn1 = reinterpret_cast<const uint4*>(rbase + c)[1];
+          }
+        };
+        uint32_t vn[16];
+        fetch_res(0);
+        if (!from_ws) {
+          tmem_ld_x16(t_row, vn);
+        }
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N; c += 16) {
           float o[16];
-          load_cols(c, o);
+          const uint4 r0 = rn0, r1 = rn1;
+          if (!from_ws) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(vn[j]);
+            if (c + 16 < BLOCK_N) tmem_ld_x16(t_row + c + 16, vn);
+          } else {
+            load_cols(c, o);
+          }
+          if (c + 16 < BLOCK_N) fetch_res(c + 16);
           if (row_ok && n0 + c < p.N) {
             const int valid = p.N - (n0 + c);
             const bool full = valid >= 16;
@@ -324,10 +353,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < 16; ++j) o[j] *= p.alpha;
             if (p.residual) {
-              const T* rp = reinterpret_cast<const T*>(p.residual) + row * p.ldr + n0 + c;
               if (full) {
-                uint4 r0 = reinterpret_cast<const uint4*>(rp)[0];
-                uint4 r1 = reinterpret_cast<const uint4*>(rp)[1];
                 const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -336,6 +362,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   o[2 * j + 1] += f.y;
                 }
               } else {
+                const T* rp = reinterpret_cast<const T*>(p.residual) + row * p.ldr + n0 + c;
                 for (int j = 0; j < 16; ++j)
                   if (j < valid) o[j] += Cvt<T>::to_f(rp[j]);
               }
@@ -384,8 +411,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   if (g->workspace && g->split_k != 1) {
     if (g->split_k > 1) {
       splits = g->split_k;
-    } else if (tiles <= 96 && kb_total >= 16) {
-      splits = (2 * 148 + tiles - 1) / tiles;
+    } else if (tiles <= 148 && kb_total >= 16) {
+      // fill at most ONE wave of 2 CTAs/SM (a second, nearly empty wave would double the time)
+      splits = (2 * 148) / tiles;
       if (splits > kb_total / 6) splits = kb_total / 6;
       if (splits > 32) splits = 32;
       if (splits < 1) splits = 1;
@@ -411,7 +439,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     attr_smem = smem;
   }
   dim3 grid(m_tiles, n_tiles, splits);
-  kern<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, tmA2, tmB2, kp);
+  ES_CUDA(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, tmA2, tmB2, kp));
   ES_CUDA(cudaGetLastError());
   return 0;
 }
@@ -427,7 +455,7 @@ static int pick_block_n(int n, int m_tiles, int act) {
     const int nt = ceil_div(n, bn);
     const double waste = static_cast<double>(nt) * bn / n;  // >= 1
     const int ctas = nt * m_tiles;
-    const int waves = ceil_div(ctas, 148);
+    const int waves = ceil_div(ctas, 296);  // two CTAs per SM
     // time ~ waves * (per-tile time ~ bn + fixed overhead)
     const double cost = waves * (bn + 48.0) * (0.9 + 0.1 * waste);
     if (cost < best_cost) {

@@ -60,6 +60,8 @@ __device__ __forceinline__ void block_reduce2_to_global(float a, float b, double
 // grid (chunks, B); block (C/8, ny). PHASE 1: stats of u. PHASE 2: z + stats of z. PHASE 3: output.
 template <typename T, int PHASE>
 __global__ void merge_kernel(const MergeK k) {
+  pdl_launch_dependents();
+  pdl_wait();  // PDL: inputs are produced by the preceding kernel
   const int v = threadIdx.x;
   const int ch = v * 8;
   const int b = blockIdx.y;
@@ -195,9 +197,9 @@ static int merge_t(const EsMerge* m, int phase, cudaStream_t s) {
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   dim3 grid(chunks, m->B, 1);
-  if (phase == 1) merge_kernel<T, 1><<<grid, block, 0, s>>>(k);
-  else if (phase == 2) merge_kernel<T, 2><<<grid, block, 0, s>>>(k);
-  else merge_kernel<T, 3><<<grid, block, 0, s>>>(k);
+  if (phase == 1) ES_CUDA(launch_kernel(merge_kernel<T, 1>, dim3(grid), dim3(block), 0, s, k));
+  else if (phase == 2) ES_CUDA(launch_kernel(merge_kernel<T, 2>, dim3(grid), dim3(block), 0, s, k));
+  else ES_CUDA(launch_kernel(merge_kernel<T, 3>, dim3(grid), dim3(block), 0, s, k));
   ES_CUDA(cudaGetLastError());
   return 0;
 }

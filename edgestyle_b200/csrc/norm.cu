@@ -24,6 +24,8 @@ __device__ __forceinline__ void store8(T* p, const float (&f)[8]) {
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ x0, int c0, long long ld0, const T* __restrict__ x1, int c1,
                                 long long ld1, int hw, int groups, float* __restrict__ ws) {
+  pdl_launch_dependents();
+  pdl_wait();  // PDL: inputs are produced by the preceding kernel
   extern __shared__ float sm[];  // [C][2]
   const int C = c0 + c1;
   const int cpg = C / groups;
@@ -48,13 +50,32 @@ __global__ void gn_stats_kernel(const T* __restrict__ x0, int c0, long long ld0,
   const int per = (hw + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per;
   const int p1 = min(hw, p0 + per);
-  for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
-    float f[8];
-    load8<T>(src + static_cast<long long>(p) * ld, f);
+  {
+    const int ny = blockDim.y;
+    int p = p0 + threadIdx.y;
+    for (; p + 3 * ny < p1; p += 4 * ny) {  // four independent 16 B loads in flight per thread
+      uint4 u[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s[j] += f[j];
-      ss[j] += f[j] * f[j];
+      for (int q = 0; q < 4; ++q) u[q] = *reinterpret_cast<const uint4*>(src + static_cast<long long>(p + q * ny) * ld);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t w[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = Cvt<T>::unpack2(w[j]);
+          s[2 * j] += f.x; ss[2 * j] += f.x * f.x;
+          s[2 * j + 1] += f.y; ss[2 * j + 1] += f.y * f.y;
+        }
+      }
+    }
+    for (; p < p1; p += ny) {
+      float f[8];
+      load8<T>(src + static_cast<long long>(p) * ld, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        ss[j] += f[j] * f[j];
+      }
     }
   }
 #pragma unroll
@@ -79,6 +100,8 @@ __global__ void gn_apply_kernel(const T* __restrict__ x0, int c0, long long ld0,
                                 long long ld1, int hw, int groups, float eps, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ ws, T* __restrict__ out,
                                 long long ldo, int silu) {
+  pdl_launch_dependents();
+  pdl_wait();  // PDL: inputs are produced by the preceding kernel
   const int C = c0 + c1;
   const int cpg = C / groups;
   const int v = threadIdx.x;
@@ -110,7 +133,31 @@ __global__ void gn_apply_kernel(const T* __restrict__ x0, int c0, long long ld0,
   const int per = (hw + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per;
   const int p1 = min(hw, p0 + per);
-  for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+  const int ny = blockDim.y;
+  int p = p0 + threadIdx.y;
+  for (; p + 3 * ny < p1; p += 4 * ny) {
+    uint4 u[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) u[q] = *reinterpret_cast<const uint4*>(src + static_cast<long long>(p + q * ny) * ld);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t w[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = Cvt<T>::unpack2(w[j]);
+        f[2 * j] = t.x;
+        f[2 * j + 1] = t.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float y = f[j] * a[j] + b[j];
+        f[j] = silu ? silu_f(y) : y;
+      }
+      store8<T>(dst + static_cast<long long>(p + q * ny) * ldo, f);
+    }
+  }
+  for (; p < p1; p += ny) {
     float f[8];
     load8<T>(src + static_cast<long long>(p) * ld, f);
 #pragma unroll
@@ -138,6 +185,7 @@ static void gn_geometry(const EsGroupNorm* g, dim3& grid, dim3& block) {
   if (ny < 1) ny = 1;
   if (ny > g->hw) ny = g->hw;
   block = dim3(vpp, ny, 1);
+  // >= 4 pixels per thread (four independent 16 B loads in flight, per-thread prologue amortised), ~4 blocks per SM
   int chunks = (4 * 148 + g->n_img - 1) / g->n_img;
   const int max_chunks = (g->hw + ny * 4 - 1) / (ny * 4);
   if (chunks > max_chunks) chunks = max_chunks;
@@ -150,9 +198,9 @@ static int gn_stats_t(const EsGroupNorm* g, cudaStream_t s) {
   dim3 grid, block;
   gn_geometry(g, grid, block);
   const size_t smem = static_cast<size_t>(g->c0 + g->c1) * 2 * sizeof(float);
-  gn_stats_kernel<T><<<grid, block, smem, s>>>(reinterpret_cast<const T*>(g->x0), g->c0, g->ld0,
+  ES_CUDA(launch_kernel(gn_stats_kernel<T>, dim3(grid), dim3(block), smem, s, reinterpret_cast<const T*>(g->x0), g->c0, g->ld0,
                                                reinterpret_cast<const T*>(g->x1), g->c1, g->ld1, g->hw, g->groups,
-                                               g->ws);
+                                               g->ws));
   ES_CUDA(cudaGetLastError());
   return 0;
 }
@@ -161,61 +209,78 @@ static int gn_apply_t(const EsGroupNorm* g, cudaStream_t s) {
   dim3 grid, block;
   gn_geometry(g, grid, block);
   ES_CHECK(g->out && g->ldo % 8 == 0 && g->gamma && g->beta, "es_groupnorm_apply: bad output/affine");
-  gn_apply_kernel<T><<<grid, block, 0, s>>>(reinterpret_cast<const T*>(g->x0), g->c0, g->ld0,
+  ES_CUDA(launch_kernel(gn_apply_kernel<T>, dim3(grid), dim3(block), 0, s, reinterpret_cast<const T*>(g->x0), g->c0, g->ld0,
                                             reinterpret_cast<const T*>(g->x1), g->c1, g->ld1, g->hw, g->groups, g->eps,
-                                            g->gamma, g->beta, g->ws, reinterpret_cast<T*>(g->out), g->ldo, g->silu);
+                                            g->gamma, g->beta, g->ws, reinterpret_cast<T*>(g->out), g->ldo, g->silu));
   ES_CUDA(cudaGetLastError());
   return 0;
 }
 
-// ---------------------------------------------------------------- LayerNorm: one warp per row
-template <typename T, int MAXV>
+// ---------------------------------------------------------------- LayerNorm: warps own rows, R rows in flight
+template <typename T, int MAXV, int R>
 __global__ void layernorm_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ out, long long ldo,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int c,
                                  float eps) {
+  pdl_launch_dependents();
+  pdl_wait();  // PDL: inputs are produced by the preceding kernel
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+  if (row0 >= rows) return;
   const int nv = c >> 3;
-  const T* src = x + static_cast<long long>(row) * ldx;
-  float f[MAXV][8];
-  float s = 0.f;
+  uint4 u[R][MAXV];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int v = lane + i * 32;
-    if (v < nv) {
-      load8<T>(src + v * 8, f[i]);
+  for (int r = 0; r < R; ++r) {
+    const T* src = x + static_cast<long long>(min(row0 + r, rows - 1)) * ldx;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += f[i][j];
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      u[r][i] = v < nv ? *reinterpret_cast<const uint4*>(src + v * 8) : make_uint4(0, 0, 0, 0);
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / c;
-  float q = 0.f;
+  for (int r = 0; r < R; ++r) {
+    float f[MAXV][8];
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int v = lane + i * 32;
-    if (v < nv) {
+    for (int i = 0; i < MAXV; ++i) {
+      const uint32_t w[4] = {u[r][i].x, u[r][i].y, u[r][i].z, u[r][i].w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = f[i][j] - mean;
-        q += d * d;
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = Cvt<T>::unpack2(w[j]);
+        f[i][2 * j] = t.x;
+        f[i][2 * j + 1] = t.y;
+        s += t.x + t.y;
       }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / c + eps);
-  T* dst = out + static_cast<long long>(row) * ldo;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / c;
+    float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int v = lane + i * 32;
-    if (v < nv) {
-      float o[8];
+    for (int i = 0; i < MAXV; ++i) {
+      if (lane + i * 32 < nv) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * gamma[v * 8 + j] + beta[v * 8 + j];
-      store8<T>(dst + v * 8, o);
+        for (int j = 0; j < 8; ++j) {
+          const float d = f[i][j] - mean;
+          q += d * d;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / c + eps);
+    if (row0 + r < rows) {
+      T* dst = out + static_cast<long long>(row0 + r) * ldo;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + i * 32;
+        if (v < nv) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * __ldg(gamma + v * 8 + j) + __ldg(beta + v * 8 + j);
+          store8<T>(dst + v * 8, o);
+        }
+      }
     }
   }
 }
@@ -225,18 +290,22 @@ static int layernorm_t(const void* x, long long ldx, void* out, long long ldo, c
                        int rows, int c, float eps, cudaStream_t s) {
   ES_CHECK(c % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && c <= 8 * 32 * 8, "es_layernorm: unsupported c=%d", c);
   const int warps = 8;
-  dim3 grid((rows + warps - 1) / warps), block(warps * 32);
   const int nv = c / 8;
-  if (nv <= 32 * 2)
-    layernorm_kernel<T, 2><<<grid, block, 0, s>>>(reinterpret_cast<const T*>(x), ldx, reinterpret_cast<T*>(out), ldo,
-                                                  gamma, beta, rows, c, eps);
-  else if (nv <= 32 * 5)
-    layernorm_kernel<T, 5><<<grid, block, 0, s>>>(reinterpret_cast<const T*>(x), ldx, reinterpret_cast<T*>(out), ldo,
-                                                  gamma, beta, rows, c, eps);
-  else
-    layernorm_kernel<T, 8><<<grid, block, 0, s>>>(reinterpret_cast<const T*>(x), ldx, reinterpret_cast<T*>(out), ldo,
-                                                  gamma, beta, rows, c, eps);
-  ES_CUDA(cudaGetLastError());
+  const T* xp = reinterpret_cast<const T*>(x);
+  T* op = reinterpret_cast<T*>(out);
+  // rows in flight per warp: more when there are plenty of rows (64x64 / 32x32 levels), else 1
+  const bool many = rows >= 8192;
+  const int R = many ? (nv <= 64 ? 4 : 2) : 1;
+  dim3 grid((rows + warps * R - 1) / (warps * R)), block(warps * 32);
+  if (nv <= 32 * 2) {
+    if (many) ES_CUDA(launch_kernel(layernorm_kernel<T, 2, 4>, grid, block, 0, s, xp, ldx, op, ldo, gamma, beta, rows, c, eps));
+    else ES_CUDA(launch_kernel(layernorm_kernel<T, 2, 1>, grid, block, 0, s, xp, ldx, op, ldo, gamma, beta, rows, c, eps));
+  } else if (nv <= 32 * 5) {
+    if (many) ES_CUDA(launch_kernel(layernorm_kernel<T, 5, 2>, grid, block, 0, s, xp, ldx, op, ldo, gamma, beta, rows, c, eps));
+    else ES_CUDA(launch_kernel(layernorm_kernel<T, 5, 1>, grid, block, 0, s, xp, ldx, op, ldo, gamma, beta, rows, c, eps));
+  } else {
+    ES_CUDA(launch_kernel(layernorm_kernel<T, 8, 1>, grid, block, 0, s, xp, ldx, op, ldo, gamma, beta, rows, c, eps));
+  }
   return 0;
 }
 

@@ -259,9 +259,13 @@ class DenoiseEngine:
             raise NotImplementedError(f"load_pattern {pattern}: only {SUPPORTED_PATTERN} (app.py:40) is supported")
         if not torch.cuda.is_available():
             raise RuntimeError("DenoiseEngine needs a CUDA device: there is no CPU fallback")
+        import os
+
         from .ext import load
 
-        load()  # fail loudly if the native library is missing
+        lib = load()  # fail loudly if the native library is missing
+        # programmatic dependent launch between consecutive kernels of the step (ES_PDL=0 disables)
+        lib.es_set_pdl(1 if os.environ.get("ES_PDL", "1") != "0" else 0)
         self.cfg = cfg = C.UNetConfig.from_any(cfg)
         self.B, self.h, self.w, self.dtype, self.dev, self.n_text = rows, h, w, dtype, torch.device(device), n_text
         self.levels = C.level_sizes(h, w, len(cfg.block_out_channels))
@@ -402,8 +406,14 @@ class DenoiseEngine:
         self.ctx_base = self.buf("ctx_base", 4 * B * self.n_text, cfg.cross_attention_dim)
         self.ctx_pose = self.ctx_base[: 3 * B * self.n_text]
         self.ctx_dec = self.ctx_base[: B * self.n_text]
-        self.gn_ws = torch.zeros(4 * B, cfg.norm_num_groups, 2, device=self.dev, dtype=torch.float32)
-        self.merge_stats = torch.zeros(B, 4, device=self.dev, dtype=torch.float64)
+        # one pool of reduction scratch for the whole step, zeroed by ONE memset at the start of the step: every
+        # GroupNorm call / merge block takes its own slot (no per-call memset launches inside the graph)
+        self._gn_slot_floats = 4 * B * cfg.norm_num_groups * 2
+        self.scratch = torch.zeros(256 * self._gn_slot_floats * 4 + 32 * B * 4 * 8, device=self.dev, dtype=torch.uint8)
+        self.gn_pool = self.scratch[: 256 * self._gn_slot_floats * 4].view(torch.float32)
+        self.merge_pool = self.scratch[256 * self._gn_slot_floats * 4:].view(torch.float64).view(32, B, 4)
+        self._gn_next = 0
+        self._merge_next = 0
         self.coef = torch.zeros(4, device=self.dev, dtype=torch.float32)
         self.guidance = torch.ones(max(B // 2, 1), device=self.dev, dtype=torch.float32)
 
@@ -424,10 +434,24 @@ class DenoiseEngine:
             assert c.shape == (B, self.cfg.block_out_channels[0], self.h, self.w), c.shape
             ops.nchw_to_nhwc(c.to(device=self.dev, dtype=torch.float32).contiguous(), self.conds[k * B * hw:(k + 1) * B * hw])
 
+    def _begin_step_scratch(self):
+        self.scratch.zero_()
+        self._gn_next = 0
+        self._merge_next = 0
+
+    def _merge_slot(self):
+        s = self.merge_pool[self._merge_next]
+        self._merge_next += 1
+        return s
+
     # ------------------------------------------------------------------------------------ layers
     def _gn(self, x, out, g, b, imgs, hw, silu, eps=None):
-        ops.groupnorm(x, out, g, b, self.gn_ws[:imgs], imgs, hw, self.cfg.norm_num_groups,
-                      self.cfg.norm_eps if eps is None else eps, silu)
+        G = self.cfg.norm_num_groups
+        if self._gn_next >= 256:
+            raise RuntimeError("GroupNorm scratch pool exhausted")
+        ws = self.gn_pool[self._gn_next * self._gn_slot_floats:][: imgs * G * 2].view(imgs, G, 2)
+        self._gn_next += 1
+        ops.groupnorm(x, out, g, b, ws, imgs, hw, G, self.cfg.norm_eps if eps is None else eps, silu, zero_ws=False)
         return out
 
     def _lin(self, L: Lin, a, out, rows_per_img: int, lora_seg_imgs: Optional[Sequence[int]], tag: str, **ep):
@@ -559,6 +583,7 @@ class DenoiseEngine:
         boc = cfg.block_out_channels
         c0 = boc[0]
         nt = self.n_text
+        self._begin_step_scratch()
         # -- sample: NCHW fp32 -> NHWC, im2col (K = 36 padded to 64)
         s16 = self.buf("sample16", B * hw, 8)
         ops.nchw_to_nhwc(self.sample_in, s16)
@@ -611,14 +636,15 @@ class DenoiseEngine:
             z = self.buf(f"merge_z{li}", n, c, torch.float32)
             if mode == "residuals":
                 dst = self.buf(f"res_out{li}", n, c)
-                ops.merge(res, scale, self.merge[li], self.merge_stats, z, B, H * W, c, dst, skip=None)
+                ops.merge(res, scale, self.merge[li], self._merge_slot(), z, B, H * W, c, dst, skip=None, zero_stats=False)
                 continue
             if li < len(self.res_shapes) - 1:
                 cbuf, xc = cat_of_skip[li]
                 dst = cbuf[:, xc:]
             else:  # mid: becomes the x half of the first decoder concat
                 dst = cats[(0, 0)][0][:, :c]
-            ops.merge(res, scale, self.merge[li], self.merge_stats, z, B, H * W, c, dst, skip=all_b[li][:n])
+            ops.merge(res, scale, self.merge[li], self._merge_slot(), z, B, H * W, c, dst, skip=all_b[li][:n],
+                      zero_stats=False)
         if mode == "residuals":
             return
         # -- UNet decoder
@@ -716,6 +742,7 @@ class DenoiseEngine:
         cfg, B, h, w = self.cfg, self.B, self.h, self.w
         hw, c0, nt = h * w, cfg.block_out_channels[0], self.n_text
         self._load_sample_t(sample, timestep)
+        self._begin_step_scratch()
         s16 = self.buf("sample16", B * hw, 8)
         ops.nchw_to_nhwc(self.sample_in, s16)
         col = self.buf("sample_col", B * hw, 64)

@@ -59,6 +59,7 @@ class EsMerge(C.Structure):
 EXPORTS = {
     "es_last_error": (C.c_char_p, []),
     "es_abi_version": (C.c_int, []),
+    "es_set_pdl": (C.c_int, [C.c_int]),
     "es_gemm": (C.c_int, [C.POINTER(EsGemm), vp]),
     "es_attention": (C.c_int, [C.POINTER(EsAttention), vp]),
     "es_groupnorm_stats": (C.c_int, [C.POINTER(EsGroupNorm), vp]),

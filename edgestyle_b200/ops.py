@@ -131,8 +131,10 @@ def attention(q, k, v, out, batch: int, heads: int, nq: int, nkv: int, scale: Op
     return out
 
 
-def groupnorm(x0, out, gamma, beta, ws, n_img: int, hw: int, groups: int, eps: float, silu: bool, x1=None):
-    """GroupNorm(+SiLU) over [n_img*hw, c0(+c1)]; ws: fp32 [n_img, groups, 2] scratch (zeroed here)."""
+def groupnorm(x0, out, gamma, beta, ws, n_img: int, hw: int, groups: int, eps: float, silu: bool, x1=None,
+              zero_ws: bool = True):
+    """GroupNorm(+SiLU) over [n_img*hw, c0(+c1)]; ws: fp32 [n_img, groups, 2] scratch (zeroed here unless the
+    caller hands in an already-zero slot, `zero_ws=False`)."""
     _need_cuda(x0, out, ws)
     g = EsGroupNorm()
     g.dtype = _dt(x0)
@@ -144,7 +146,8 @@ def groupnorm(x0, out, gamma, beta, ws, n_img: int, hw: int, groups: int, eps: f
     g.ws = ws.data_ptr()
     g.out, g.ldo = out.data_ptr(), out.stride(0)
     g.silu = 1 if silu else 0
-    ws.zero_()
+    if zero_ws:
+        ws.zero_()
     lib = load()
     _count(2)  # stats + apply (the workspace memset is torch's)
     check(lib.es_groupnorm_stats(C.byref(g), _stream()), "es_groupnorm_stats")
@@ -161,7 +164,7 @@ def layernorm(x, out, gamma, beta, eps: float = 1e-5):
 
 
 def merge(res: Sequence[torch.Tensor], scale: Sequence[float], prm: dict, stats, z, B: int, hw: int, Cc: int, dst,
-          skip=None):
+          skip=None, zero_stats: bool = True):
     """EdgeStyle ControlNetBlock over six [B*hw, C] residual slabs; dst = skip + block(res)."""
     m = EsMerge()
     m.dtype = _dt(res[0])
@@ -175,7 +178,8 @@ def merge(res: Sequence[torch.Tensor], scale: Sequence[float], prm: dict, stats,
     if skip is not None:
         m.skip, m.lds = skip.data_ptr(), skip.stride(0)
     m.dst, m.ldd = dst.data_ptr(), dst.stride(0)
-    stats.zero_()
+    if zero_stats:
+        stats.zero_()
     lib = load()
     _count(3)  # three phases (the stats memset is torch's)
     for ph in (1, 2, 3):

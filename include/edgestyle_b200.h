@@ -28,6 +28,10 @@ extern "C" {
 
 const char* es_last_error(void);
 int es_abi_version(void);
+/* Programmatic dependent launch for every kernel of the library (off by default): each kernel's prologue then
+ * overlaps the previous kernel's tail and it waits (griddepcontrol.wait) before its first global access.
+ * Returns the previous setting. */
+int es_set_pdl(int enabled);
 
 /* ------------------------------------------------------------------------------------------
  * es_gemm: tcgen05/TMEM implicit-GEMM for conv3x3(stride 1, pad 1) / conv1x1 / Linear.
