@@ -276,7 +276,10 @@ class DenoiseEngine:
         for i, c in enumerate(cfg.block_out_channels):
             if c % 8 or c % cfg.norm_num_groups or (c // cfg.num_heads) % 8:
                 raise ValueError(f"channel count {c} unsupported (needs %8, %groups, head_dim %8)")
-        ops.set_gemm_workspace(256 << 20, self.dev)  # split-K scratch shared by all GEMM launches of the stream
+        ops.set_gemm_workspace(256 << 20, self.dev)  # split-K scratch of the main stream
+        self._side_stream = torch.cuda.Stream(device=self.dev)
+        self._side_ws = torch.zeros(128 << 20, dtype=torch.uint8, device=self.dev)
+        ops.set_stream_workspace(self._side_stream, self._side_ws)  # concurrent launches must not share scratch
         self._pack(unet_sd, lora_sds, pose_sd, merge_sd)
         self._alloc_static()
 
@@ -594,19 +597,35 @@ class DenoiseEngine:
         enc_cols = Eb.temb_cols
         temb_base = self._time_path(Eb, [(0, B), (1, B), (2, 2 * B)], "base",
                                     [enc_cols + self.dec_temb_cols, enc_cols, enc_cols])
-        temb_pose = self._time_path(Ep, [(0, 3 * B)], "pose", [Ep.temb_cols])
+        cond = lambda k: self.conds[k * B * hw:(k + 1) * B * hw]
+        # -- the two batched encoder passes are independent: the pose pass (time path, conv_in, encoder, zero-convs)
+        #    runs on a second stream and fills the SMs that the base pass's partial waves leave idle
+        main = torch.cuda.current_stream()
+        side = self._side_stream
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            temb_pose = self._time_path(Ep, [(0, 3 * B)], "pose", [Ep.temb_cols])
+            xp = self.buf("pose.x0", 3 * B * hw, c0)
+            for slot, k in ((0, 1), (1, 3), (2, 5)):
+                ops.gemm(col, Ep.conv_in, c0, out=xp[slot * B * hw:(slot + 1) * B * hw], bias=Ep.conv_in_b,
+                         residual=cond(k))
+            skips_p, mid_p = self._encoder(Ep, xp, 3 * B, temb_pose, self.ctx_pose, None, "pose")
+            zres_p = []
+            for li, ((c, H, W), src) in enumerate(zip(self.res_shapes, skips_p + [mid_p])):
+                rp = self.buf(f"zres_p{li}", 3 * B * H * W, c)
+                ops.gemm(src, self.zero_pose[li][0], c, out=rp, bias=self.zero_pose[li][1])
+                zres_p.append(rp)
+            join = torch.cuda.Event()
+            join.record(side)
         # -- conv_in (+ cached conditioning embedding, controllora.py:197-203)
         xb = self.buf("base.x0", 4 * B * hw, c0)
-        cond = lambda k: self.conds[k * B * hw:(k + 1) * B * hw]
         ops.gemm(col, Eb.conv_in, c0, out=xb[:B * hw], bias=Eb.conv_in_b)
         for slot, k in ((1, 0), (2, 2), (3, 4)):
             ops.gemm(col, Eb.conv_in, c0, out=xb[slot * B * hw:(slot + 1) * B * hw], bias=Eb.conv_in_b, residual=cond(k))
-        xp = self.buf("pose.x0", 3 * B * hw, c0)
-        for slot, k in ((0, 1), (1, 3), (2, 5)):
-            ops.gemm(col, Ep.conv_in, c0, out=xp[slot * B * hw:(slot + 1) * B * hw], bias=Ep.conv_in_b, residual=cond(k))
-        # -- the two batched encoder passes
         skips_b, mid_b = self._encoder(Eb, xb, 4 * B, temb_base, self.ctx_base, (B, B, 2 * B), "base")
-        skips_p, mid_p = self._encoder(Ep, xp, 3 * B, temb_pose, self.ctx_pose, None, "pose")
+        main.wait_event(join)
         # -- decoder concat buffers (x | skip) and their geometry
         rev = list(reversed(boc))
         rev_attn = list(reversed(cfg.down_has_attn))
@@ -624,14 +643,12 @@ class DenoiseEngine:
         # -- zero convs (controllora.py:240-254) + EdgeStyle merge (edgestyle_multicontrolnet.py:160-169)
         scale = [float(s) for s in cond_scale]
         all_b = skips_b + [mid_b]
-        all_p = skips_p + [mid_p]
         for li, (c, H, W) in enumerate(self.res_shapes):
             n = B * H * W
             rb = self.buf(f"zres_b{li}", 3 * n, c)
-            rp = self.buf(f"zres_p{li}", 3 * n, c)
+            rp = zres_p[li]
             zw, zb = self.zero_base[li]
             ops.gemm(all_b[li][n:], zw, c, out=rb, bias=zb, segs=([0, n, 3 * n], [0, c], None))
-            ops.gemm(all_p[li], self.zero_pose[li][0], c, out=rp, bias=self.zero_pose[li][1])
             res = [rb[:n], rp[:n], rb[n:2 * n], rp[n:2 * n], rb[2 * n:], rp[2 * n:]]
             z = self.buf(f"merge_z{li}", n, c, torch.float32)
             if mode == "residuals":

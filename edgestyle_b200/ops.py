@@ -25,6 +25,13 @@ def set_gemm_workspace(nbytes: int = 256 << 20, device="cuda") -> torch.Tensor:
     return GEMM_WORKSPACE
 
 
+STREAM_WORKSPACES = {}  # cuda stream handle -> split-K scratch (concurrent streams must not share one)
+
+
+def set_stream_workspace(stream: "torch.cuda.Stream", ws: torch.Tensor) -> None:
+    STREAM_WORKSPACES[stream.cuda_stream] = ws
+
+
 LAUNCHES = 0  # native kernel launches issued through this module (bench.py reports it as gpu_launches)
 
 
@@ -106,7 +113,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: i
     g.block_n = block_n
     g.stages = stages
     g.split_k = split_k
-    ws = workspace if workspace is not None else GEMM_WORKSPACE
+    ws = workspace if workspace is not None else STREAM_WORKSPACES.get(_stream(), GEMM_WORKSPACE)
     if ws is not None:
         g.workspace = ws.data_ptr()
         g.workspace_bytes = ws.numel() * ws.element_size()
