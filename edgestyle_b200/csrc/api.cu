@@ -34,7 +34,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box) {
+                    const uint32_t* box, bool swizzle128) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return -1;
   cuuint64_t gdim[5];
@@ -48,7 +48,8 @@ int encode_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t
     if (i > 0) gstr[i - 1] = strides_bytes[i];
   }
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
-                  gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] strides [%llu %llu %llu] box [%u %u %u %u] base %p",

@@ -33,7 +33,7 @@ void set_error(const char* fmt, ...);
 // cuTensorMapEncodeTiled resolved through the runtime (no link-time dependency on libcuda).
 // dims/strides innermost first; strides in BYTES for dims 1..rank-1. 16-bit elements, SWIZZLE_128B.
 int encode_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box);
+                    const uint32_t* box, bool swizzle128 = true);
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

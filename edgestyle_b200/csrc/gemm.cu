@@ -10,6 +10,8 @@
 //   smem ring   : `stages` x (A 16 KB + B BLOCK_N*128 B), SWIZZLE_128B, full/empty mbarriers.
 //
 // Replaces the cuDNN/cuBLAS dispatches listed at include/edgestyle_b200.h (es_gemm).
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -18,6 +20,17 @@ namespace es {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kGemmThreads = 192;
+
+// Optional event trace (clock64 stamps of CTA (1,0,0)) for pipeline analysis: build with -DES_GEMM_TRACE.
+#ifdef ES_GEMM_TRACE
+__device__ long long g_gemm_trace[16];
+#define GEMM_TRACE(slot)                                                                        \
+  do {                                                                                          \
+    if (blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0) g_gemm_trace[slot] = clock64();  \
+  } while (0)
+#else
+#define GEMM_TRACE(slot) do {} while (0)
+#endif
 
 struct GemmKParams {
   int W, H, NI;
@@ -47,12 +60,16 @@ struct GemmKParams {
   int splits;            // split-K factor (grid.z)
   float* ws_partial;     // [splits][tiles][128][BLOCK_N] fp32 partial accumulators
   int* ws_counter;       // [tiles] arrival counters (zero on entry, reset by the finishing CTA)
+  int tma_epi;           // 1: epilogue goes regs -> swizzled smem panels -> TMA store (residual via TMA load)
+  int n_out;             // output columns in total (N, or N/2 for GEGLU)
 };
 
 template <typename T, int BLOCK_N>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+            const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmOp,
+            const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmRp,
             const GemmKParams p) {
   constexpr int kABytes = kBlockM * kBlockK * 2;
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
@@ -66,10 +83,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t res_bar;
   __shared__ uint32_t tmem_base_smem;
   __shared__ int splitk_last;
 
   pdl_launch_dependents();
+  if (threadIdx.x == 0) GEMM_TRACE(0);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
@@ -121,6 +140,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&accum_bar, 1);
+    mbar_init(&res_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -134,6 +154,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // PDL: everything above (barrier init, TMEM alloc, descriptor prefetch) overlaps the previous kernel's tail;
   // global memory written by it may only be touched after this point.
   pdl_wait();
+  if (threadIdx.x == 0) GEMM_TRACE(1);
 
   if (warp == 0) {
     // =============================== TMA producer ===========================================
@@ -173,6 +194,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t ph = (it / stages) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        if (it == 0) GEMM_TRACE(2);
         const uint32_t sa = smem_u32(smem + s * kStageBytes);
         const uint32_t sb = sa + kABytes;
         const uint64_t adesc = smem_desc_sw128(sa, 16, 1024);
@@ -184,6 +206,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
       }
+      GEMM_TRACE(3);
       if (has_work) umma_commit(&accum_bar);  // accumulator complete
       else mbar_arrive(&accum_bar);
     }
@@ -209,12 +232,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) GEMM_TRACE(4);
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 
     // ---- split-K: publish this CTA's partial tile; only the last arriver continues to the epilogue ----
     const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
     const long long tiles = static_cast<long long>(gridDim.x) * gridDim.y;
     bool from_ws = false;
+    // A tail tile of a row segment must not store the rows that belong to the next segment: those tiles (and
+    // fp32 outputs) take the per-thread store path below; everything else goes through smem + TMA.
+    const bool use_tma_epi = p.tma_epi && !(p.flat && x0 + kBlockM > x_end && x_end < p.W);
     if (p.splits > 1) {
       // layout [split][tile][BLOCK_N/4][128 rows] float4: a warp's 32 rows store 512 contiguous bytes
       float4* wp = reinterpret_cast<float4*>(p.ws_partial) +
@@ -283,7 +310,96 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       };
 
-      if (p.act == ES_ACT_GEGLU) {
+      if (use_tma_epi) {
+        // ---------------- smem-staged epilogue: 64-column panels [128 rows x 128 B], SWIZZLE_128B ----------------
+        // The pipeline's smem is free (every MMA has retired), so the panels alias the stage buffers.
+        constexpr int NOUT = BLOCK_N;                      // accumulator columns per tile
+        const bool geglu = p.act == ES_ACT_GEGLU;
+        const int n_tile_out = geglu ? NOUT / 2 : NOUT;    // output columns of this tile
+        const int oc0 = geglu ? blockIdx.y * (NOUT / 2) : n0;
+        const int full_panels = n_tile_out / 64;
+        const int rem = n_tile_out % 64;                   // last, narrower panel (unswizzled, pitch rem*2 B)
+        const bool has_res = p.residual != nullptr;
+        if (has_res && threadIdx.x == 64) {
+          mbar_expect_tx(&res_bar, static_cast<uint32_t>(kBlockM * n_tile_out * 2));
+          for (int pn = 0; pn < full_panels; ++pn) tma_load_4d(smem + pn * 16384, &tmR, &res_bar, oc0 + pn * 64, x0, y0, i0);
+          if (rem) tma_load_4d(smem + full_panels * 16384, &tmRp, &res_bar, oc0 + full_panels * 64, x0, y0, i0);
+        }
+        if (has_res) mbar_wait(&res_bar, 0);
+        constexpr int HALF = NOUT / 2;
+#pragma unroll 1
+        for (int c = 0; c < n_tile_out; c += 16) {
+          float o[16];
+          if (geglu) {
+            float a[16], g[16];
+            load_cols(c, a);
+            load_cols(HALF + c, g);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float av = a[j], gv = g[j];
+              if (p.bias) {
+                av += p.bias[b_noff + n0 + c + j];
+                gv += p.bias[b_noff + n0 + HALF + c + j];
+              }
+              o[j] = p.alpha * av * gelu_erf_f(gv);
+            }
+          } else {
+            load_cols(c, o);
+            const int valid = p.N - (n0 + c);  // columns past N are clipped by the TMA store
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < valid) o[j] += p.bias[b_noff + n0 + c + j];
+            }
+            if (p.rowvec && row_ok) {
+              const float* rv = p.rowvec + static_cast<long long>(img) * p.rowvec_ld + n0 + c;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < valid) o[j] += rv[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] *= p.alpha;
+          }
+          // smem location of this thread's 32 bytes (two 16 B chunks)
+          const int pn = c >> 6;
+          uint8_t* pbase = smem + pn * 16384;
+          uint4* d0;
+          uint4* d1;
+          if (pn < full_panels) {
+            const int ch = (c & 63) >> 3;  // 16 B chunk index inside the 128 B row
+            d0 = reinterpret_cast<uint4*>(pbase + r * 128 + ((ch ^ (r & 7)) << 4));
+            d1 = reinterpret_cast<uint4*>(pbase + r * 128 + (((ch + 1) ^ (r & 7)) << 4));
+          } else {
+            d0 = reinterpret_cast<uint4*>(pbase + r * (rem * 2) + (c & 63) * 2);
+            d1 = d0 + 1;
+          }
+          if (has_res) {
+            const uint4 r0 = *d0, r1 = *d1;
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 f = Cvt<T>::unpack2(rr[j]);
+              o[2 * j] += f.x;
+              o[2 * j + 1] += f.y;
+            }
+          }
+          uint4 w0, w1;
+          w0.x = Cvt<T>::pack2(o[0], o[1]); w0.y = Cvt<T>::pack2(o[2], o[3]);
+          w0.z = Cvt<T>::pack2(o[4], o[5]); w0.w = Cvt<T>::pack2(o[6], o[7]);
+          w1.x = Cvt<T>::pack2(o[8], o[9]); w1.y = Cvt<T>::pack2(o[10], o[11]);
+          w1.z = Cvt<T>::pack2(o[12], o[13]); w1.w = Cvt<T>::pack2(o[14], o[15]);
+          *d0 = w0;
+          *d1 = w1;
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {
+          for (int pn = 0; pn < full_panels; ++pn) tma_store_4d(&tmO, smem + pn * 16384, oc0 + pn * 64, x0, y0, i0);
+          if (rem) tma_store_4d(&tmOp, smem + full_panels * 16384, oc0 + full_panels * 64, x0, y0, i0);
+          tma_store_commit();
+          tma_store_wait_read0();
+        }
+      } else if (p.act == ES_ACT_GEGLU) {
         constexpr int HALF = BLOCK_N / 2;
         const int oc0 = blockIdx.y * HALF;  // output column base
         const int n_out = p.N / 2;
@@ -385,6 +501,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   epilogue_done:;
+    if (threadIdx.x == 64) GEMM_TRACE(5);
   }
 
   // ---- teardown ------------------------------------------------------------------------------
@@ -393,6 +510,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+    if (lane == 0) GEMM_TRACE(6);
   }
 }
 
@@ -403,6 +521,34 @@ template <typename T, int BLOCK_N>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
                        const CUtensorMap& tmB2, GemmKParams& kp, int m_tiles, int n_tiles, const EsGemm* g,
                        cudaStream_t stream) {
+  // ---- epilogue tensor maps: output (and residual) tiles as 64-column panels over the same pixel box as A
+  CUtensorMap tmO = tmA, tmOp = tmA, tmR = tmA, tmRp = tmA;
+  kp.n_out = g->act == ES_ACT_GEGLU ? g->n / 2 : g->n;
+  kp.tma_epi = 0;
+  {
+    const int n_tile_out = g->act == ES_ACT_GEGLU ? BLOCK_N / 2 : BLOCK_N;
+    const int rem = n_tile_out % 64;
+    const bool aligned = (reinterpret_cast<uintptr_t>(g->out) & 15) == 0 && g->ldc % 8 == 0 && kp.n_out % 8 == 0 &&
+                         (!g->residual || ((reinterpret_cast<uintptr_t>(g->residual) & 15) == 0 && g->ldr % 8 == 0));
+    if (!g->out_fp32 && aligned && !getenv("ES_NO_TMA_EPILOGUE")) {
+      auto make = [&](CUtensorMap* full, CUtensorMap* part, const void* base, long long ld) -> int {
+        const uint64_t pitch = static_cast<uint64_t>(ld) * 2;
+        uint64_t dims[4] = {static_cast<uint64_t>(kp.n_out), static_cast<uint64_t>(kp.W), static_cast<uint64_t>(kp.H),
+                            static_cast<uint64_t>(kp.NI)};
+        uint64_t strides[4] = {0, pitch, pitch * kp.W, pitch * kp.W * kp.H};
+        uint32_t box[4] = {64u, static_cast<uint32_t>(kp.bw), static_cast<uint32_t>(kp.bh), static_cast<uint32_t>(kp.bn)};
+        if (n_tile_out >= 64 && encode_tmap_16b(full, base, 4, dims, strides, box, true)) return -1;
+        if (rem) {
+          box[0] = static_cast<uint32_t>(rem);
+          if (encode_tmap_16b(part, base, 4, dims, strides, box, false)) return -1;
+        }
+        return 0;
+      };
+      if (make(&tmO, &tmOp, g->out, g->ldc)) return -3;
+      if (g->residual && make(&tmR, &tmRp, g->residual, g->ldr)) return -3;
+      kp.tma_epi = 1;
+    }
+  }
   constexpr int kStageBytes = kBlockM * kBlockK * 2 + BLOCK_N * kBlockK * 2;
   const int kb_total = kp.taps * kp.kblocks1 + kp.kblocks2;
   const int tiles = m_tiles * n_tiles;
@@ -439,7 +585,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     attr_smem = smem;
   }
   dim3 grid(m_tiles, n_tiles, splits);
-  ES_CUDA(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, tmA2, tmB2, kp));
+  ES_CUDA(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, tmA2, tmB2, tmO, tmOp, tmR, tmRp, kp));
   ES_CUDA(cudaGetLastError());
   return 0;
 }
@@ -613,6 +759,12 @@ static int gemm_dispatch(const EsGemm* g, cudaStream_t stream) {
 }
 
 }  // namespace es
+
+#ifdef ES_GEMM_TRACE
+extern "C" int es_gemm_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, es::g_gemm_trace, sizeof(es::g_gemm_trace)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int es_gemm(const EsGemm* g, void* stream) {
   if (!g) {

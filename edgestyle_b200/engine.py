@@ -277,9 +277,21 @@ class DenoiseEngine:
             if c % 8 or c % cfg.norm_num_groups or (c // cfg.num_heads) % 8:
                 raise ValueError(f"channel count {c} unsupported (needs %8, %groups, head_dim %8)")
         ops.set_gemm_workspace(256 << 20, self.dev)  # split-K scratch of the main stream
-        self._side_stream = torch.cuda.Stream(device=self.dev)
-        self._side_ws = torch.zeros(128 << 20, dtype=torch.uint8, device=self.dev)
-        ops.set_stream_workspace(self._side_stream, self._side_ws)  # concurrent launches must not share scratch
+        # encoder chains (see _run_step): ES_CHAINS = "b0123;p012" style spec, default below
+        spec = os.environ.get("ES_CHAINS", "b0123;p012")
+        self.chains = []
+        for part in spec.split(";"):
+            self.chains.append(("base" if part[0] == "b" else "pose", [int(ch) for ch in part[1:]]))
+        assert sorted(b for k, bl in self.chains if k == "base" for b in bl) == [0, 1, 2, 3], spec
+        assert sorted(b for k, bl in self.chains if k == "pose" for b in bl) == [0, 1, 2], spec
+        assert self.chains[0][0] == "base" and 0 in self.chains[0][1], "the first chain (main stream) must hold the UNet rows"
+        self._chain_streams = [torch.cuda.Stream(device=self.dev) for _ in range(len(self.chains) - 1)]
+        self._merge_stream = torch.cuda.Stream(device=self.dev)
+        self._side_ws = []
+        for st in self._chain_streams + [self._merge_stream]:  # concurrent launches must not share split-K scratch
+            ws = torch.zeros(128 << 20, dtype=torch.uint8, device=self.dev)
+            self._side_ws.append(ws)
+            ops.set_stream_workspace(st, ws)
         self._pack(unet_sd, lora_sds, pose_sd, merge_sd)
         self._alloc_static()
 
@@ -459,7 +471,7 @@ class DenoiseEngine:
 
     def _lin(self, L: Lin, a, out, rows_per_img: int, lora_seg_imgs: Optional[Sequence[int]], tag: str, **ep):
         """out = a @ L.w^T (+ LoRA per row segment) with the fused epilogue `ep`."""
-        if L.down is not None and lora_seg_imgs is not None:
+        if L.down is not None and lora_seg_imgs is not None and (lora_seg_imgs[1] + lora_seg_imgs[2]) > 0:
             n0, n1, n2 = [s * rows_per_img for s in lora_seg_imgs]  # rows of: no-LoRA | group 0 | group 1
             M = a.shape[0]
             t = self.buf(f"{tag}.lora_t", M, L.rp)
@@ -517,13 +529,13 @@ class DenoiseEngine:
         self._lin(T.proj_out, hcur, out, hw, None, tag, residual=x)
         return out
 
-    def _time_path(self, E: EncoderW, groups: Sequence[Tuple[int, int]], tag: str, ncols: Sequence[int]):
+    def _time_path(self, E: EncoderW, groups: Sequence[Tuple[int, int]], tag: str, ncols: Sequence[int], out=None):
         """groups: [(weight-group index, n images)] in pass order.  Returns temb [imgs_total, cols] fp32."""
         cfg, B = self.cfg, self.B
         c0, td = cfg.block_out_channels[0], cfg.time_embed_dim
         total = sum(n for _, n in groups)
         cols = max(ncols)
-        temb = self.buf(f"{tag}.temb", total, cols, torch.float32)
+        temb = out if out is not None else self.buf(f"{tag}.temb", total, cols, torch.float32)
         sin = self.buf("t_sin", B, c0, torch.float32)
         r0 = 0
         for (gi, n), nc in zip(groups, ncols):
@@ -598,34 +610,62 @@ class DenoiseEngine:
         temb_base = self._time_path(Eb, [(0, B), (1, B), (2, 2 * B)], "base",
                                     [enc_cols + self.dec_temb_cols, enc_cols, enc_cols])
         cond = lambda k: self.conds[k * B * hw:(k + 1) * B * hw]
-        # -- the two batched encoder passes are independent: the pose pass (time path, conv_in, encoder, zero-convs)
-        #    runs on a second stream and fills the SMs that the base pass's partial waves leave idle
+        # -- encoder chains.  Image order of the base weight set: unet (B) | agn (B) | clo cond2 (B) | clo cond4 (B);
+        #    of the pose set: cond1 | cond3 | cond5 (B each).  `self.chains` groups consecutive image blocks into
+        #    independent traversals, each on its own stream: most layers at CFG batch 2 are latency / occupancy
+        #    bound, so concurrent chains fill the SMs that one chain's partial waves leave idle.
         main = torch.cuda.current_stream()
-        side = self._side_stream
         fork = torch.cuda.Event()
         fork.record(main)
-        side.wait_event(fork)
-        with torch.cuda.stream(side):
-            temb_pose = self._time_path(Ep, [(0, 3 * B)], "pose", [Ep.temb_cols])
-            xp = self.buf("pose.x0", 3 * B * hw, c0)
-            for slot, k in ((0, 1), (1, 3), (2, 5)):
-                ops.gemm(col, Ep.conv_in, c0, out=xp[slot * B * hw:(slot + 1) * B * hw], bias=Ep.conv_in_b,
-                         residual=cond(k))
-            skips_p, mid_p = self._encoder(Ep, xp, 3 * B, temb_pose, self.ctx_pose, None, "pose")
-            zres_p = []
-            for li, ((c, H, W), src) in enumerate(zip(self.res_shapes, skips_p + [mid_p])):
-                rp = self.buf(f"zres_p{li}", 3 * B * H * W, c)
-                ops.gemm(src, self.zero_pose[li][0], c, out=rp, bias=self.zero_pose[li][1])
-                zres_p.append(rp)
-            join = torch.cuda.Event()
-            join.record(side)
-        # -- conv_in (+ cached conditioning embedding, controllora.py:197-203)
         xb = self.buf("base.x0", 4 * B * hw, c0)
-        ops.gemm(col, Eb.conv_in, c0, out=xb[:B * hw], bias=Eb.conv_in_b)
-        for slot, k in ((1, 0), (2, 2), (3, 4)):
-            ops.gemm(col, Eb.conv_in, c0, out=xb[slot * B * hw:(slot + 1) * B * hw], bias=Eb.conv_in_b, residual=cond(k))
-        skips_b, mid_b = self._encoder(Eb, xb, 4 * B, temb_base, self.ctx_base, (B, B, 2 * B), "base")
-        main.wait_event(join)
+        xp = self.buf("pose.x0", 3 * B * hw, c0)
+        base_cond = (None, 0, 2, 4)   # conditioning net index of base image block 0..3
+        pose_cond = (1, 3, 5)
+        lora_of_block = (0, 1, 2, 2)  # segment class of base block: 0 = UNet rows (no LoRA), 1 = agn, 2 = clo
+        results = {}                  # ("base"|"pose", block) -> (chain skips+mid list, first image of block in chain)
+        done_events = []
+        temb_pose = None
+        for ci, (kind, blocks) in enumerate(self.chains):
+            st = main if ci == 0 else self._chain_streams[ci - 1]
+            if st is not main:
+                st.wait_event(fork)
+            with torch.cuda.stream(st):
+                b0, nb = blocks[0], len(blocks)
+                tag = f"{kind}{b0}"
+                if kind == "base":
+                    E, x_all, ctx_all, temb_all = Eb, xb, self.ctx_base, temb_base
+                    for blk in blocks:
+                        k = base_cond[blk]
+                        ops.gemm(col, E.conv_in, c0, out=xb[blk * B * hw:(blk + 1) * B * hw], bias=E.conv_in_b,
+                                 residual=None if k is None else cond(k))
+                    cnt = [0, 0, 0]
+                    for blk in blocks:
+                        cnt[lora_of_block[blk]] += B
+                    seg = tuple(cnt)
+                else:
+                    E, x_all, ctx_all = Ep, xp, self.ctx_pose
+                    if temb_pose is None:
+                        temb_pose = self.buf("pose.temb", 3 * B, Ep.temb_cols, torch.float32)
+                    self._time_path(Ep, [(0, nb * B)], tag, [Ep.temb_cols], out=temb_pose[b0 * B:(b0 + nb) * B])
+                    temb_all = temb_pose
+                    for blk in blocks:
+                        ops.gemm(col, E.conv_in, c0, out=xp[blk * B * hw:(blk + 1) * B * hw], bias=E.conv_in_b,
+                                 residual=cond(pose_cond[blk]))
+                    seg = None
+                imgs = nb * B
+                sk, md = self._encoder(E, x_all[b0 * B * hw:(b0 + nb) * B * hw], imgs, temb_all[b0 * B:(b0 + nb) * B],
+                                       ctx_all[b0 * B * nt:(b0 + nb) * B * nt], seg, tag)
+                for i, blk in enumerate(blocks):
+                    results[(kind, blk)] = (sk + [md], i * B)
+                ev = torch.cuda.Event()
+                ev.record(st)
+                done_events.append(ev)
+
+        def block_rows(kind, blk, li):
+            """rows of image block `blk` at residual level li: [B*H*W, C] view into its chain's buffer"""
+            outs, first = results[(kind, blk)]
+            c, H, W = self.res_shapes[li]
+            return outs[li][first * H * W:(first + B) * H * W]
         # -- decoder concat buffers (x | skip) and their geometry
         rev = list(reversed(boc))
         rev_attn = list(reversed(cfg.down_has_attn))
@@ -640,37 +680,53 @@ class DenoiseEngine:
                 x_ch = rev[i]
                 sidx -= 1
         cat_of_skip = {v[2]: (v[0], v[1]) for v in cats.values()}
-        # -- zero convs (controllora.py:240-254) + EdgeStyle merge (edgestyle_multicontrolnet.py:160-169)
+        # -- zero convs (controllora.py:240-254) + EdgeStyle merge (edgestyle_multicontrolnet.py:160-169), on the side
+        #    stream in the order the decoder consumes them (mid, then skips 11..0): the large 64x64-level merges
+        #    overlap the decoder's deep levels; the decoder waits on one event per level
         scale = [float(s) for s in cond_scale]
-        all_b = skips_b + [mid_b]
-        for li, (c, H, W) in enumerate(self.res_shapes):
-            n = B * H * W
-            rb = self.buf(f"zres_b{li}", 3 * n, c)
-            rp = zres_p[li]
-            zw, zb = self.zero_base[li]
-            ops.gemm(all_b[li][n:], zw, c, out=rb, bias=zb, segs=([0, n, 3 * n], [0, c], None))
-            res = [rb[:n], rp[:n], rb[n:2 * n], rp[n:2 * n], rb[2 * n:], rp[2 * n:]]
-            z = self.buf(f"merge_z{li}", n, c, torch.float32)
-            if mode == "residuals":
-                dst = self.buf(f"res_out{li}", n, c)
-                ops.merge(res, scale, self.merge[li], self._merge_slot(), z, B, H * W, c, dst, skip=None, zero_stats=False)
-                continue
-            if li < len(self.res_shapes) - 1:
-                cbuf, xc = cat_of_skip[li]
-                dst = cbuf[:, xc:]
-            else:  # mid: becomes the x half of the first decoder concat
-                dst = cats[(0, 0)][0][:, :c]
-            ops.merge(res, scale, self.merge[li], self._merge_slot(), z, B, H * W, c, dst, skip=all_b[li][:n],
-                      zero_stats=False)
+        merged = {}
+        side = self._merge_stream
+        for ev in done_events:
+            side.wait_event(ev)
+        with torch.cuda.stream(side):
+            for li in reversed(range(len(self.res_shapes))):
+                c, H, W = self.res_shapes[li]
+                n = B * H * W
+                rb = self.buf(f"zres_b{li}", 3 * n, c)
+                rp = self.buf(f"zres_p{li}", 3 * n, c)
+                zw, zb = self.zero_base[li]
+                for slot, (blk, noff) in enumerate(((1, 0), (2, c), (3, c))):  # agn | clo(cond 2) | clo(cond 4)
+                    ops.gemm(block_rows("base", blk, li), zw, c, out=rb[slot * n:(slot + 1) * n], bias=zb,
+                             segs=([0, n], [noff], None))
+                for blk in range(3):
+                    ops.gemm(block_rows("pose", blk, li), self.zero_pose[li][0], c, out=rp[blk * n:(blk + 1) * n],
+                             bias=self.zero_pose[li][1])
+                res = [rb[:n], rp[:n], rb[n:2 * n], rp[n:2 * n], rb[2 * n:], rp[2 * n:]]
+                z = self.buf(f"merge_z{li}", n, c, torch.float32)
+                unet_rows = block_rows("base", 0, li)
+                if mode == "residuals":
+                    dst, skip = self.buf(f"res_out{li}", n, c), None
+                elif li < len(self.res_shapes) - 1:
+                    cbuf, xc = cat_of_skip[li]
+                    dst, skip = cbuf[:, xc:], unet_rows
+                else:  # mid: becomes the x half of the first decoder concat
+                    dst, skip = cats[(0, 0)][0][:, :c], unet_rows
+                ops.merge(res, scale, self.merge[li], self._merge_slot(), z, B, H * W, c, dst, skip=skip,
+                          zero_stats=False)
+                merged[li] = torch.cuda.Event()
+                merged[li].record(side)
         if mode == "residuals":
+            main.wait_event(merged[0])  # the side stream is in order: the last event covers all levels
             return
+        main.wait_event(merged[len(self.res_shapes) - 1])
         # -- UNet decoder
         for i in range(len(boc)):
             H, W = self.levels[len(boc) - 1 - i]
             M = B * H * W
             cout = rev[i]
             for j in range(n_up):
-                cbuf, _, _ = cats[(i, j)]
+                cbuf, _, sidx_ij = cats[(i, j)]
+                main.wait_event(merged[sidx_ij])
                 last = (j == n_up - 1)
                 if not last:
                     dest = cats[(i, j + 1)][0][:, :cout]

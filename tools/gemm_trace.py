@@ -1,0 +1,32 @@
+"""clock64 trace of one GEMM CTA: where does a short-K tile spend its time?  (tools/libgemm_trace.so, -DES_GEMM_TRACE)"""
+import ctypes as C, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from edgestyle_b200 import ext  # noqa: E402
+ext.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgemm_trace.so")
+from edgestyle_b200 import ops  # noqa: E402
+lib = ext.load()
+lib.es_gemm_trace.restype = C.c_int
+lib.es_gemm_trace.argtypes = [C.c_void_p]
+names = ["start", "setup done", "first stage full (MMA)", "last MMA issued", "accum visible (epi)", "epilogue done", "dealloc"]
+for (M, N, K, res) in [(24576, 320, 320, True), (24576, 320, 320, False), (8192, 320, 320, True), (24576, 320, 1280, True),
+                       (2048, 1280, 1280, True), (512, 1280, 1280, True)]:
+    a = torch.randn(M, K, device="cuda", dtype=torch.float16)
+    b = torch.randn(N, K, device="cuda", dtype=torch.float16)
+    out = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    r = torch.randn(M, N, device="cuda", dtype=torch.float16) if res else None
+    bias = torch.zeros(N, device="cuda")
+    for _ in range(3):
+        ops.gemm(a, b, N, out=out, bias=bias, residual=r)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        ops.gemm(a, b, N, out=out, bias=bias, residual=r)
+    e1.record()
+    torch.cuda.synchronize()
+    buf = (C.c_longlong * 16)()
+    lib.es_gemm_trace(buf)
+    t = list(buf)[:7]
+    print(f"M={M} N={N} K={K} residual={res}: {e0.elapsed_time(e1) * 50:.1f} us/launch; CTA(1,0) cycles:",
+          ", ".join(f"{n}=+{t[i] - t[0]}" for i, n in enumerate(names)))
