@@ -60,6 +60,8 @@ struct GemmKParams {
   int splits;            // split-K factor (grid.z)
   float* ws_partial;     // [splits][tiles][128][BLOCK_N] fp32 partial accumulators
   int* ws_counter;       // [tiles] arrival counters (zero on entry, reset by the finishing CTA)
+  float* gn_ws;          // optional: GroupNorm statistics of the OUTPUT accumulated here, [img][groups][2] (sum, sumsq)
+  int gn_cpg, gn_groups; // channels per group, groups
   int tma_epi;           // 1: epilogue goes regs -> swizzled smem panels -> TMA store (residual via TMA load)
   int n_out;             // output columns in total (N, or N/2 for GEGLU)
 };
@@ -310,6 +312,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       };
 
+      // GroupNorm statistics of the tile being written (fused producer-side stats: the consumer GroupNorm then
+      // only needs its apply pass).  Every lane of a warp holds the same 16 output channels of 32 different pixels
+      // of ONE image, so each group segment is warp-reduced and lane 0 issues one atomic per (image, group).
+      auto gn_accumulate = [&](const float (&o)[16], int c) {
+        const int col0 = n0 + c;
+        int nvalid = p.N - col0;
+        if (nvalid > 16) nvalid = 16;
+        if (nvalid <= 0) return;
+        const int g_first = col0 / p.gn_cpg, g_last = (col0 + nvalid - 1) / p.gn_cpg;
+        for (int g = g_first; g <= g_last; ++g) {
+          const int lo = max(col0, g * p.gn_cpg) - col0, hi = min(col0 + nvalid, (g + 1) * p.gn_cpg) - col0;
+          float sv = 0.f, qv = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j >= lo && j < hi && row_ok) {
+              sv += o[j];
+              qv += o[j] * o[j];
+            }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            sv += __shfl_xor_sync(0xffffffffu, sv, off);
+            qv += __shfl_xor_sync(0xffffffffu, qv, off);
+          }
+          // rows of a warp never straddle images (checked on the host): use lane 0's image
+          const int img0 = __shfl_sync(0xffffffffu, img, 0);
+          const int ok0 = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, 0);
+          if (lane == 0 && (ok0 || sv != 0.f || qv != 0.f)) {
+            float* w = p.gn_ws + (static_cast<long long>(img0) * p.gn_groups + g) * 2;
+            atomicAdd(w, sv);
+            atomicAdd(w + 1, qv);
+          }
+        }
+      };
       if (use_tma_epi) {
         // ---------------- smem-staged epilogue: 64-column panels [128 rows x 128 B], SWIZZLE_128B ----------------
         // The pipeline's smem is free (every MMA has retired), so the panels alias the stage buffers.
@@ -383,6 +418,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               o[2 * j + 1] += f.y;
             }
           }
+          if (p.gn_ws && !geglu) gn_accumulate(o, c);
           uint4 w0, w1;
           w0.x = Cvt<T>::pack2(o[0], o[1]); w0.y = Cvt<T>::pack2(o[2], o[3]);
           w0.z = Cvt<T>::pack2(o[4], o[5]); w0.w = Cvt<T>::pack2(o[6], o[7]);
@@ -483,6 +519,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   if (j < valid) o[j] += Cvt<T>::to_f(rp[j]);
               }
             }
+            if (p.gn_ws) gn_accumulate(o, c);
             if (p.out_fp32) {
               float* optr = reinterpret_cast<float*>(p.out) + row * p.ldc + n0 + c;
               if (full) {
@@ -699,6 +736,16 @@ static int gemm_dispatch(const EsGemm* g, cudaStream_t stream) {
   kp.ldc = g->ldc;
   kp.out_fp32 = g->out_fp32;
   if (g->residual) ES_CHECK(g->ldr % 8 == 0, "es_gemm: ldr must be a multiple of 8");
+  kp.gn_ws = g->gn_ws;
+  kp.gn_groups = g->gn_groups;
+  kp.gn_cpg = g->gn_groups > 0 ? g->n / g->gn_groups : 0;
+  if (g->gn_ws) {
+    ES_CHECK(g->gn_groups > 0 && g->n % g->gn_groups == 0 && g->act == ES_ACT_NONE, "es_gemm: bad fused-GroupNorm config");
+    // a warp's 32 tile rows must belong to one image
+    const long long rpi = flat ? g->rows_per_img : static_cast<long long>(g->w) * g->h;
+    ES_CHECK(rpi > 0 && rpi % 32 == 0, "es_gemm: fused GroupNorm statistics need rows-per-image %% 32 == 0 (got %lld)", rpi);
+    if (flat) ES_CHECK(g->nseg <= 1 || true, "es_gemm: ok");
+  }
   if (g->act == ES_ACT_GEGLU) ES_CHECK(g->n % 2 == 0 && !g->out_fp32 && !g->residual && !g->rowvec, "es_gemm: bad GEGLU config");
 
   int bn_tile = g->block_n > 0 ? g->block_n : pick_block_n(g->n, m_tiles, g->act);

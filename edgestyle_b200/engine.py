@@ -112,6 +112,7 @@ class Tfm:
     ff2: Lin
     proj_out: Lin
     c: int
+    uid: str = ""
 
 
 class _Packer:
@@ -229,6 +230,7 @@ class _Packer:
             self.lin([f"{t}.ff.net.2"], [f"{t}.ff.net.2.bias"]),
             self.lin([f"{p}.proj_out"], [f"{p}.proj_out.bias"]),
             c,
+            p,
         )
 
 
@@ -272,6 +274,9 @@ class DenoiseEngine:
         self.use_graph = use_graph
         self._bufs: Dict[str, torch.Tensor] = {}
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self.fuse_gn_stats = os.environ.get("ES_FUSE_GN", "1") != "0"
+        self._stats_of = {}
+        self._kv_recompute = False  # True: redo the text K/V projections inside every step (reference behaviour)
         self.launches_per_step = 0
         for i, c in enumerate(cfg.block_out_channels):
             if c % 8 or c % cfg.norm_num_groups or (c // cfg.num_heads) % 8:
@@ -440,6 +445,39 @@ class DenoiseEngine:
         pe = prompt_embeds.to(device=self.dev, dtype=self.dtype).reshape(B * nt, -1)
         for g in range(4):
             self.ctx_base[g * B * nt:(g + 1) * B * nt].copy_(pe)
+        self._precompute_text_kv()
+
+    def _chain_geometry(self):
+        """(tag, EncoderW, first image block, n blocks, LoRA segment image counts) per encoder chain."""
+        B = self.B
+        lora_of_block = (0, 1, 2, 2)
+        out = []
+        for kind, blocks in self.chains:
+            b0, nb = blocks[0], len(blocks)
+            if kind == "base":
+                cnt = [0, 0, 0]
+                for blk in blocks:
+                    cnt[lora_of_block[blk]] += B
+                out.append((f"{kind}{b0}", self.enc_base, b0, nb, tuple(cnt)))
+            else:
+                out.append((f"{kind}{b0}", self.enc_pose, b0, nb, None))
+        return out
+
+    def _precompute_text_kv(self):
+        """attn2.to_k / to_v of every transformer on the (step-invariant) prompt embeddings, LoRA included."""
+        B, nt = self.B, self.n_text
+        for tag, E, b0, nb, seg in self._chain_geometry():
+            ctx_all = self.ctx_base if E is self.enc_base else self.ctx_pose
+            ctx = ctx_all[b0 * B * nt:(b0 + nb) * B * nt]
+            tf = [t for lvl in E.down_tfm for t in lvl if t is not None] + [E.mid_tfm]
+            for T in tf:
+                kv = self.buf(f"kv.{tag}.{T.uid}", nb * B * nt, 2 * T.c)
+                self._lin(T.kv2, ctx, kv, nt, seg, tag + ".kv")
+        for lvl in self.up_tfm:
+            for T in lvl:
+                if T is not None:
+                    kv = self.buf(f"kv.dec.{T.uid}", B * nt, 2 * T.c)
+                    self._lin(T.kv2, self.ctx_dec, kv, nt, None, "dec.kv")
 
     def set_conditioning(self, conds: Sequence[torch.Tensor]):
         """Six cached conditioning embeddings [B, c0, h, w] (prepare_image, edgestyle_pipeline.py:629-664)."""
@@ -450,6 +488,7 @@ class DenoiseEngine:
             ops.nchw_to_nhwc(c.to(device=self.dev, dtype=torch.float32).contiguous(), self.conds[k * B * hw:(k + 1) * B * hw])
 
     def _begin_step_scratch(self):
+        self._stats_of = {}
         self.scratch.zero_()
         self._gn_next = 0
         self._merge_next = 0
@@ -460,17 +499,37 @@ class DenoiseEngine:
         return s
 
     # ------------------------------------------------------------------------------------ layers
-    def _gn(self, x, out, g, b, imgs, hw, silu, eps=None):
+    def _gn_slot(self, imgs):
         G = self.cfg.norm_num_groups
         if self._gn_next >= 256:
             raise RuntimeError("GroupNorm scratch pool exhausted")
         ws = self.gn_pool[self._gn_next * self._gn_slot_floats:][: imgs * G * 2].view(imgs, G, 2)
         self._gn_next += 1
-        ops.groupnorm(x, out, g, b, ws, imgs, hw, G, self.cfg.norm_eps if eps is None else eps, silu, zero_ws=False)
+        return ws
+
+    def _stats_for(self, out, imgs, hw):
+        """Slot in which the GEMM producing `out` accumulates GroupNorm statistics (None when not fusable: a strided
+        view of a concat buffer, or a level whose images are not a multiple of 32 rows)."""
+        if not self.fuse_gn_stats or hw % 32 != 0 or out.stride(0) != out.shape[1]:
+            return None
+        ws = self._gn_slot(imgs)
+        self._stats_of[(out.data_ptr(), out.shape[0], out.shape[1])] = ws
+        return ws
+
+    def _gn(self, x, out, g, b, imgs, hw, silu, eps=None):
+        G = self.cfg.norm_num_groups
+        eps = self.cfg.norm_eps if eps is None else eps
+        ws = self._stats_of.pop((x.data_ptr(), x.shape[0], x.shape[1]), None)
+        if ws is not None:
+            ops.groupnorm(x, out, g, b, ws, imgs, hw, G, eps, silu, stats_ready=True)
+        else:
+            ops.groupnorm(x, out, g, b, self._gn_slot(imgs), imgs, hw, G, eps, silu, zero_ws=False)
         return out
 
     def _lin(self, L: Lin, a, out, rows_per_img: int, lora_seg_imgs: Optional[Sequence[int]], tag: str, **ep):
         """out = a @ L.w^T (+ LoRA per row segment) with the fused epilogue `ep`."""
+        if ep.get("gn_ws") is not None:
+            ep["rows_per_img"] = rows_per_img  # fused GroupNorm statistics are per image
         if L.down is not None and lora_seg_imgs is not None and (lora_seg_imgs[1] + lora_seg_imgs[2]) > 0:
             n0, n1, n2 = [s * rows_per_img for s in lora_seg_imgs]  # rows of: no-LoRA | group 0 | group 1
             M = a.shape[0]
@@ -487,14 +546,19 @@ class DenoiseEngine:
         g1 = self.buf(f"{tag}.gn1", M, R.cin)
         self._gn(x, g1, R.n1g, R.n1b, imgs, H * W, True)
         hbuf = self.buf(f"{tag}.h", M, R.cout)
+        G = self.cfg.norm_num_groups
         ops.gemm(g1, R.w1, R.cout, out=hbuf, taps=9, whn=(W, H, imgs), bias=R.b1,
-                 rowvec=temb[:, R.temb_off:R.temb_off + R.cout], c1=R.cin)
+                 rowvec=temb[:, R.temb_off:R.temb_off + R.cout], c1=R.cin,
+                 gn_ws=self._stats_for(hbuf, imgs, H * W), gn_groups=G)
         g2 = self.buf(f"{tag}.gn2", M, R.cout)
         self._gn(hbuf, g2, R.n2g, R.n2b, imgs, H * W, True)
+        ows = self._stats_for(out, imgs, H * W)
         if R.wsc is not None:
-            ops.gemm(g2, R.w2, R.cout, out=out, taps=9, whn=(W, H, imgs), bias=R.b2, a2=x, b2=R.wsc, c1=R.cout)
+            ops.gemm(g2, R.w2, R.cout, out=out, taps=9, whn=(W, H, imgs), bias=R.b2, a2=x, b2=R.wsc, c1=R.cout,
+                     gn_ws=ows, gn_groups=G)
         else:
-            ops.gemm(g2, R.w2, R.cout, out=out, taps=9, whn=(W, H, imgs), bias=R.b2, residual=x, c1=R.cout)
+            ops.gemm(g2, R.w2, R.cout, out=out, taps=9, whn=(W, H, imgs), bias=R.b2, residual=x, c1=R.cout,
+                     gn_ws=ows, gn_groups=G)
         return out
 
     def _transformer(self, T: Tfm, x, imgs, H, W, ctx, out, tag, seg):
@@ -517,8 +581,10 @@ class DenoiseEngine:
         ops.layernorm(hcur, ln, *T.ln2)
         q = self.buf(f"{tag}.q2", M, c)
         self._lin(T.q2, ln, q, hw, seg, tag + ".o")
-        kv = self.buf(f"{tag}.kv2", imgs * nt, 2 * c)
-        self._lin(T.kv2, ctx, kv, nt, seg, tag + ".kv")
+        # text K/V projections depend only on the prompt and the weights: computed once per set_prompt()
+        kv = self.buf(f"kv.{tag.split('.')[0]}.{T.uid}", imgs * nt, 2 * c)
+        if self._kv_recompute:
+            self._lin(T.kv2, ctx, kv, nt, seg, tag + ".kv")
         ops.attention(q, kv[:, :c], kv[:, c:], att, imgs, heads, hw, nt)
         self._lin(T.o2, att, hcur, hw, seg, tag + ".o", residual=hcur)
         # feed-forward (GEGLU fused in the first GEMM's epilogue)
@@ -526,7 +592,8 @@ class DenoiseEngine:
         u = self.buf(f"{tag}.ff", M, 4 * c)
         self._lin(T.ff1, ln, u, hw, seg, tag + ".o", act=ACT_GEGLU)
         self._lin(T.ff2, u, hcur, hw, seg, tag + ".ff2", residual=hcur)
-        self._lin(T.proj_out, hcur, out, hw, None, tag, residual=x)
+        self._lin(T.proj_out, hcur, out, hw, None, tag, residual=x,
+                  gn_ws=self._stats_for(out, imgs, hw), gn_groups=self.cfg.norm_num_groups)
         return out
 
     def _time_path(self, E: EncoderW, groups: Sequence[Tuple[int, int]], tag: str, ncols: Sequence[int], out=None):
@@ -574,7 +641,8 @@ class DenoiseEngine:
                 col = self.buf(f"{tag}.L{i}.col", imgs * Hn * Wn, 9 * c)
                 ops.im2col3x3(x, col, imgs, H, W, c, 2)
                 out = self.buf(f"{tag}.skip{len(skips)}", imgs * Hn * Wn, c)
-                ops.gemm(col, E.down_conv[i][0], c, out=out, bias=E.down_conv[i][1])
+                ops.gemm(col, E.down_conv[i][0], c, out=out, bias=E.down_conv[i][1], rows_per_img=Hn * Wn,
+                         gn_ws=self._stats_for(out, imgs, Hn * Wn), gn_groups=cfg.norm_num_groups)
                 x = out
                 skips.append(x)
         H, W = self.levels[-1]
@@ -831,7 +899,11 @@ class DenoiseEngine:
         ctx = self.buf("single.ctx", B * nt, cfg.cross_attention_dim)
         ctx.copy_(prompt_embeds.to(device=self.dev, dtype=self.dtype).reshape(B * nt, -1))
         seg = None if group is None else ((0, B, 0) if group == 0 else (0, 0, B))
-        skips, mid = self._encoder(E, x0, B, temb, ctx, seg, "single")
+        self._kv_recompute = True  # the prompt is an argument of this call: no cached text K/V
+        try:
+            skips, mid = self._encoder(E, x0, B, temb, ctx, seg, "single")
+        finally:
+            self._kv_recompute = False
         n_res = len(self.res_shapes)
         if guess_mode:  # controllora.py:257-265
             scales = (torch.logspace(-1, 0, n_res) * conditioning_scale).tolist()

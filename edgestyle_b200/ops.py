@@ -65,7 +65,8 @@ def _need_cuda(*ts):
 def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: int = 1, whn=None, bias=None,
          rowvec=None, rows_per_img: int = 0, residual=None, act: int = ACT_NONE, alpha: float = 1.0,
          a2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None, segs=None, block_n: int = 0,
-         c1: Optional[int] = None, stages: int = 0, split_k: int = 0, workspace: Optional[torch.Tensor] = None):
+         c1: Optional[int] = None, stages: int = 0, split_k: int = 0, workspace: Optional[torch.Tensor] = None,
+         gn_ws: Optional[torch.Tensor] = None, gn_groups: int = 0):
     """out[m, :n] = epilogue(A (*) B^T).  a: [M, >=c1] (pitch = a.stride(0)); b: [n_total, taps*c1].
 
     whn=(w, h, n_img) for taps == 9.  segs = list of (row_start, b_noff, b2_noff) + final row end via segs_end.
@@ -113,6 +114,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: i
     g.block_n = block_n
     g.stages = stages
     g.split_k = split_k
+    if gn_ws is not None:
+        g.gn_ws = gn_ws.data_ptr()
+        g.gn_groups = gn_groups
     ws = workspace if workspace is not None else STREAM_WORKSPACES.get(_stream(), GEMM_WORKSPACE)
     if ws is not None:
         g.workspace = ws.data_ptr()
@@ -139,7 +143,7 @@ def attention(q, k, v, out, batch: int, heads: int, nq: int, nkv: int, scale: Op
 
 
 def groupnorm(x0, out, gamma, beta, ws, n_img: int, hw: int, groups: int, eps: float, silu: bool, x1=None,
-              zero_ws: bool = True):
+              zero_ws: bool = True, stats_ready: bool = False):
     """GroupNorm(+SiLU) over [n_img*hw, c0(+c1)]; ws: fp32 [n_img, groups, 2] scratch (zeroed here unless the
     caller hands in an already-zero slot, `zero_ws=False`)."""
     _need_cuda(x0, out, ws)
@@ -153,9 +157,13 @@ def groupnorm(x0, out, gamma, beta, ws, n_img: int, hw: int, groups: int, eps: f
     g.ws = ws.data_ptr()
     g.out, g.ldo = out.data_ptr(), out.stride(0)
     g.silu = 1 if silu else 0
+    lib = load()
+    if stats_ready:  # the producing GEMM already accumulated (sum, sumsq) into ws (EsGemm.gn_ws)
+        _count(1)
+        check(lib.es_groupnorm_apply(C.byref(g), _stream()), "es_groupnorm_apply")
+        return out
     if zero_ws:
         ws.zero_()
-    lib = load()
     _count(2)  # stats + apply (the workspace memset is torch's)
     check(lib.es_groupnorm_stats(C.byref(g), _stream()), "es_groupnorm_stats")
     check(lib.es_groupnorm_apply(C.byref(g), _stream()), "es_groupnorm_apply")

@@ -83,6 +83,10 @@ typedef struct EsGemm {
   int block_n; /* 0 = auto */
   int stages;  /* smem pipeline depth, 0 = auto */
   int split_k; /* 0 = auto, 1 = off, >1 = forced; needs `workspace` */
+  float* gn_ws; /* optional: accumulate GroupNorm statistics of the OUTPUT here ([img][gn_groups][2] sum/sumsq, zeroed
+                   by the caller) so the consuming GroupNorm skips its statistics pass; needs rows-per-image % 32 == 0
+                   (flat mode: rows_per_img must be set) */
+  int gn_groups;
   void* workspace; /* optional split-K scratch: first 64 KiB = tile counters (zero-initialised ONCE by the caller,
                       self-resetting), rest = fp32 partial tiles.  Must not be shared by concurrent launches. */
   long long workspace_bytes;

@@ -192,6 +192,31 @@ def test_conv3x3_with_fused_1x1_shortcut():
     _close(out, want, 5e-3, 5e-3, "conv3x3 + shortcut")
 
 
+@pytest.mark.parametrize("n_img,h,w,cin,cout,split", [(2, 32, 32, 64, 320, 0), (4, 8, 8, 256, 640, 3), (2, 16, 16, 64, 64, 0)])
+def test_conv3x3_fused_groupnorm_stats(n_img, h, w, cin, cout, split):
+    """The GEMM epilogue accumulates (sum, sumsq) per (image, group) of its OUTPUT; GroupNorm then only applies."""
+    from edgestyle_b200 import ops
+
+    ops.set_gemm_workspace(256 << 20)
+    x = _rand(n_img * h * w, cin, seed=97)
+    wt = _rand(cout, 9 * cin, scale=(9 * cin) ** -0.5, seed=98)
+    bias = _rand(cout, dtype=torch.float32, seed=99)
+    res = _rand(n_img * h * w, cout, seed=100)
+    out = torch.empty(n_img * h * w, cout, device=DEV, dtype=torch.float16)
+    ws = torch.zeros(n_img, 32, 2, device=DEV)
+    ops.gemm(x, wt, cout, out=out, taps=9, whn=(w, h, n_img), bias=bias, residual=res, gn_ws=ws, gn_groups=32,
+             split_k=split)
+    o = out.float().view(n_img, h * w, 32, cout // 32)
+    want = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1)
+    _close(ws, want, 0.05, 2e-3, "fused gn stats")
+    gamma = _rand(cout, dtype=torch.float32, seed=101) * 0.1 + 1
+    beta = _rand(cout, dtype=torch.float32, seed=102) * 0.1
+    y = torch.empty_like(out)
+    ops.groupnorm(out, y, gamma, beta, ws, n_img, h * w, 32, 1e-5, True, stats_ready=True)
+    ref = F.silu(F.group_norm(out.float().view(n_img, h * w, cout).permute(0, 2, 1), 32, gamma, beta, 1e-5))
+    _close(y, ref.permute(0, 2, 1).reshape(-1, cout), 5e-3, 5e-3, "gn apply with fused stats")
+
+
 # ------------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("batch,heads,d,nq,nkv", [(2, 8, 40, 4096, 4096), (2, 8, 80, 1024, 1024), (3, 8, 160, 256, 256),
