@@ -64,16 +64,29 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmV, const AttParams p) {
   constexpr uint32_t kTmemCols = NA <= 2 ? 256 : 512;
   constexpr int kOCol = 128;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // No static shared memory at all: the dynamic region then starts at the CTA's (1024-byte aligned) window base, so
+  // SWIZZLE_128B needs no alignment slack and two CTAs of the d<=64 variant (7 x 16 KB + barriers each) fit one SM.
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + NA * kAtomBytes;
   uint8_t* sV = sK + NA * kAtomBytes;
-  uint8_t* sP = sV + NA * kAtomBytes;  // 2 atoms
-  __shared__ __align__(8) uint64_t q_full, k_full, v_full, k_empty, v_empty, s_full, p_full, o_done;
-  __shared__ uint32_t tmem_base_smem;
+  uint8_t* sP = sV + NA * kAtomBytes;  // 2 buffers x 2 atoms: softmax(j+1) writes one while PV(j) reads the other
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kAtomBytes);
+  uint64_t& q_full = bars[0];
+  uint64_t& k_full = bars[1];
+  uint64_t& v_full = bars[2];
+  uint64_t& k_empty = bars[3];
+  uint64_t& v_empty = bars[4];
+  uint64_t& s_full = bars[5];
+  uint64_t& p_full = bars[6];
+  uint64_t& o_done = bars[7];
+  uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 8);
 
   pdl_launch_dependents();
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("edgestyle_b200: attention smem base not 1024-byte aligned\n");
+    __trap();
+  }
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128;
@@ -155,7 +168,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {  // 128 keys = 8 x K16
-          const uint64_t ad = smem_desc_sw128(aP + (k >> 2) * kAtomBytes, 16, 1024) + 2 * (k & 3);
+          const uint64_t ad = smem_desc_sw128(aP + ((j & 1) * 2 + (k >> 2)) * kAtomBytes, 16, 1024) + 2 * (k & 3);
           // V: MN-major, 16 keys = 2048 B along K; N atoms (64 of d) kAtomBytes apart
           const uint64_t bd = smem_desc_sw128(aV + k * 2048, kAtomBytes, 1024);
           umma_f16(tmem_base + kOCol, ad, bd, idesc_pv, (j | k) != 0);
@@ -179,7 +192,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     constexpr float kSlack = 8.0f;
 
     // writes P for columns [c, c+32) of this thread's row from raw scores v, with shift -neg_m
-    auto emit_p = [&](const uint32_t (&v)[32], int c, float neg_m, int kv_valid, bool full_tile, float& sum) {
+    auto emit_p = [&](const uint32_t (&v)[32], int c, float neg_m, int kv_valid, bool full_tile, float& sum, int pbuf) {
       uint32_t pk[16];
       float s0 = 0.f, s1 = 0.f;
       if (full_tile) {
@@ -202,7 +215,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
       sum += s0 + s1;
-      uint8_t* prow = sP + (c >> 6) * kAtomBytes + r * 128;
+      uint8_t* prow = sP + (pbuf * 2 + (c >> 6)) * kAtomBytes + r * 128;
       const int cc0 = (c & 63) >> 3;  // first 16 B chunk of this 32-column group inside the atom
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
@@ -229,7 +242,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (threadIdx.x == 64) ATT_TRACE(1, 4 * j + 0);
       mbar_wait(&s_full, ph);
       if (threadIdx.x == 64) ATT_TRACE(1, 4 * j + 1);
-      if (j > 0) mbar_wait(&o_done, ph ^ 1);  // PV(j-1) retired: P may be overwritten, O may be touched
+      // P is double-buffered and QK(j) completes after PV(j-2) on the in-order tensor pipe, so P[j & 1] is free here;
+      // only the (rare) O rescale below has to wait for PV(j-1)
       tc_fence_after();
       if (threadIdx.x == 64) ATT_TRACE(1, 4 * j + 2);
       float mx = -INFINITY;
@@ -259,23 +273,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_ld_wait();
         tmem_ld_x32(t_row + 32, vb);
         if (j > 0 && attempt == 0) mx = tile_max(va, 0, kv_valid, full_tile, mx);
-        emit_p(va, 0, neg_m, kv_valid, full_tile, sum);
+        emit_p(va, 0, neg_m, kv_valid, full_tile, sum, j & 1);
         tmem_ld_wait();
         tmem_ld_x32(t_row + 64, va);
         if (j > 0 && attempt == 0) mx = tile_max(vb, 32, kv_valid, full_tile, mx);
-        emit_p(vb, 32, neg_m, kv_valid, full_tile, sum);
+        emit_p(vb, 32, neg_m, kv_valid, full_tile, sum, j & 1);
         tmem_ld_wait();
         tmem_ld_x32(t_row + 96, vb);
         if (j > 0 && attempt == 0) mx = tile_max(va, 64, kv_valid, full_tile, mx);
-        emit_p(va, 64, neg_m, kv_valid, full_tile, sum);
+        emit_p(va, 64, neg_m, kv_valid, full_tile, sum, j & 1);
         tmem_ld_wait();
         if (j > 0 && attempt == 0) mx = tile_max(vb, 96, kv_valid, full_tile, mx);
-        emit_p(vb, 96, neg_m, kv_valid, full_tile, sum);
+        emit_p(vb, 96, neg_m, kv_valid, full_tile, sum, j & 1);
         if (j == 0 || attempt == 1) break;
         const float m_tile = mx * sl2;
         redo = __any_sync(0xffffffffu, m_tile > m_run + kSlack);
         if (!redo) break;
         // rare path: raise the shift of the rows that need it, rescale their O / row-sum columns, redo P
+        mbar_wait(&o_done, ph ^ 1);  // PV(j-1) must have retired before O is touched
+        tc_fence_after();
         const float m_new = fmaxf(m_run, m_tile);
         const float alpha = ex2_approx(m_run - m_new);
 #pragma unroll 1
@@ -358,7 +374,7 @@ static int launch_attention(const EsAttention* a, cudaStream_t stream) {
   p.out = a->out;
   p.ldo = a->ldo;
   p.bso = a->bso;
-  const size_t smem = static_cast<size_t>(3 * NA + 2) * kAtomBytes + 1024;
+  const size_t smem = static_cast<size_t>(3 * NA + 4) * kAtomBytes + 128;  // + barriers; no alignment slack (see kernel)
   auto kern = attention_kernel<T, NA>;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
