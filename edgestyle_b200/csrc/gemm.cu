@@ -627,8 +627,19 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return 0;
 }
 
-static int pick_block_n(int n, int m_tiles, int act) {
-  // prefer no column waste, then enough CTAs to cover the 148 SMs
+static int pick_block_n(int n, int m_tiles, int act, int kb_total) {
+  // Measured on B200 (tools/smallm_sweep.py, tools/gemm_sweep.py):
+  //  * small M with a long K (8x8-level convs, M <= 512): 64-wide tiles + split-K stream the weights best;
+  //  * mid M (<= 2048 rows) with a long K: the widest tile that divides N, so A is re-read from L2 as little as
+  //    possible, again with split-K filling the machine;
+  //  * otherwise a wave-quantised cost model over two resident CTAs per SM.
+  if (act != ES_ACT_GEGLU && kb_total >= 32) {
+    if (m_tiles <= 4 && n >= 64) return 64;
+    if (m_tiles <= 16) {
+      if (n % 160 == 0) return 160;
+      if (n % 128 == 0) return 128;
+    }
+  }
   const int cands[5] = {256, 160, 128, 64, 32};
   int best = 32;
   double best_cost = 1e30;
@@ -748,7 +759,7 @@ static int gemm_dispatch(const EsGemm* g, cudaStream_t stream) {
   }
   if (g->act == ES_ACT_GEGLU) ES_CHECK(g->n % 2 == 0 && !g->out_fp32 && !g->residual && !g->rowvec, "es_gemm: bad GEGLU config");
 
-  int bn_tile = g->block_n > 0 ? g->block_n : pick_block_n(g->n, m_tiles, g->act);
+  int bn_tile = g->block_n > 0 ? g->block_n : pick_block_n(g->n, m_tiles, g->act, g->taps * ceil_div(g->c1, kBlockK));
   const int n_tiles = ceil_div(g->n, bn_tile);
   if (g->act == ES_ACT_GEGLU) ES_CHECK(g->n % bn_tile == 0, "es_gemm: GEGLU needs n %% block_n == 0 (n=%d bn=%d)", g->n, bn_tile);
 

@@ -30,11 +30,12 @@ def wrap(name, fn, describe):
         if os.environ.get("COLD"):
             flush.fill_(0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = ops.LAUNCHES
         e0.record()
         r = fn(*a, **k)
         e1.record()
         torch.cuda.synchronize()
-        records.append((name, desc, e0.elapsed_time(e1) * 1e3, flops, nbytes))
+        records.append((name, desc, e0.elapsed_time(e1) * 1e3, flops, nbytes, ops.LAUNCHES - n0))
         return r
     return inner
 
@@ -84,11 +85,11 @@ eng.step(x, 500.0)  # warm-up (allocations)
 records.clear()
 eng.step(x, 500.0)
 import json
-json.dump([(r[0], r[1], r[3], r[4]) for r in records], open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "oplog.json"), "w"))
+json.dump([(r[0], r[1], r[3], r[4], r[5]) for r in records], open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "oplog.json"), "w"))
 tot = sum(r[2] for r in records)
 print(f"ops {len(records)}  total {tot / 1e3:.2f} ms  ({'cold' if os.environ.get('COLD') else 'warm'} L2)")
 by = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
-for name, desc, us, fl, by_ in records:
+for name, desc, us, fl, by_, _nl in records:
     k = (name, desc)
     by[k][0] += 1
     by[k][1] += us
