@@ -20,6 +20,7 @@ Everything is enqueued on the current CUDA stream through the C-ABI (edgestyle_b
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -299,6 +300,14 @@ class DenoiseEngine:
             ops.set_stream_workspace(st, ws)
         self._pack(unet_sd, lora_sds, pose_sd, merge_sd)
         self._alloc_static()
+        # per-shape GEMM tile / split-K selection: committed table first, measure whatever is missing during the
+        # first (eager) step on this device
+        self._tuned_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuned_b200.json")
+        if os.environ.get("ES_AUTOTUNE", "1") != "0":
+            if os.environ.get("ES_RETUNE", "0") == "0":
+                ops.TUNER.load(self._tuned_path)
+            ops.TUNER.enabled = True
+        self._tuning_done = False
 
     # ------------------------------------------------------------------------------------ packing
     def _pack_encoder(self, sd, loras) -> EncoderW:
@@ -841,11 +850,13 @@ class DenoiseEngine:
             n0 = ops.LAUNCHES
             self._run_step(key)
             self.launches_per_step = ops.LAUNCHES - n0
+            self._finish_tuning()
             return self.eps_out
         gph = self._graphs.get(key)
         if gph is None:
-            self._run_step(key)  # eager warm-up: allocates every buffer, sets kernel attributes
+            self._run_step(key)  # eager warm-up: allocates every buffer, sets kernel attributes, tunes GEMM tiles
             torch.cuda.synchronize()
+            self._finish_tuning()
             gph = torch.cuda.CUDAGraph()
             n0 = ops.LAUNCHES
             with torch.cuda.graph(gph):
@@ -854,6 +865,15 @@ class DenoiseEngine:
             self._graphs[key] = gph
         gph.replay()
         return self.eps_out
+
+    def _finish_tuning(self):
+        """Called after the first full eager step: freeze the tuner (lookups stay active) and dump the table."""
+        if ops.TUNER.enabled and not self._tuning_done:
+            ops.TUNER.enabled = False
+            self._tuning_done = True
+            dump = os.environ.get("ES_TUNE_DUMP")
+            if dump:
+                ops.TUNER.save(dump)
 
     def _load_sample_t(self, sample, timestep):
         self.sample_in.copy_(sample.to(device=self.dev, dtype=torch.float32))

@@ -62,6 +62,83 @@ def _need_cuda(*ts):
             raise ext.EdgeStyleNativeError("edgestyle_b200 ops need CUDA tensors (no CPU fallback)")
 
 
+class GemmTuner:
+    """Per-shape (block_n, split_k) selection by measurement on the device the engine runs on.
+
+    The first time a GEMM signature is seen (eager warm-up step of the engine) every candidate tile width /
+    split-K factor is timed with CUDA events on a scratch output (cold L2: a 256 MB buffer is rewritten between
+    runs, as weights are cold in the real step) and the fastest is cached; the table can be saved to / loaded
+    from JSON so later processes skip the search."""
+
+    BNS = (32, 64, 128, 160, 256)
+
+    def __init__(self):
+        self.table = {}
+        self.enabled = False
+        self._flush = None
+        self._scratch = {}
+
+    @staticmethod
+    def key(a, n, c1, taps, whn, act, a2, residual, segs, out, gn_ws):
+        return "|".join(str(x) for x in (
+            str(a.dtype).split(".")[-1], a.shape[0], n, c1, taps, whn if taps == 9 else None, act,
+            None if a2 is None else a2.shape[1], residual is not None,
+            None if not segs else (tuple(segs[0]), tuple(segs[1]), None if segs[2] is None else tuple(segs[2])),
+            str(out.dtype).split(".")[-1], gn_ws is not None))
+
+    def load(self, path):
+        import json
+        import os
+
+        if os.path.exists(path):
+            self.table.update(json.load(open(path)))
+
+    def save(self, path):
+        import json
+
+        json.dump(self.table, open(path, "w"), indent=0, sort_keys=True)
+
+    def candidates(self, M, n, kb_total, act, fixed_bn):
+        m_tiles = (M + 127) // 128
+        bns = [fixed_bn] if fixed_bn else [bn for bn in self.BNS if bn <= max(32, 2 * n) and not (act and bn % 32)]
+        out = []
+        for bn in bns:
+            tiles = m_tiles * ((n + bn - 1) // bn)
+            sks = [1]
+            if tiles <= 148 and kb_total >= 16:
+                sks += sorted({s for s in (2, 3, 4, 6, 8, 12, 16, 24, 296 // tiles) if 2 <= s <= kb_total // 4 and s * tiles <= 2 * 296})
+            out += [(bn, sk) for sk in sks]
+        return out
+
+    def tune(self, key, run, M, n, kb_total, act, fixed_bn):
+        if self._flush is None:
+            self._flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        best = None
+        for bn, sk in self.candidates(M, n, kb_total, act, fixed_bn):
+            try:
+                run(bn, sk)
+                torch.cuda.synchronize()
+            except ext.EdgeStyleNativeError:
+                continue
+            ts = []
+            for _ in range(3):
+                self._flush.fill_(0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                run(bn, sk)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            t = sorted(ts)[1]
+            if best is None or t < best[0]:
+                best = (t, bn, sk)
+        self.table[key] = [best[1], best[2], round(best[0] * 1e3, 1)]
+        return best[1], best[2]
+
+
+TUNER = GemmTuner()
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: int = 1, whn=None, bias=None,
          rowvec=None, rows_per_img: int = 0, residual=None, act: int = ACT_NONE, alpha: float = 1.0,
          a2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None, segs=None, block_n: int = 0,
@@ -111,6 +188,26 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: i
     g.out = out.data_ptr()
     g.ldc = out.stride(0)
     g.out_fp32 = 1 if out.dtype == torch.float32 else 0
+    if TUNER.enabled and stages == 0 and split_k == 0 and not torch.cuda.is_current_stream_capturing():
+        key = TUNER.key(a, n, g.c1, taps, whn, act, a2, residual, segs, out, gn_ws)
+        hit = TUNER.table.get(key)
+        if hit is None:
+            # time candidates on scratch outputs so that in-place residual updates / statistics are not repeated
+            sk_out = TUNER._scratch.setdefault(("o", out.shape, out.dtype), torch.empty_like(out.contiguous()))
+            sk_gn = None if gn_ws is None else torch.zeros_like(gn_ws)
+            kb_total = taps * ((g.c1 + 63) // 64) + (0 if a2 is None else (a2.shape[1] + 63) // 64)
+
+            def run(bn, sk):
+                gemm(a, b, n, out=sk_out, taps=taps, whn=whn, bias=bias, rowvec=rowvec, rows_per_img=rows_per_img,
+                     residual=residual, act=act, alpha=alpha, a2=a2, b2=b2, segs=segs, block_n=bn, c1=c1, stages=0,
+                     split_k=sk, workspace=workspace, gn_ws=sk_gn, gn_groups=gn_groups)
+
+            hit = TUNER.tune(key, run, M, n, kb_total, act, block_n)
+        block_n, split_k = hit[0], hit[1]
+    elif TUNER.table and stages == 0 and split_k == 0:
+        hit = TUNER.table.get(TUNER.key(a, n, g.c1, taps, whn, act, a2, residual, segs, out, gn_ws))
+        if hit is not None:
+            block_n, split_k = hit[0], hit[1]
     g.block_n = block_n
     g.stages = stages
     g.split_k = split_k

@@ -92,3 +92,130 @@ def test_ddim20_psnr_full_size():
     psnr = _psnr(lat, want)
     print(f"20-step DDIM latent PSNR = {psnr:.2f} dB")
     assert psnr >= 40.0, psnr
+
+
+def test_guidance_sweep_batch8_per_row_guidance():
+    """BASELINE config 3: 4 guidance scales x CFG = 8 rows in one batch; per-image guidance vector on the device."""
+    from edgestyle_b200 import ops
+    from oracle.schedulers import DDIMScheduler
+    from oracle.sd15 import SD15Config
+    from oracle.step import cfg_combine, fused_step
+
+    cfg = SD15Config(block_out_channels=(64, 128, 256, 256), cross_attention_dim=96)
+    images = 4
+    m, inp, eng = _mk(cfg, 16, 16, rank=4, images=images)
+    scales = torch.tensor([3.0, 4.5, 6.0, 7.5], device=DEV)
+    x = torch.cat([inp.latents] * 2)
+    t = torch.tensor(951, device=DEV)
+    want_eps = fused_step(m, x, t, inp.prompt_embeds, inp.conditioning_scale, inp.conds)
+    sch = DDIMScheduler()
+    sch.set_timesteps(20)
+    want = sch.step(cfg_combine(want_eps, scales), 951, inp.latents)
+    eng.step(x, t, inp.conditioning_scale)
+    lat = inp.latents.clone().float()
+    a_t, a_p = sch.coefficients(951)
+    eng.cfg_ddim_update(lat, float(a_t), float(a_p), scales)
+    assert (lat - want).abs().max().item() <= 2e-2
+
+
+def test_nonsquare_latent_and_bf16():
+    """BASELINE config 5 geometry at reduced width: a non-square latent (12 x 16 -> 6 x 8 -> 3 x 4 -> 2 x 2 levels need
+    masked tiles) in bf16 storage; bf16's 8-bit mantissa is judged on cosine + a looser max-abs bound."""
+    from oracle.sd15 import SD15Config
+    from oracle.step import fused_step
+
+    cfg = SD15Config(block_out_channels=(64, 128, 256, 256), cross_attention_dim=96)
+    for dtype, tol in ((torch.float16, 2e-2), (torch.bfloat16, 8e-2)):
+        m, inp, eng = _mk(cfg, 24, 32, rank=4, images=1, dtype=dtype)
+        x = torch.cat([inp.latents] * 2)
+        t = torch.tensor(501, device=DEV)
+        want = fused_step(m, x, t, inp.prompt_embeds, inp.conditioning_scale, inp.conds)
+        got = eng.step(x, t, inp.conditioning_scale)
+        cos, mx = _metrics(got, want)
+        print(f"{dtype}: cos={cos:.6f} max_abs={mx:.4g}")
+        assert cos >= 0.999 and mx <= tol, (dtype, cos, mx)
+
+
+def test_model_mirror_forward_signatures():
+    """EdgeStyleMultiControlNetModel.forward / CachedControlNetModel.forward through the host mirrors vs the oracle."""
+    from edgestyle_b200 import config as C
+    from edgestyle_b200.model import (CachedControlNetModel, ControlLoRAModel, EdgeStyleMultiControlNetModel,
+                                      UNet2DConditionModel)
+    from oracle.sd15 import SD15Config
+    from oracle.step import build_models, synthetic_inputs
+
+    ocfg = SD15Config(block_out_channels=(64, 128, 256, 256), cross_attention_dim=96)
+    h = w = 16
+    m = build_models(ocfg, (h, w), rank=4)
+    inp = synthetic_inputs(ocfg, 1, h, w)
+    cfg = C.UNetConfig.from_any(ocfg)
+    unet = UNet2DConditionModel(cfg, m.unet.state_dict())
+    agn = ControlLoRAModel(cfg, m.lora_agnostic.state_dict(), 4, unet=unet)
+    clo = ControlLoRAModel(cfg, m.lora_clothes.state_dict(), 4, unet=unet)
+    pose = CachedControlNetModel(cfg, m.openpose.state_dict())
+    multi = EdgeStyleMultiControlNetModel([agn, pose, clo, pose, clo, pose], m.controlnet.merge_state_dict(), (h, w))
+    m.unet.to(DEV)
+    m.controlnet.to(DEV)
+    x = torch.cat([inp.latents] * 2).to(DEV)
+    pe = inp.prompt_embeds.to(DEV)
+    conds = [c.to(DEV) for c in inp.conds]
+    t = torch.tensor(651, device=DEV)
+    scale = [1.0, 0.5, 1.0, 2.0, 1.0, 1.0]
+    want_d, want_m = m.controlnet(x, t, pe, conds, scale, return_dict=False)
+    got_d, got_m = multi(x, t, pe, conds, scale, return_dict=False)
+    assert len(got_d) == 12
+    for a, b in zip(got_d + [got_m], want_d + [want_m]):
+        assert a.shape == b.shape
+        assert (a - b).abs().max().item() <= 2e-2 * max(1.0, b.abs().max().item())
+    # single nets: ControlLoRA (tied + LoRA) and the plain ControlNet, incl. guess_mode scales
+    for net, onet, cond in ((agn, m.lora_agnostic, conds[0]), (clo, m.lora_clothes, conds[2]), (pose, m.openpose, conds[1])):
+        for guess in (False, True):
+            wd, wm = onet(x, t, pe, cond, 0.75, guess_mode=guess)
+            out = net(x, t, pe, cond, conditioning_scale=0.75, guess_mode=guess, return_dict=True)
+            for a, b in zip(list(out.down_block_res_samples) + [out.mid_block_res_sample], wd + [wm]):
+                assert (a - b).abs().max().item() <= 1e-2 * max(1.0, b.abs().max().item())
+
+
+def test_pipeline_call_matches_oracle_denoise():
+    """EdgeStyleStableDiffusionControlNetPipeline.__call__ (host tensors in, latents out) vs the oracle loop."""
+    from edgestyle_b200 import config as C
+    from edgestyle_b200.model import (CachedControlNetModel, ControlLoRAModel, EdgeStyleMultiControlNetModel,
+                                      EdgeStyleStableDiffusionControlNetPipeline, UNet2DConditionModel)
+    from oracle.sd15 import SD15Config
+    from oracle.step import build_models, denoise, synthetic_inputs
+
+    ocfg = SD15Config(block_out_channels=(64, 128, 256, 256), cross_attention_dim=96)
+    h = w = 16
+    m = build_models(ocfg, (h, w), rank=4)
+    inp = synthetic_inputs(ocfg, 1, h, w)
+    cfg = C.UNetConfig.from_any(ocfg)
+    unet = UNet2DConditionModel(cfg, m.unet.state_dict())
+    agn = ControlLoRAModel(cfg, m.lora_agnostic.state_dict(), 4, unet=unet)
+    clo = ControlLoRAModel(cfg, m.lora_clothes.state_dict(), 4, unet=unet)
+    pose = CachedControlNetModel(cfg, m.openpose.state_dict())
+    multi = EdgeStyleMultiControlNetModel([agn, pose, clo, pose, clo, pose], m.controlnet.merge_state_dict(), (h, w))
+    pipe = EdgeStyleStableDiffusionControlNetPipeline(unet=unet, controlnet=multi)
+    seen = []
+    out = pipe(image=inp.conds, prompt_embeds=inp.prompt_embeds[1:], negative_prompt_embeds=inp.prompt_embeds[:1],
+               latents=inp.latents, num_inference_steps=5, guidance_scale=4.5, output_type="latent",
+               control_guidance_end=[1.0, 1.0, 0.6, 1.0, 1.0, 1.0],
+               callback_on_step_end=lambda p, i, t, kw: seen.append(i) or {})
+    assert seen == [0, 1, 2, 3, 4]
+    # oracle with the same control_guidance gating (edgestyle_pipeline.py:418-427): net 2 off from step 3 of 5
+    m.unet.to(DEV)
+    m.controlnet.to(DEV)
+    from oracle.schedulers import DDIMScheduler
+    from oracle.step import cfg_combine, fused_step
+
+    sch = DDIMScheduler()
+    ts = sch.set_timesteps(5)
+    lat = inp.latents.to(DEV)
+    pe = inp.prompt_embeds.to(DEV)
+    conds = [c.to(DEV) for c in inp.conds]
+    for i, t in enumerate(ts):
+        keep = [1.0] * 6
+        keep[2] = 1.0 - float((i + 1) / 5 > 0.6)
+        eps = fused_step(m, torch.cat([lat] * 2), t.to(DEV), pe, keep, conds)
+        lat = sch.step(cfg_combine(eps, 4.5), t, lat)
+    assert out.images.shape == lat.shape
+    assert _psnr(out.images, lat) >= 40.0
