@@ -32,7 +32,10 @@ UNIT = "steps/s"
 # algorithmic FLOPs per step at CFG batch 2, 64x64 latent (UNet 401.64 + 6 x 134.28 GMAC per row =
 # 4.829 TFLOP) MINUS the step-invariant text K/V projections (5.56 GMAC/row = 0.022 TFLOP) that the engine computes
 # once per prompt instead of every step -- only executed work is credited.
-TFLOP_PER_STEP_B2 = 4.829 - 0.022
+TFLOP_PER_STEP_B2 = 4.807
+# DRAM bytes per step of the dominant kernel family + the rest of the step, from profiles/r1_launches_final.csv
+# (ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 673 launches of one step, caches flushed per kernel)
+DRAM_BYTES_PER_STEP_B2 = 9.04e9
 
 
 def measured_peaks():
@@ -262,9 +265,11 @@ def run_ours(args):
                         "(prompt embeds, 6 cached cond embeddings, latents) to host latents, per-step latent read-back"},
         "gpu_launches": int(launches_timed),
         "roofline": {"bound": "tensor", "achieved": round(achieved_tf, 2), "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": round(achieved_tf / peak_tf, 4), "traffic": None,
+                     "frac": round(achieved_tf / peak_tf, 4),
+                     "traffic": DRAM_BYTES_PER_STEP_B2 * images if images == 1 else None,
                      "kernel": "es::gemm_kernel (tcgen05 implicit GEMM) -- whole-step algorithmic FLOPs "
-                               f"({TFLOP_PER_STEP_B2} TFLOP per CFG pair, SURVEY.md 8(d)) over the CUDA-event step time",
+                               f"({TFLOP_PER_STEP_B2} TFLOP per CFG pair, SURVEY.md 8(d)) over the CUDA-event step time; "
+                               "traffic = DRAM bytes of all launches of one step (profiles/r1_launches_final.csv)",
                      "peak_source": peak_src},
     }
     if not args.no_cpu_baseline and world == 1:
