@@ -62,6 +62,7 @@ struct GemmKParams {
   int* ws_counter;       // [tiles] arrival counters (zero on entry, reset by the finishing CTA)
   float* gn_ws;          // optional: GroupNorm statistics of the OUTPUT accumulated here, [img][groups][2] (sum, sumsq)
   int gn_cpg, gn_groups; // channels per group, groups
+  int b_blocked;         // weights stored K-block-major: [tap*kblocks + cb][n][64] (contiguous 128 B x BLOCK_N tiles)
   int tma_epi;           // 1: epilogue goes regs -> swizzled smem panels -> TMA store (residual via TMA load)
   int n_out;             // output columns in total (N, or N/2 for GEGLU)
 };
@@ -178,7 +179,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             dx = tap % 3 - 1;
           }
           tma_load_4d(sa, &tmA, &full_bar[s], cb * kBlockK, x0 + dx, y0 + dy, i0);
-          tma_load_3d(sb, &tmB, &full_bar[s], cb * kBlockK, tap, b_noff + n0);
+          if (p.b_blocked) tma_load_3d(sb, &tmB, &full_bar[s], 0, b_noff + n0, kb);
+          else tma_load_3d(sb, &tmB, &full_bar[s], cb * kBlockK, tap, b_noff + n0);
         } else {
           const int cb = kb - kb1;
           tma_load_4d(sa, &tmA2, &full_bar[s], cb * kBlockK, x0, y0, i0);  // centre tap (1x1)
@@ -779,7 +781,15 @@ static int gemm_dispatch(const EsGemm* g, cudaStream_t stream) {
     strides[3] = pitch * W * H;
     if (encode_tmap_16b(&tmA, g->a, 4, dims, strides, box)) return -3;
   }
-  {
+  kp.b_blocked = g->b_blocked;
+  if (g->b_blocked) {
+    // K-block-major weights: [taps * kblocks1][n_total_b][64] -- every B tile is one contiguous BLOCK_N x 128 B chunk
+    uint64_t dims[3] = {64, static_cast<uint64_t>(g->n_total_b), static_cast<uint64_t>(g->taps) * kp.kblocks1};
+    uint64_t strides[3] = {0, 128, static_cast<uint64_t>(g->n_total_b) * 128};
+    uint32_t box[3] = {static_cast<uint32_t>(kBlockK), static_cast<uint32_t>(bn_tile), 1u};
+    ES_CHECK(g->n_total_b >= g->n, "es_gemm: n_total_b < n");
+    if (encode_tmap_16b(&tmB, g->b, 3, dims, strides, box)) return -3;
+  } else {
     uint64_t dims[3] = {static_cast<uint64_t>(g->c1), static_cast<uint64_t>(g->taps),
                         static_cast<uint64_t>(g->n_total_b)};
     uint64_t strides[3] = {0, static_cast<uint64_t>(g->c1) * 2, static_cast<uint64_t>(g->c1) * 2 * g->taps};

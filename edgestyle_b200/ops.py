@@ -143,7 +143,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: i
          rowvec=None, rows_per_img: int = 0, residual=None, act: int = ACT_NONE, alpha: float = 1.0,
          a2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None, segs=None, block_n: int = 0,
          c1: Optional[int] = None, stages: int = 0, split_k: int = 0, workspace: Optional[torch.Tensor] = None,
-         gn_ws: Optional[torch.Tensor] = None, gn_groups: int = 0):
+         gn_ws: Optional[torch.Tensor] = None, gn_groups: int = 0, b_blocked: bool = False):
     """out[m, :n] = epilogue(A (*) B^T).  a: [M, >=c1] (pitch = a.stride(0)); b: [n_total, taps*c1].
 
     whn=(w, h, n_img) for taps == 9.  segs = list of (row_start, b_noff, b2_noff) + final row end via segs_end.
@@ -161,9 +161,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: i
         g.w, g.h, g.n_img = whn
         assert g.w * g.h * g.n_img == M
     g.taps = taps
-    assert b.is_contiguous() and b.shape[1] == taps * g.c1, (b.shape, taps, g.c1)
+    if b_blocked:  # [taps * kblocks][n_total][64]
+        assert b.is_contiguous() and b.dim() == 3 and b.shape[2] == 64 and b.shape[0] == taps * ((g.c1 + 63) // 64)
+        g.n_total_b = b.shape[1]
+        g.b_blocked = 1
+    else:
+        assert b.is_contiguous() and b.shape[1] == taps * g.c1, (b.shape, taps, g.c1)
+        g.n_total_b = b.shape[0]
     g.b = b.data_ptr()
-    g.n_total_b = b.shape[0]
     if a2 is not None:
         assert b2 is not None and b2.is_contiguous() and a2.shape[0] == M
         g.a2, g.c2, g.lda2 = a2.data_ptr(), a2.shape[1], a2.stride(0)
@@ -200,7 +205,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: i
             def run(bn, sk):
                 gemm(a, b, n, out=sk_out, taps=taps, whn=whn, bias=bias, rowvec=rowvec, rows_per_img=rows_per_img,
                      residual=residual, act=act, alpha=alpha, a2=a2, b2=b2, segs=segs, block_n=bn, c1=c1, stages=0,
-                     split_k=sk, workspace=workspace, gn_ws=sk_gn, gn_groups=gn_groups)
+                     split_k=sk, workspace=workspace, gn_ws=sk_gn, gn_groups=gn_groups, b_blocked=b_blocked)
 
             hit = TUNER.tune(key, run, M, n, kb_total, act, block_n)
         block_n, split_k = hit[0], hit[1]
