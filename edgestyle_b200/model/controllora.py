@@ -24,6 +24,52 @@ class ControlNetOutput:
     mid_block_res_sample: torch.Tensor
 
 
+WEIGHTS_NAME = "diffusion_pytorch_model.safetensors"  # diffusers' SAFETENSORS_WEIGHTS_NAME
+CONFIG_NAME = "config.json"
+
+
+def _save_dir(directory, state_dict, config: dict):
+    import json
+    import os
+
+    from safetensors.torch import save_file
+
+    if os.path.isfile(directory):
+        raise ValueError(f"Provided path ({directory}) should be a directory, not a file")
+    os.makedirs(directory, exist_ok=True)
+    save_file({k: v.detach().cpu().contiguous() for k, v in state_dict.items()}, os.path.join(directory, WEIGHTS_NAME),
+              metadata={"format": "pt"})
+    json.dump(config, open(os.path.join(directory, CONFIG_NAME), "w"), indent=2)
+
+
+def _load_dir(directory):
+    import json
+    import os
+
+    from safetensors.torch import load_file
+
+    if not os.path.isdir(directory):
+        raise ValueError(f"Provided path ({directory}) should be a directory")
+    cfg_path = os.path.join(directory, CONFIG_NAME)
+    config = json.load(open(cfg_path)) if os.path.exists(cfg_path) else {}
+    return load_file(os.path.join(directory, WEIGHTS_NAME)), config
+
+
+def _config_dict(cfg: C.UNetConfig, **extra) -> dict:
+    d = {k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.__dict__.items()}
+    d.update(extra)
+    return d
+
+
+def _config_from_dict(d: dict) -> C.UNetConfig:
+    names = C.UNetConfig.__dataclass_fields__
+    # diffusers' own config.json uses `attention_head_dim: 8` for "8 heads" 
+    kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in d.items() if k in names}
+    if "num_heads" not in kw and "attention_head_dim" in d and isinstance(d["attention_head_dim"], int):
+        kw["num_heads"] = d["attention_head_dim"]
+    return C.UNetConfig(**kw)
+
+
 def _check_spec(sd: Mapping[str, torch.Tensor], spec: Dict[str, Tuple[int, ...]], what: str, allow_extra=()):
     missing = [k for k in spec if k not in sd]
     if missing:
@@ -46,6 +92,14 @@ class UNet2DConditionModel:
 
     def state_dict(self):
         return self._sd
+
+    def save_pretrained(self, directory):
+        _save_dir(directory, self._sd, _config_dict(self.config, _class_name="UNet2DConditionModel"))
+
+    @classmethod
+    def from_pretrained(cls, directory, **_):
+        sd, cfg = _load_dir(directory)
+        return cls(_config_from_dict(cfg), sd)
 
 
 class CachedControlNetModel:
@@ -96,6 +150,18 @@ class CachedControlNetModel:
 
     def preprocess_image(self, image):
         raise NotImplementedError("the per-call precompute stage (VAE / openpose embedder) is row N2 of SURVEY.md 8(f)")
+
+    # -- checkpoint format (diffusers layout: <dir>/config.json + <dir>/diffusion_pytorch_model.safetensors) ------
+    def _extra_config(self) -> dict:
+        return {"_class_name": "ControlNetModel"}
+
+    def save_pretrained(self, directory, **_):
+        _save_dir(directory, self.state_dict(), _config_dict(self.config, **self._extra_config()))
+
+    @classmethod
+    def from_pretrained(cls, directory, **_):
+        sd, cfg = _load_dir(directory)
+        return cls(_config_from_dict(cfg), sd)
 
 
 class ControlLoRAModel(CachedControlNetModel):
@@ -155,6 +221,17 @@ class ControlLoRAModel(CachedControlNetModel):
                 self._sd[k] = v
             elif strict and (k.split(".")[0] not in self._skip_layers) and not k.startswith("controlnet_cond_embedding."):
                 raise KeyError(k)
+
+    def _extra_config(self) -> dict:
+        return {"_class_name": "ControlLoRAModel", "lora_linear_rank": self.lora_linear_rank,
+                "lora_conv2d_rank": self.lora_conv2d_rank, "uses_vae": True}
+
+    @classmethod
+    def from_pretrained(cls, directory, unet: Optional[UNet2DConditionModel] = None, **_):
+        """Loads only LoRA + non-tied tensors (what :600-606 saves); call tie_weights(unet) afterwards (app.py:95-97)."""
+        sd, cfg = _load_dir(directory)
+        return cls(_config_from_dict(cfg), sd, lora_linear_rank=cfg.get("lora_linear_rank", 4),
+                   lora_conv2d_rank=cfg.get("lora_conv2d_rank", 0), unet=unet)
 
     def fuse_lora(self, lora_scale: float = 1.0, safe_fusing: bool = False):
         raise NotImplementedError(

@@ -106,3 +106,57 @@ class EdgeStyleMultiControlNetModel:
 
     def fuse(self):
         raise NotImplementedError("see ControlLoRAModel.fuse_lora: LoRA is applied inside the GEMM")
+
+    # -- checkpoint directory format of the reference (edgestyle_multicontrolnet.py:213-282, 289-430) ----------------
+    def save_pretrained(self, save_directory, save_pattern: Optional[Sequence[Optional[int]]] = None, **_):
+        """<dir>/diffusion_pytorch_model.safetensors = merge blocks only (:173-193);
+        <dir>/controlnet_{idx}/ for every distinct idx of `save_pattern` (:242-281)."""
+        import os
+
+        from safetensors.torch import save_file
+
+        from .controllora import WEIGHTS_NAME
+
+        if os.path.isfile(save_directory):
+            raise ValueError(f"Provided path ({save_directory}) should be a directory, not a file")
+        os.makedirs(save_directory, exist_ok=True)
+        save_file({k: v.detach().cpu().contiguous() for k, v in self._merge_sd.items()},
+                  os.path.join(save_directory, WEIGHTS_NAME), metadata={"format": "pt"})
+        save_pattern = list(save_pattern) if save_pattern is not None else [None] * len(self.nets)
+        saved = []
+        for i, net in enumerate(self.nets):
+            if save_pattern[i] is not None and save_pattern[i] not in saved:
+                net.save_pretrained(os.path.join(save_directory, f"controlnet_{save_pattern[i]}"))
+                saved.append(save_pattern[i])
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_path, *, load_pattern=None, static_controlnets=None,
+                        controlnet_class=ControlLoRAModel, vae=None, torch_dtype=None, latent_hw=(64, 64), **kwargs):
+        import os
+
+        from safetensors.torch import load_file
+
+        from .controllora import WEIGHTS_NAME
+
+        if not os.path.isdir(pretrained_model_path):
+            raise ValueError(f"Provided path ({pretrained_model_path}) should be a directory")
+        if load_pattern is None:
+            raise ValueError("load_pattern must be provided")
+        static_controlnets = static_controlnets or [None] * len(load_pattern)
+        loaded, nets = {}, []
+        for i, load in enumerate(load_pattern):
+            if load is not None:
+                if load not in loaded:
+                    loaded[load] = controlnet_class.from_pretrained(os.path.join(pretrained_model_path, f"controlnet_{load}"))
+                    if vae is not None and hasattr(loaded[load], "set_autoencoder"):
+                        loaded[load].set_autoencoder(vae)
+                nets.append(loaded[load])
+            else:
+                nets.append(static_controlnets[i])
+        for i, n in enumerate(nets):
+            if n is None:
+                raise ValueError(f"All controlnets must be provided. controlnet {i} is None.")
+        merge_sd = load_file(os.path.join(pretrained_model_path, WEIGHTS_NAME))
+        if torch_dtype is not None and not isinstance(torch_dtype, torch.dtype):
+            raise ValueError(f"{torch_dtype} needs to be of type `torch.dtype`")
+        return cls(nets, merge_sd, latent_hw=latent_hw, dtype=torch_dtype or torch.float16)

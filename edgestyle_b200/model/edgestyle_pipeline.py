@@ -138,8 +138,11 @@ class EdgeStyleStableDiffusionControlNetPipeline:
             cond_scale = [c * k for c, k in zip(controlnet_conditioning_scale, keeps)]
             x = sch.scale_model_input(torch.cat([latents] * 2), t)  # :443-450
             eng.step(x, float(t), cond_scale)
-            a_t, a_prev = sch.coefficients(int(t))
-            eng.cfg_ddim_update(latents, a_t, a_prev)
+            if hasattr(sch, "device_step"):   # UniPC: x0-prediction + predictor/corrector linear combinations
+                sch.device_step(eng.eps_out, latents, eng.guidance)
+            else:                             # DDIM: fused CFG + update
+                a_t, a_prev = sch.coefficients(int(t))
+                eng.cfg_ddim_update(latents, a_t, a_prev)
             self.h2d_bytes += 4 + 16  # timestep + 4 scheduler coefficients
             if callback_on_step_end is not None:
                 out = callback_on_step_end(self, i, t, {k: locals()[k] for k in callback_on_step_end_tensor_inputs})

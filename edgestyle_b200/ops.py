@@ -371,3 +371,25 @@ def cfg_ddim(eps, latents, guidance, coef, eps_out=None):
     check(load().es_cfg_ddim(eps.data_ptr(), latents.data_ptr(), guidance.data_ptr(), coef.data_ptr(), _p(eps_out),
                              imgs, chw, _stream()), "es_cfg_ddim")
     return latents
+
+
+def cfg_x0(eps, sample, guidance, alpha: float, sigma: float, x0):
+    """x0 = (sample - sigma * cfg(eps)) / alpha (UniPC convert_model_output)."""
+    imgs = sample.shape[0]
+    _count()
+    check(load().es_cfg_x0(eps.data_ptr(), sample.data_ptr(), guidance.data_ptr(), float(alpha), float(sigma),
+                           x0.data_ptr(), imgs, sample[0].numel(), _stream()), "es_cfg_x0")
+    return x0
+
+
+def lincomb(out, terms):
+    """out = sum(c * x for c, x in terms) over fp32 tensors of out's shape (at most 4 terms; out may alias an x)."""
+    terms = [(float(c), x) for c, x in terms if x is not None and c != 0.0]
+    assert 1 <= len(terms) <= 4
+    terms += [(0.0, None)] * (4 - len(terms))
+    args = []
+    for c, x in terms:
+        args += [c, _p(x)]
+    _count()
+    check(load().es_lincomb4(out.data_ptr(), *args, out.numel(), _stream()), "es_lincomb4")
+    return out

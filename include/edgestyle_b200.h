@@ -195,6 +195,14 @@ int es_add(int dtype, const void* a, long long lda, const void* b, long long ldb
 int es_cfg_ddim(const float* eps, float* latents, const float* guidance, const float* coef, float* eps_out, int imgs,
                 int chw, void* stream);
 
+/* UniPC (reference default scheduler, /root/reference/app.py:118) on the device: x0-prediction from the guided
+ * noise (convert_model_output), and the predictor / corrector updates as linear combinations whose scalar
+ * coefficients the host derives from the sigma table (diffusers UniPCMultistepScheduler, bh2, order 2). */
+int es_cfg_x0(const float* eps, const float* sample, const float* guidance, float alpha, float sigma, float* x0,
+              int imgs, int chw, void* stream);
+int es_lincomb4(float* out, float c0, const float* x0, float c1, const float* x1, float c2, const float* x2, float c3,
+                const float* x3, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

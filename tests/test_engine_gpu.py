@@ -219,3 +219,37 @@ def test_pipeline_call_matches_oracle_denoise():
         lat = sch.step(cfg_combine(eps, 4.5), t, lat)
     assert out.images.shape == lat.shape
     assert _psnr(out.images, lat) >= 40.0
+
+
+@pytest.mark.parametrize("spacing", ["leading", "linspace"])
+def test_unipc_pipeline_matches_oracle(spacing):
+    """N3: the reference's default scheduler (UniPC bh2, order 2) driven on the device vs the oracle's UniPC loop."""
+    from edgestyle_b200 import config as C
+    from edgestyle_b200.model import (CachedControlNetModel, ControlLoRAModel, EdgeStyleMultiControlNetModel,
+                                      EdgeStyleStableDiffusionControlNetPipeline, UNet2DConditionModel)
+    from edgestyle_b200.schedulers import UniPCMultistepScheduler
+    from oracle.schedulers import UniPCMultistepScheduler as OracleUniPC
+    from oracle.sd15 import SD15Config
+    from oracle.step import build_models, denoise, synthetic_inputs
+
+    ocfg = SD15Config(block_out_channels=(64, 128, 256, 256), cross_attention_dim=96)
+    h = w = 16
+    m = build_models(ocfg, (h, w), rank=4)
+    inp = synthetic_inputs(ocfg, 1, h, w)
+    cfg = C.UNetConfig.from_any(ocfg)
+    unet = UNet2DConditionModel(cfg, m.unet.state_dict())
+    agn = ControlLoRAModel(cfg, m.lora_agnostic.state_dict(), 4, unet=unet)
+    clo = ControlLoRAModel(cfg, m.lora_clothes.state_dict(), 4, unet=unet)
+    pose = CachedControlNetModel(cfg, m.openpose.state_dict())
+    multi = EdgeStyleMultiControlNetModel([agn, pose, clo, pose, clo, pose], m.controlnet.merge_state_dict(), (h, w))
+    pipe = EdgeStyleStableDiffusionControlNetPipeline(unet=unet, controlnet=multi,
+                                                      scheduler=UniPCMultistepScheduler(timestep_spacing=spacing))
+    out = pipe(image=inp.conds, prompt_embeds=inp.prompt_embeds[1:], negative_prompt_embeds=inp.prompt_embeds[:1],
+               latents=inp.latents, num_inference_steps=8, guidance_scale=3.5, output_type="latent")
+    m.unet.to(DEV)
+    m.controlnet.to(DEV)
+    inp.latents, inp.prompt_embeds, inp.conds = inp.latents.to(DEV), inp.prompt_embeds.to(DEV), [c.to(DEV) for c in inp.conds]
+    want = denoise(m, inp, 8, 3.5, scheduler=OracleUniPC(timestep_spacing=spacing))
+    psnr = _psnr(out.images, want)
+    print(f"UniPC {spacing}: latent PSNR {psnr:.1f} dB")
+    assert psnr >= 40.0

@@ -128,3 +128,47 @@ def test_pipeline_rejects_out_of_scope_arguments(models):
         pipe(image=conds, prompt_embeds=pe, negative_prompt_embeds=pe, output_type="latent", guess_mode=True)
     with pytest.raises(ValueError):
         pipe(image=conds[:4], prompt_embeds=pe, negative_prompt_embeds=pe, output_type="latent")
+
+
+def test_checkpoint_directory_roundtrip(models, tmp_path):
+    """N1: the reference's on-disk format -- merge blocks at the top level, one controlnet_{idx}/ per distinct
+    ControlLoRA with ONLY LoRA + non-tied tensors, shared objects restored from load_pattern."""
+    import os
+
+    from safetensors.torch import load_file
+
+    from edgestyle_b200.model import (CachedControlNetModel, ControlLoRAModel, EdgeStyleMultiControlNetModel,
+                                      UNet2DConditionModel)
+
+    cfg = C.UNetConfig.from_any(TINY)
+    unet = UNet2DConditionModel(cfg, models.unet.state_dict())
+    agn = ControlLoRAModel(cfg, models.lora_agnostic.state_dict(), 4, unet=unet)
+    clo = ControlLoRAModel(cfg, models.lora_clothes.state_dict(), 4, unet=unet)
+    pose = CachedControlNetModel(cfg, models.openpose.state_dict())
+    multi = EdgeStyleMultiControlNetModel([agn, pose, clo, pose, clo, pose], models.controlnet.merge_state_dict(), (8, 8))
+    d = str(tmp_path / "edgestyle")
+    pattern = [0, None, 1, None, 1, None]
+    multi.save_pretrained(d, save_pattern=pattern)
+    unet.save_pretrained(str(tmp_path / "unet"))
+    pose.save_pretrained(str(tmp_path / "openpose"))
+    assert sorted(os.listdir(d)) == ["controlnet_0", "controlnet_1", "diffusion_pytorch_model.safetensors"]
+    top = load_file(os.path.join(d, "diffusion_pytorch_model.safetensors"))
+    assert all(k.startswith("multi_controlnet_") for k in top)
+    sub = load_file(os.path.join(d, "controlnet_1", "diffusion_pytorch_model.safetensors"))
+    assert all(k.split(".")[0] not in ControlLoRAModel._skip_layers or ".lora_layer." in k for k in sub)
+    unet2 = UNet2DConditionModel.from_pretrained(str(tmp_path / "unet"))
+    pose2 = CachedControlNetModel.from_pretrained(str(tmp_path / "openpose"))
+    multi2 = EdgeStyleMultiControlNetModel.from_pretrained(d, load_pattern=pattern, controlnet_class=ControlLoRAModel,
+                                                           static_controlnets=[None, pose2, None, pose2, None, pose2],
+                                                           latent_hw=(8, 8))
+    assert multi2.nets[2] is multi2.nets[4] and multi2.nets[0] is not multi2.nets[2]  # train_...py:849-856
+    for n in (multi2.nets[0], multi2.nets[2]):
+        n.tie_weights(unet2)
+    assert multi2.unet() is unet2 and unet2.config == cfg
+    for a, b in ((multi.state_dict(), multi2.state_dict()), (agn.state_dict(), multi2.nets[0].state_dict()),
+                 (clo.state_dict(), multi2.nets[2].state_dict()), (unet.state_dict(), unet2.state_dict())):
+        assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
+    with pytest.raises(ValueError):
+        EdgeStyleMultiControlNetModel.from_pretrained(d, controlnet_class=ControlLoRAModel)  # load_pattern required
+    with pytest.raises(ValueError):
+        EdgeStyleMultiControlNetModel.from_pretrained(d, load_pattern=pattern, controlnet_class=ControlLoRAModel)
