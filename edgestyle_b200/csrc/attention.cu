@@ -18,6 +18,7 @@ namespace es {
 
 constexpr int kAttThreads = 192;
 constexpr int kAtomBytes = 128 * 128;  // 128 rows x 128 B
+constexpr int kKV = 64;                // keys per K/V tile
 
 __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -62,25 +63,27 @@ template <typename T, int NA>
 __global__ void __launch_bounds__(kAttThreads, NA == 1 ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttParams p) {
+  // TMEM: S double-buffered (2 x 64 fp32 columns) + O (dN columns)
   constexpr uint32_t kTmemCols = NA <= 2 ? 256 : 512;
   constexpr int kOCol = 128;
+  constexpr int kKVAtom = kKV * 128;  // bytes of one 64-column atom of a K / V tile (kKV rows x 128 B)
   // No static shared memory at all: the dynamic region then starts at the CTA's (1024-byte aligned) window base, so
-  // SWIZZLE_128B needs no alignment slack and two CTAs of the d<=64 variant (7 x 16 KB + barriers each) fit one SM.
+  // SWIZZLE_128B needs no alignment slack and two CTAs of the d <= 64 variant (80 KB each) fit one SM.
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + NA * kAtomBytes;
-  uint8_t* sV = sK + NA * kAtomBytes;
-  uint8_t* sP = sV + NA * kAtomBytes;  // 2 buffers x 2 atoms: softmax(j+1) writes one while PV(j) reads the other
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kAtomBytes);
+  uint8_t* sQ = smem;                              // NA atoms x [128 rows x 128 B]
+  uint8_t* sK = sQ + NA * kAtomBytes;              // 2 stages x NA atoms x [64 rows x 128 B]
+  uint8_t* sV = sK + 2 * NA * kKVAtom;             // 2 stages x NA atoms x [64 rows x 128 B]
+  uint8_t* sP = sV + 2 * NA * kKVAtom;             // 2 buffers x [128 rows x 128 B] (64 keys = one 128 B row)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kAtomBytes);
   uint64_t& q_full = bars[0];
-  uint64_t& k_full = bars[1];
-  uint64_t& v_full = bars[2];
-  uint64_t& k_empty = bars[3];
-  uint64_t& v_empty = bars[4];
-  uint64_t& s_full = bars[5];
-  uint64_t& p_full = bars[6];
-  uint64_t& o_done = bars[7];
-  uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2]
+  uint64_t* p_full = bars + 11;   // [2]
+  uint64_t& o_done = bars[13];
+  uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 14);
 
   pdl_launch_dependents();
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
@@ -92,19 +95,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int q0 = blockIdx.x * 128;
   const int head = blockIdx.y;
   const int b = blockIdx.z;
-  const int n_tiles = (p.nkv + 127) / 128;
+  const int n_tiles = (p.nkv + kKV - 1) / kKV;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(&q_full, 1);
-    mbar_init(&k_full, 1);
-    mbar_init(&v_full, 1);
-    mbar_init(&k_empty, 1);
-    mbar_init(&v_empty, 1);
-    mbar_init(&s_full, 1);
-    mbar_init(&p_full, 128);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 128);
+    }
     mbar_init(&o_done, 1);
     fence_mbar_init();
   }
@@ -116,69 +121,78 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  // PDL: everything above (barrier init, TMEM alloc, descriptor prefetch) overlaps the previous kernel's tail;
-  // global memory written by it may only be touched after this point.
+  // PDL: everything above overlaps the previous kernel's tail; its outputs may only be read after this point.
   pdl_wait();
 
   if (warp == 0) {
+    // ================================ TMA producer: Q once, then 2-stage K and V rings ==========================
     if (lane == 0) {
       mbar_expect_tx(&q_full, NA * kAtomBytes);
 #pragma unroll
       for (int a = 0; a < NA; ++a) tma_load_4d(sQ + a * kAtomBytes, &tmQ, &q_full, a * 64, head, q0, b);
       for (int j = 0; j < n_tiles; ++j) {
-        const uint32_t ph = j & 1;
-        mbar_wait(&k_empty, ph ^ 1);
-        mbar_expect_tx(&k_full, NA * kAtomBytes);
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_expect_tx(&k_full[s], NA * kKVAtom);
 #pragma unroll
-        for (int a = 0; a < NA; ++a) tma_load_4d(sK + a * kAtomBytes, &tmK, &k_full, a * 64, head, j * 128, b);
-        mbar_wait(&v_empty, ph ^ 1);
-        mbar_expect_tx(&v_full, NA * kAtomBytes);
+        for (int a = 0; a < NA; ++a)
+          tma_load_4d(sK + (s * NA + a) * kKVAtom, &tmK, &k_full[s], a * 64, head, j * kKV, b);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_expect_tx(&v_full[s], NA * kKVAtom);
 #pragma unroll
-        for (int a = 0; a < NA; ++a) tma_load_4d(sV + a * kAtomBytes, &tmV, &v_full, a * 64, head, j * 128, b);
+        for (int a = 0; a < NA; ++a)
+          tma_load_4d(sV + (s * NA + a) * kKVAtom, &tmV, &v_full[s], a * 64, head, j * kKV, b);
       }
     }
   } else if (warp == 1) {
+    // ================================ MMA issuer ================================================================
+    // S(j+2) = Q K(j+2)^T is issued as soon as softmax(j) has consumed S[j & 1], i.e. two tiles ahead of the PV that
+    // needs it: the softmax warps never wait for a QK^T, and PV(j) retires while softmax(j+1) runs.
     if (lane == 0) {
-      const uint32_t idesc_qk = make_idesc_f16(128, 128, Cvt<T>::kFmt, 0, 0);
+      const uint32_t idesc_qk = make_idesc_f16(128, kKV, Cvt<T>::kFmt, 0, 0);
       const uint32_t idesc_pv = make_idesc_f16(128, p.dN, Cvt<T>::kFmt, 0, 1);
       const int kq = (p.d + 15) / 16;  // MMAs along the head dim
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
       mbar_wait(&q_full, 0);
       auto issue_qk = [&](int j) {
-        mbar_wait(&k_full, j & 1);
+        const int s = j & 1;
+        mbar_wait(&k_full[s], (j >> 1) & 1);
         tc_fence_after();
         for (int k = 0; k < kq; ++k) {
           const uint64_t ad = smem_desc_sw128(aQ + (k >> 2) * kAtomBytes, 16, 1024) + 2 * (k & 3);
-          const uint64_t bd = smem_desc_sw128(aK + (k >> 2) * kAtomBytes, 16, 1024) + 2 * (k & 3);
-          umma_f16(tmem_base, ad, bd, idesc_qk, k != 0);
+          const uint64_t bd = smem_desc_sw128(aK + (s * NA + (k >> 2)) * kKVAtom, 16, 1024) + 2 * (k & 3);
+          umma_f16(tmem_base + s * kKV, ad, bd, idesc_qk, k != 0);
         }
-        umma_commit(&k_empty);
-        umma_commit(&s_full);
+        umma_commit(&k_empty[s]);
+        umma_commit(&s_full[s]);
       };
       issue_qk(0);
+      if (n_tiles > 1) issue_qk(1);
       for (int j = 0; j < n_tiles; ++j) {
-        const uint32_t ph = j & 1;
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
         ATT_TRACE(0, 4 * j + 1);
-        mbar_wait(&p_full, ph);  // P(j) in smem and S(j) consumed
+        mbar_wait(&p_full[s], ph);  // P(j) in smem and S[s] consumed
         ATT_TRACE(0, 4 * j + 2);
-        // S is free again: start the next tile's scores first so its softmax can begin while PV(j) runs
-        if (j + 1 < n_tiles) issue_qk(j + 1);
-        ATT_TRACE(0, 4 * j + 0);
-        mbar_wait(&v_full, ph);
+        mbar_wait(&v_full[s], ph);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {  // 128 keys = 8 x K16
-          const uint64_t ad = smem_desc_sw128(aP + ((j & 1) * 2 + (k >> 2)) * kAtomBytes, 16, 1024) + 2 * (k & 3);
-          // V: MN-major, 16 keys = 2048 B along K; N atoms (64 of d) kAtomBytes apart
-          const uint64_t bd = smem_desc_sw128(aV + k * 2048, kAtomBytes, 1024);
+        for (int k = 0; k < kKV / 16; ++k) {
+          const uint64_t ad = smem_desc_sw128(aP + s * kAtomBytes, 16, 1024) + 2 * k;
+          // V: MN-major, 16 keys = 2048 B along K; N atoms (64 of d) kKVAtom apart
+          const uint64_t bd = smem_desc_sw128(aV + s * NA * kKVAtom + k * 2048, kKVAtom, 1024);
           umma_f16(tmem_base + kOCol, ad, bd, idesc_pv, (j | k) != 0);
         }
-        umma_commit(&v_empty);
+        umma_commit(&v_empty[s]);
         umma_commit(&o_done);
         ATT_TRACE(0, 4 * j + 3);
+        if (j + 2 < n_tiles) issue_qk(j + 2);
+        ATT_TRACE(0, 4 * j + 0);
       }
     }
   } else {
+    // ================================ softmax: thread r owns query row r (TMEM lane r) ==========================
     const int qd = warp & 3;
     const int r = qd * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
@@ -215,8 +229,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
       sum += s0 + s1;
-      uint8_t* prow = sP + (pbuf * 2 + (c >> 6)) * kAtomBytes + r * 128;
-      const int cc0 = (c & 63) >> 3;  // first 16 B chunk of this 32-column group inside the atom
+      // canonical K-major SWIZZLE_128B: row r at r*128 B, 16 B chunk index XOR (r & 7)
+      uint8_t* prow = sP + pbuf * kAtomBytes + r * 128;
+      const int cc0 = c >> 3;  // first 16 B chunk of this 32-column group
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         const int chunk = (cc0 + q4) ^ (r & 7);
@@ -236,61 +251,46 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     };
 
     for (int j = 0; j < n_tiles; ++j) {
-      const uint32_t ph = j & 1;
-      const int kv_valid = min(128, p.nkv - j * 128);
-      const bool full_tile = kv_valid == 128;
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      const int kv_valid = min(kKV, p.nkv - j * kKV);
+      const bool full_tile = kv_valid == kKV;
+      const uint32_t t_s = t_row + s * kKV;
       if (threadIdx.x == 64) ATT_TRACE(1, 4 * j + 0);
-      mbar_wait(&s_full, ph);
+      mbar_wait(&s_full[s], ph);
       if (threadIdx.x == 64) ATT_TRACE(1, 4 * j + 1);
-      // P is double-buffered and QK(j) completes after PV(j-2) on the in-order tensor pipe, so P[j & 1] is free here;
-      // only the (rare) O rescale below has to wait for PV(j-1)
+      // P[s] is free: QK(j) completes after PV(j-2) on the in-order tensor pipe.  Only the (rare) O rescale below
+      // has to wait for PV(j-1).
       tc_fence_after();
-      if (threadIdx.x == 64) ATT_TRACE(1, 4 * j + 2);
       float mx = -INFINITY;
       uint32_t va[32], vb[32];
       if (j == 0) {
-        // first tile: a max pass to establish the shift (TMEM loads software-pipelined against the math)
-        tmem_ld_x32(t_row, va);
+        // first tile: a max pass to establish the shift
+        tmem_ld_x32(t_s, va);
         tmem_ld_wait();
-        tmem_ld_x32(t_row + 32, vb);
+        tmem_ld_x32(t_s + 32, vb);
         mx = tile_max(va, 0, kv_valid, full_tile, mx);
         tmem_ld_wait();
-        tmem_ld_x32(t_row + 64, va);
         mx = tile_max(vb, 32, kv_valid, full_tile, mx);
-        tmem_ld_wait();
-        tmem_ld_x32(t_row + 96, vb);
-        mx = tile_max(va, 64, kv_valid, full_tile, mx);
-        tmem_ld_wait();
-        mx = tile_max(vb, 96, kv_valid, full_tile, mx);
         m_run = mx * sl2;
       }
-      bool redo = false;
       float sum = 0.f;
       for (int attempt = 0; attempt < 2; ++attempt) {
         const float neg_m = -m_run;
         sum = 0.f;
-        tmem_ld_x32(t_row, va);
+        tmem_ld_x32(t_s, va);
         tmem_ld_wait();
-        tmem_ld_x32(t_row + 32, vb);
+        tmem_ld_x32(t_s + 32, vb);  // in flight while the first half is exponentiated
         if (j > 0 && attempt == 0) mx = tile_max(va, 0, kv_valid, full_tile, mx);
-        emit_p(va, 0, neg_m, kv_valid, full_tile, sum, j & 1);
+        emit_p(va, 0, neg_m, kv_valid, full_tile, sum, s);
         tmem_ld_wait();
-        tmem_ld_x32(t_row + 64, va);
         if (j > 0 && attempt == 0) mx = tile_max(vb, 32, kv_valid, full_tile, mx);
-        emit_p(vb, 32, neg_m, kv_valid, full_tile, sum, j & 1);
-        tmem_ld_wait();
-        tmem_ld_x32(t_row + 96, vb);
-        if (j > 0 && attempt == 0) mx = tile_max(va, 64, kv_valid, full_tile, mx);
-        emit_p(va, 64, neg_m, kv_valid, full_tile, sum, j & 1);
-        tmem_ld_wait();
-        if (j > 0 && attempt == 0) mx = tile_max(vb, 96, kv_valid, full_tile, mx);
-        emit_p(vb, 96, neg_m, kv_valid, full_tile, sum, j & 1);
+        emit_p(vb, 32, neg_m, kv_valid, full_tile, sum, s);
         if (j == 0 || attempt == 1) break;
         const float m_tile = mx * sl2;
-        redo = __any_sync(0xffffffffu, m_tile > m_run + kSlack);
-        if (!redo) break;
-        // rare path: raise the shift of the rows that need it, rescale their O / row-sum columns, redo P
-        mbar_wait(&o_done, ph ^ 1);  // PV(j-1) must have retired before O is touched
+        if (!__any_sync(0xffffffffu, m_tile > m_run + kSlack)) break;
+        // rare path: raise the shift of the rows that need it, rescale their O, redo P
+        mbar_wait(&o_done, (j - 1) & 1);  // PV(j-1) must have retired before O is touched
         tc_fence_after();
         const float m_new = fmaxf(m_run, m_tile);
         const float alpha = ex2_approx(m_run - m_new);
@@ -310,10 +310,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       l_run += sum;
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       tc_fence_before();
-      mbar_arrive(&p_full);
+      mbar_arrive(&p_full[s]);
       if (threadIdx.x == 64) ATT_TRACE(1, 4 * j + 3);
     }
-    // epilogue: O / l   (l = row sum accumulated by the tensor core in the columns right after O)
+    // epilogue: O / l
     mbar_wait(&o_done, (n_tiles - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
@@ -361,9 +361,10 @@ static int launch_attention(const EsAttention* a, cudaStream_t stream) {
   {
     uint64_t dims[4] = {(uint64_t)a->d, (uint64_t)a->heads, (uint64_t)a->nkv, (uint64_t)a->batch};
     uint64_t str[4] = {0, (uint64_t)a->d * 2, (uint64_t)a->ldk * 2, (uint64_t)a->bsk * 2};
-    if (encode_tmap_16b(&tmK, a->k, 4, dims, str, box)) return -3;
+    const uint32_t boxkv[4] = {64u, 1u, static_cast<uint32_t>(kKV), 1u};
+    if (encode_tmap_16b(&tmK, a->k, 4, dims, str, boxkv)) return -3;
     uint64_t strv[4] = {0, (uint64_t)a->d * 2, (uint64_t)a->ldv * 2, (uint64_t)a->bsv * 2};
-    if (encode_tmap_16b(&tmV, a->v, 4, dims, strv, box)) return -3;
+    if (encode_tmap_16b(&tmV, a->v, 4, dims, strv, boxkv)) return -3;
   }
   AttParams p;
   p.d = a->d;
@@ -374,7 +375,7 @@ static int launch_attention(const EsAttention* a, cudaStream_t stream) {
   p.out = a->out;
   p.ldo = a->ldo;
   p.bso = a->bso;
-  const size_t smem = static_cast<size_t>(3 * NA + 4) * kAtomBytes + 128;  // + barriers; no alignment slack (see kernel)
+  const size_t smem = static_cast<size_t>(NA + 2) * kAtomBytes + 4 * NA * kKV * 128 + 128;  // Q + 2 P + 2x(K,V) + barriers
   auto kern = attention_kernel<T, NA>;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
