@@ -131,6 +131,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const bool has_work = kb_end > kb_begin;
 
   // ---- one-time setup ----------------------------------------------------------------------
+  // TMA load of k-block kb into its ring slot (producer thread only)
+  auto produce = [&](int kb) {
+    const int it = kb - kb_begin;
+    const int s = it % stages;
+    const uint32_t ph = (it / stages) & 1;
+    mbar_wait(&empty_bar[s], ph ^ 1);
+    uint8_t* sa = smem + s * kStageBytes;
+    uint8_t* sb = sa + kABytes;
+    mbar_expect_tx(&full_bar[s], kStageBytes);
+    if (kb < kb1) {
+      const int tap = kb / p.kblocks1;
+      const int cb = kb - tap * p.kblocks1;
+      int dx = 0, dy = 0;
+      if (p.taps == 9) {
+        dy = tap / 3 - 1;
+        dx = tap % 3 - 1;
+      }
+      tma_load_4d(sa, &tmA, &full_bar[s], cb * kBlockK, x0 + dx, y0 + dy, i0);
+      if (p.b_blocked) tma_load_3d(sb, &tmB, &full_bar[s], 0, b_noff + n0, kb);
+      else tma_load_3d(sb, &tmB, &full_bar[s], cb * kBlockK, tap, b_noff + n0);
+    } else {
+      const int cb = kb - kb1;
+      tma_load_4d(sa, &tmA2, &full_bar[s], cb * kBlockK, x0, y0, i0);  // centre tap (1x1)
+      tma_load_3d(sb, &tmB2, &full_bar[s], cb * kBlockK, 0, b2_noff + n0);
+    }
+  };
+  const int kb_prefill = min(kb_end, kb_begin + stages);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -145,6 +172,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     mbar_init(&accum_bar, 1);
     mbar_init(&res_bar, 1);
     fence_mbar_init();
+    // The first ring fill needs neither TMEM nor the other warps: issue it now so that the load latency overlaps
+    // the TMEM allocation and the CTA-wide barrier below.  (PDL: inputs may only be read after griddepcontrol.wait.)
+    pdl_wait();
+    for (int kb = kb_begin; kb < kb_prefill; ++kb) produce(kb);
   }
   if (warp == 1) {
     tmem_alloc(&tmem_base_smem, kTmemCols);
@@ -162,31 +193,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0) {
     // =============================== TMA producer ===========================================
     if (lane == 0) {
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        const int it = kb - kb_begin;
-        const int s = it % stages;
-        const uint32_t ph = (it / stages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * kStageBytes;
-        uint8_t* sb = sa + kABytes;
-        mbar_expect_tx(&full_bar[s], kStageBytes);
-        if (kb < kb1) {
-          const int tap = kb / p.kblocks1;
-          const int cb = kb - tap * p.kblocks1;
-          int dx = 0, dy = 0;
-          if (p.taps == 9) {
-            dy = tap / 3 - 1;
-            dx = tap % 3 - 1;
-          }
-          tma_load_4d(sa, &tmA, &full_bar[s], cb * kBlockK, x0 + dx, y0 + dy, i0);
-          if (p.b_blocked) tma_load_3d(sb, &tmB, &full_bar[s], 0, b_noff + n0, kb);
-          else tma_load_3d(sb, &tmB, &full_bar[s], cb * kBlockK, tap, b_noff + n0);
-        } else {
-          const int cb = kb - kb1;
-          tma_load_4d(sa, &tmA2, &full_bar[s], cb * kBlockK, x0, y0, i0);  // centre tap (1x1)
-          tma_load_3d(sb, &tmB2, &full_bar[s], cb * kBlockK, 0, b2_noff + n0);
-        }
-      }
+      for (int kb = kb_prefill; kb < kb_end; ++kb) produce(kb);
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =============================================
