@@ -143,56 +143,78 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int n, in
   out[r * dim + half + k] = sinf(a);
 }
 
-// ---------------------------------------------------------------- tiny-M linear: one warp per output column
+// ---------------------------------------------------------------- tiny-M linear: one warp per two output columns
+// x rows (activation applied once) are staged in shared memory; every lane streams 16 B weight vectors of its two
+// columns, so a block keeps 2 x 8 independent weight streams in flight (HBM-bound GEMV: the weights are read once).
+constexpr int kSlWarps = 8;
+constexpr int kSlCols = 2;
 template <typename T, int RC>
 __global__ void small_linear_kernel(const float* __restrict__ x, int ldx, const T* __restrict__ w,
                                     const float* __restrict__ bias, float* __restrict__ y, int ldy, int rows, int n,
                                     int k, int silu_in, int silu_out, int accumulate) {
+  extern __shared__ float xs[];  // [min(rows, RC)][k]
   pdl_launch_dependents();
   pdl_wait();  // PDL: inputs are produced by the preceding kernel
   const int lane = threadIdx.x & 31;
-  const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (col >= n) return;
-  const T* wr = w + static_cast<long long>(col) * k;
+  const int col0 = (blockIdx.x * kSlWarps + (threadIdx.x >> 5)) * kSlCols;
   for (int r0 = 0; r0 < rows; r0 += RC) {
-    float acc[RC];
+    const int nr = min(RC, rows - r0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nr * k; i += blockDim.x) {
+      const int r = i / k, c = i - r * k;
+      float xv = x[static_cast<long long>(r0 + r) * ldx + c];
+      xs[i] = silu_in ? silu_f(xv) : xv;
+    }
+    __syncthreads();
+    float acc[kSlCols][RC];
 #pragma unroll
-    for (int r = 0; r < RC; ++r) acc[r] = 0.f;
+    for (int cc = 0; cc < kSlCols; ++cc)
+#pragma unroll
+      for (int r = 0; r < RC; ++r) acc[cc][r] = 0.f;
     for (int kk = lane * 8; kk < k; kk += 256) {
-      const uint4 u = *reinterpret_cast<const uint4*>(wr + kk);
-      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-      float wf[8];
+      uint4 u[kSlCols];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = Cvt<T>::unpack2(uu[j]);
-        wf[2 * j] = f.x;
-        wf[2 * j + 1] = f.y;
+      for (int cc = 0; cc < kSlCols; ++cc)
+        u[cc] = (col0 + cc < n) ? *reinterpret_cast<const uint4*>(w + static_cast<long long>(col0 + cc) * k + kk)
+                                : make_uint4(0, 0, 0, 0);
+      float wf[kSlCols][8];
+#pragma unroll
+      for (int cc = 0; cc < kSlCols; ++cc) {
+        const uint32_t uu[4] = {u[cc].x, u[cc].y, u[cc].z, u[cc].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = Cvt<T>::unpack2(uu[j]);
+          wf[cc][2 * j] = f.x;
+          wf[cc][2 * j + 1] = f.y;
+        }
       }
 #pragma unroll
       for (int r = 0; r < RC; ++r) {
-        if (r0 + r < rows) {
-          const float* xr = x + static_cast<long long>(r0 + r) * ldx + kk;
+        if (r < nr) {
+          const float4 x0 = *reinterpret_cast<const float4*>(xs + r * k + kk);
+          const float4 x1 = *reinterpret_cast<const float4*>(xs + r * k + kk + 4);
+          const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float xv = xr[j];
-            if (silu_in) xv = silu_f(xv);
-            acc[r] += xv * wf[j];
-          }
+          for (int cc = 0; cc < kSlCols; ++cc)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[cc][r] += xv[j] * wf[cc][j];
         }
       }
     }
 #pragma unroll
-    for (int r = 0; r < RC; ++r) {
-      float a = acc[r];
+    for (int cc = 0; cc < kSlCols; ++cc)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (lane == 0 && r0 + r < rows) {
-        if (bias) a += bias[col];
-        if (silu_out) a = silu_f(a);
-        float* yp = y + static_cast<long long>(r0 + r) * ldy + col;
-        *yp = accumulate ? (*yp + a) : a;
+      for (int r = 0; r < RC; ++r) {
+        float a = acc[cc][r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0 && r < nr && col0 + cc < n) {
+          if (bias) a += bias[col0 + cc];
+          if (silu_out) a = silu_f(a);
+          float* yp = y + static_cast<long long>(r0 + r) * ldy + col0 + cc;
+          *yp = accumulate ? (*yp + a) : a;
+        }
       }
-    }
   }
 }
 
@@ -341,15 +363,29 @@ extern "C" int es_small_linear(int dtype, const float* x, int ldx, const void* w
                                int rows, int n, int k, int silu_in, int silu_out, int accumulate, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   ES_CHECK(k % 8 == 0 && ldx % 4 == 0, "es_small_linear: k must be a multiple of 8");
-  const int warps = 4;
-  dim3 grid(ceil_div(n, warps)), block(warps * 32);
+  constexpr int RC = 4;
+  const size_t smem = static_cast<size_t>(rows < RC ? rows : RC) * k * sizeof(float);
+  ES_CHECK(smem <= 48 * 1024, "es_small_linear: k too large (%d)", k);
+  dim3 grid(ceil_div(n, kSlWarps * kSlCols)), block(kSlWarps * 32);
   if (dtype == ES_DTYPE_BF16)
-    ES_CUDA(launch_kernel(small_linear_kernel<__nv_bfloat16, 8>, dim3(grid), dim3(block), 0, s, x, ldx, reinterpret_cast<const __nv_bfloat16*>(w), bias,
-                                                                 y, ldy, rows, n, k, silu_in, silu_out, accumulate));
+    ES_CUDA(launch_kernel(small_linear_kernel<__nv_bfloat16, RC>, dim3(grid), dim3(block), smem, s, x, ldx,
+                          reinterpret_cast<const __nv_bfloat16*>(w), bias, y, ldy, rows, n, k, silu_in, silu_out, accumulate));
   else
-    ES_CUDA(launch_kernel(small_linear_kernel<__half, 8>, dim3(grid), dim3(block), 0, s, x, ldx, reinterpret_cast<const __half*>(w), bias, y, ldy, rows,
-                                                          n, k, silu_in, silu_out, accumulate));
+    ES_CUDA(launch_kernel(small_linear_kernel<__half, RC>, dim3(grid), dim3(block), smem, s, x, ldx,
+                          reinterpret_cast<const __half*>(w), bias, y, ldy, rows, n, k, silu_in, silu_out, accumulate));
   ES_CUDA(cudaGetLastError());
+  return 0;
+}
+// Timeline probe: writes %globaltimer (ns) after every earlier kernel of the stream has completed.
+__global__ void stamp_kernel(unsigned long long* slot) {
+  pdl_wait();
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+extern "C" int es_stamp(unsigned long long* slot, void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  ES_CUDA(launch_kernel(stamp_kernel, dim3(1), dim3(1), 0, s, slot));
   return 0;
 }
 extern "C" int es_cfg_x0(const float* eps, const float* sample, const float* guidance, float alpha, float sigma, float* x0,

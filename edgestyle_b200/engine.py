@@ -78,6 +78,7 @@ class Lin:
     up: Optional[torch.Tensor] = None    # [G * n, rp]
     rp: int = 0
     block_n: int = 0
+    groups: int = 1  # > 1: `w` / `bias` hold (1 + G) copies stacked along N: [W; W + up_1 down_1; ...] (LoRA fused)
 
 
 @dataclass
@@ -117,8 +118,9 @@ class Tfm:
 
 
 class _Packer:
-    def __init__(self, sd, loras: Sequence[Dict[str, torch.Tensor]], dtype, device):
+    def __init__(self, sd, loras: Sequence[Dict[str, torch.Tensor]], dtype, device, fuse_lora: bool = True):
         self.sd, self.loras, self.dtype, self.device = sd, list(loras), dtype, device
+        self.fuse_lora = fuse_lora
 
     def f32(self, k):
         return self.sd[k].to(device=self.device, dtype=torch.float32).contiguous()
@@ -183,6 +185,17 @@ class _Packer:
             bias = bias[perm] if bias is not None else None
             if up is not None:
                 up = [u[perm] for u in up]
+        if up is not None and self.fuse_lora:
+            # W_g = W + up_g down_g (controllora.py:728-737 `fuse_lora`, LoRA scale 1.0), one copy per weight group
+            # stacked along N: a row segment of the batched pass then simply selects its copy (EsGemm.seg_b_noff).
+            # Costs 2 extra copies of the Linear weights in HBM (~0.46 GB) and removes the 82 skinny down-projection
+            # launches per step from the base pass.
+            G = len(up)
+            rp = rp_tot
+            ws_g = [w] + [w + up[g] @ down[g * rp:(g + 1) * rp] for g in range(G)]
+            bias_g = None if bias is None else torch.cat([bias] * (G + 1))
+            return Lin(self.mat(torch.cat(ws_g, 0)), None if bias_g is None else bias_g.to(self.device).contiguous(),
+                       n_tot, None, None, 0, block_n, G + 1)
         if up is not None:
             up = torch.cat(up, 0)
         return Lin(self.mat(w), None if bias is None else bias.to(self.device).contiguous(), n_tot,
@@ -276,6 +289,10 @@ class DenoiseEngine:
         self._bufs: Dict[str, torch.Tensor] = {}
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.fuse_gn_stats = os.environ.get("ES_FUSE_GN", "1") != "0"
+        # ControlLoRA update: "fused" = one fused weight copy per LoRA group (default), "unfused" = rank-r update as
+        # extra K-blocks of the accumulator (t = x down^T, then [x | t] [W | up]^T)
+        self.fuse_lora = os.environ.get("ES_LORA", "fused") != "unfused"
+        self.merge_early = os.environ.get("ES_MERGE_EARLY", "0") != "0"
         self._stats_of = {}
         self._kv_recompute = False  # True: redo the text K/V projections inside every step (reference behaviour)
         self.launches_per_step = 0
@@ -312,7 +329,7 @@ class DenoiseEngine:
     # ------------------------------------------------------------------------------------ packing
     def _pack_encoder(self, sd, loras) -> EncoderW:
         cfg = self.cfg
-        P = _Packer(sd, loras, self.dtype, self.dev)
+        P = _Packer(sd, loras, self.dtype, self.dev, self.fuse_lora)
         c0 = cfg.block_out_channels[0]
         wci = torch.zeros(c0, 64)
         wci[:, :9 * cfg.in_channels] = sd["conv_in.weight"].float().cpu().permute(0, 2, 3, 1).reshape(c0, -1)
@@ -539,7 +556,15 @@ class DenoiseEngine:
         """out = a @ L.w^T (+ LoRA per row segment) with the fused epilogue `ep`."""
         if ep.get("gn_ws") is not None:
             ep["rows_per_img"] = rows_per_img  # fused GroupNorm statistics are per image
-        if L.down is not None and lora_seg_imgs is not None and (lora_seg_imgs[1] + lora_seg_imgs[2]) > 0:
+        if L.groups > 1:
+            M = a.shape[0]
+            if lora_seg_imgs is None:
+                segs = ([0, M], [0], None)
+            else:
+                n0, n1, n2 = [s * rows_per_img for s in lora_seg_imgs]  # rows of: no-LoRA | group 0 | group 1
+                segs = ([0, n0, n0 + n1, n0 + n1 + n2], [0, L.n, 2 * L.n], None)
+            ops.gemm(a, L.w, L.n, out=out, bias=L.bias, block_n=L.block_n, segs=segs, **ep)
+        elif L.down is not None and lora_seg_imgs is not None and (lora_seg_imgs[1] + lora_seg_imgs[2]) > 0:
             n0, n1, n2 = [s * rows_per_img for s in lora_seg_imgs]  # rows of: no-LoRA | group 0 | group 1
             M = a.shape[0]
             t = self.buf(f"{tag}.lora_t", M, L.rp)
@@ -618,17 +643,21 @@ class DenoiseEngine:
             e1 = self.buf(f"{tag}.e1.{gi}", B, td, torch.float32)
             e2 = self.buf(f"{tag}.e2.{gi}", B, td, torch.float32)
             ops.small_linear(sin, E.te1[gi][0], E.te1[gi][1], e1, silu_out=True)
-            ops.small_linear(e1, E.te2[gi][0], E.te2[gi][1], e2)
+            # every consumer of emb applies SiLU first (ResnetBlock2D.time_emb_proj(nonlinearity(temb))): store silu(emb)
+            ops.small_linear(e1, E.te2[gi][0], E.te2[gi][1], e2, silu_out=True)
             # images of one group repeat the B timestep rows (n is a multiple of B)
             for rep in range(n // B):
-                ops.small_linear(e2, E.temb_w[gi][:nc], E.temb_b[gi][:nc], temb[r0:r0 + B, :nc], silu_in=True)
+                ops.small_linear(e2, E.temb_w[gi][:nc], E.temb_b[gi][:nc], temb[r0:r0 + B, :nc])
                 r0 += B
         return temb
 
-    def _encoder(self, E: EncoderW, x, imgs, temb, ctx, seg, tag):
-        """x: conv_in output (+cond) [imgs*hw, c0].  Returns 12 skip tensors + mid."""
+    def _encoder(self, E: EncoderW, x, imgs, temb, ctx, seg, tag, on_level=None):
+        """x: conv_in output (+cond) [imgs*hw, c0].  Returns 12 skip tensors + mid.  `on_level(li, tensor)` is called
+        right after residual level li (0..11 skips, 12 = mid) has been enqueued."""
         cfg = self.cfg
         skips = [x]
+        notify = on_level if on_level is not None else (lambda li, t: None)
+        notify(0, x)
         for i, (H, W) in enumerate(self.levels):
             c = cfg.block_out_channels[i]
             for j in range(cfg.layers_per_block):
@@ -645,6 +674,7 @@ class DenoiseEngine:
                     self._transformer(T, r_out, imgs, H, W, ctx, out, f"{tag}.L{i}", seg)
                 x = out
                 skips.append(x)
+                notify(len(skips) - 1, x)
             if E.down_conv[i] is not None:
                 Hn, Wn = self.levels[i + 1]
                 col = self.buf(f"{tag}.L{i}.col", imgs * Hn * Wn, 9 * c)
@@ -654,6 +684,7 @@ class DenoiseEngine:
                          gn_ws=self._stats_for(out, imgs, Hn * Wn), gn_groups=cfg.norm_num_groups)
                 x = out
                 skips.append(x)
+                notify(len(skips) - 1, x)
         H, W = self.levels[-1]
         c = cfg.block_out_channels[-1]
         M = imgs * H * W
@@ -663,6 +694,7 @@ class DenoiseEngine:
         self._transformer(E.mid_tfm, m0, imgs, H, W, ctx, m1, f"{tag}.mid", seg)
         mid = self.buf(f"{tag}.mid2", M, c)
         self._resnet(E.mid_res[1], m1, imgs, H, W, temb, mid, f"{tag}.mid")
+        notify(len(skips), mid)
         return skips, mid
 
     # ------------------------------------------------------------------------------------ the step
@@ -701,6 +733,7 @@ class DenoiseEngine:
         lora_of_block = (0, 1, 2, 2)  # segment class of base block: 0 = UNet rows (no LoRA), 1 = agn, 2 = clo
         results = {}                  # ("base"|"pose", block) -> (chain skips+mid list, first image of block in chain)
         done_events = []
+        level_events = []             # per chain: residual level -> event recorded once that level has been enqueued
         temb_pose = None
         for ci, (kind, blocks) in enumerate(self.chains):
             st = main if ci == 0 else self._chain_streams[ci - 1]
@@ -730,8 +763,16 @@ class DenoiseEngine:
                                  residual=cond(pose_cond[blk]))
                     seg = None
                 imgs = nb * B
+                lev = {}
+
+                def on_level(li, _t, lev=lev, st=st):
+                    lev[li] = torch.cuda.Event()
+                    lev[li].record(st)
+
+                level_events.append(lev)
                 sk, md = self._encoder(E, x_all[b0 * B * hw:(b0 + nb) * B * hw], imgs, temb_all[b0 * B:(b0 + nb) * B],
-                                       ctx_all[b0 * B * nt:(b0 + nb) * B * nt], seg, tag)
+                                       ctx_all[b0 * B * nt:(b0 + nb) * B * nt], seg, tag,
+                                       on_level if self.merge_early else None)
                 for i, blk in enumerate(blocks):
                     results[(kind, blk)] = (sk + [md], i * B)
                 ev = torch.cuda.Event()
@@ -763,21 +804,49 @@ class DenoiseEngine:
         scale = [float(s) for s in cond_scale]
         merged = {}
         side = self._merge_stream
-        for ev in done_events:
-            side.wait_event(ev)
+        if not self.merge_early:
+            for ev in done_events:
+                side.wait_event(ev)
+
+        def block_span(kind, blks, li):
+            """rows of consecutive image blocks `blks` at level li when they sit back to back in ONE chain buffer"""
+            outs0, first0 = results[(kind, blks[0])]
+            for j, blk in enumerate(blks):
+                outs, first = results[(kind, blk)]
+                if outs is not outs0 or first != first0 + j * B:
+                    return None
+            c, H, W = self.res_shapes[li]
+            return outs0[li][first0 * H * W:(first0 + len(blks) * B) * H * W]
+
+        # early: level by level as the encoders produce them (only the mid level is left on the critical path between
+        # the encoders and the decoder); late: after both encoders, in the order the decoder consumes them
+        order = range(len(self.res_shapes)) if self.merge_early else reversed(range(len(self.res_shapes)))
         with torch.cuda.stream(side):
-            for li in reversed(range(len(self.res_shapes))):
+            for li in order:
+                if self.merge_early:
+                    for lev in level_events:
+                        side.wait_event(lev[li])
                 c, H, W = self.res_shapes[li]
                 n = B * H * W
                 rb = self.buf(f"zres_b{li}", 3 * n, c)
                 rp = self.buf(f"zres_p{li}", 3 * n, c)
                 zw, zb = self.zero_base[li]
-                for slot, (blk, noff) in enumerate(((1, 0), (2, c), (3, c))):  # agn | clo(cond 2) | clo(cond 4)
-                    ops.gemm(block_rows("base", blk, li), zw, c, out=rb[slot * n:(slot + 1) * n], bias=zb,
-                             segs=([0, n], [noff], None))
-                for blk in range(3):
-                    ops.gemm(block_rows("pose", blk, li), self.zero_pose[li][0], c, out=rp[blk * n:(blk + 1) * n],
-                             bias=self.zero_pose[li][1])
+                # zero convs (controllora.py:240-254): the three ControlLoRA image blocks (agn | clo | clo) are one GEMM
+                # with the weight set selected per row segment, the three openpose blocks one GEMM
+                span = block_span("base", (1, 2, 3), li)
+                if span is not None:
+                    ops.gemm(span, zw, c, out=rb, bias=zb, segs=([0, n, 3 * n], [0, c], None))
+                else:
+                    for slot, (blk, noff) in enumerate(((1, 0), (2, c), (3, c))):  # agn | clo(cond 2) | clo(cond 4)
+                        ops.gemm(block_rows("base", blk, li), zw, c, out=rb[slot * n:(slot + 1) * n], bias=zb,
+                                 segs=([0, n], [noff], None))
+                span = block_span("pose", (0, 1, 2), li)
+                if span is not None:
+                    ops.gemm(span, self.zero_pose[li][0], c, out=rp, bias=self.zero_pose[li][1])
+                else:
+                    for blk in range(3):
+                        ops.gemm(block_rows("pose", blk, li), self.zero_pose[li][0], c, out=rp[blk * n:(blk + 1) * n],
+                                 bias=self.zero_pose[li][1])
                 res = [rb[:n], rp[:n], rb[n:2 * n], rp[n:2 * n], rb[2 * n:], rp[2 * n:]]
                 z = self.buf(f"merge_z{li}", n, c, torch.float32)
                 unet_rows = block_rows("base", 0, li)
@@ -793,7 +862,8 @@ class DenoiseEngine:
                 merged[li] = torch.cuda.Event()
                 merged[li].record(side)
         if mode == "residuals":
-            main.wait_event(merged[0])  # the side stream is in order: the last event covers all levels
+            # the side stream is in order: the last event covers all levels
+            main.wait_event(merged[len(self.res_shapes) - 1 if self.merge_early else 0])
             return
         main.wait_event(merged[len(self.res_shapes) - 1])
         # -- UNet decoder

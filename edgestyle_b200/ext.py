@@ -76,6 +76,7 @@ EXPORTS = {
     "es_add": (C.c_int, [C.c_int, vp, ll, vp, ll, vp, ll, C.c_int, C.c_int, vp]),
     "es_cfg_ddim": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]),
     "es_cfg_x0": (C.c_int, [vp, vp, vp, C.c_float, C.c_float, vp, C.c_int, C.c_int, vp]),
+    "es_stamp": (C.c_int, [vp, vp]),
     "es_lincomb4": (C.c_int, [vp, C.c_float, vp, C.c_float, vp, C.c_float, vp, C.c_float, vp, ll, vp]),
 }
 

@@ -203,6 +203,10 @@ int es_cfg_x0(const float* eps, const float* sample, const float* guidance, floa
 int es_lincomb4(float* out, float c0, const float* x0, float c1, const float* x1, float c2, const float* x2, float c3,
                 const float* x3, long long n, void* stream);
 
+/* Profiling probe (tools/timeline.py): a 1-thread kernel that stores the GPU's %globaltimer (ns) into *slot once all
+ * earlier work of `stream` has completed -- lets a captured multi-stream step be timed op by op. */
+int es_stamp(unsigned long long* slot, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
