@@ -241,6 +241,45 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const long long row = (static_cast<long long>(img_c) * p.H + y) * p.W + x;
     const int img = p.flat ? (p.rows_per_img > 0 ? x / p.rows_per_img : 0) : img_c;
 
+    // A tail tile of a row segment must not store the rows that belong to the next segment: those tiles (and
+    // fp32 outputs) take the per-thread store path below; everything else goes through smem + TMA.  The staged
+    // per-column vector below needs one image per warp (32 rows).
+    const bool rv_uniform = !p.rowvec || (p.flat ? (p.rows_per_img > 0 && p.rows_per_img % 32 == 0)
+                                                 : ((p.bw * p.bh) % 32 == 0));
+    const bool use_tma_epi = p.tma_epi && rv_uniform && !(p.flat && x0 + kBlockM > x_end && x_end < p.W);
+    // ---- while the mainloop runs: fetch this thread's slice of the per-column epilogue vector
+    //      vec[warp][col] = bias[col] + rowvec[image of the warp's rows][col]  (registers now, smem after the MMAs)
+    constexpr int kVPT = (BLOCK_N + 127) / 128;
+    float vpre[4][kVPT];
+    if (use_tma_epi) {
+      const int et = threadIdx.x - 64;
+#pragma unroll
+      for (int i = 0; i < kVPT; ++i) {
+        const int col = et + 128 * i;
+        const bool col_ok = col < BLOCK_N && n0 + col < p.N;
+        const float bv = (col_ok && p.bias) ? p.bias[b_noff + n0 + col] : 0.f;
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) {
+          float rv = 0.f;
+          if (col_ok && p.rowvec) {
+            // image of row w4*32 of this tile (the warp's rows all share it)
+            const int r4 = w4 * 32;
+            int ximg;
+            bool ok4;
+            if (p.flat) {
+              ximg = (x0 + r4) / p.rows_per_img;
+              ok4 = x0 + r4 < x_end;
+            } else {
+              ximg = i0 + r4 / (p.bw * p.bh);
+              ok4 = ximg < p.NI;
+            }
+            if (ok4) rv = p.rowvec[static_cast<long long>(ximg) * p.rowvec_ld + n0 + col];
+          }
+          vpre[w4][i] = bv + rv;
+        }
+      }
+    }
+
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
     if (threadIdx.x == 64) GEMM_TRACE(4);
@@ -250,9 +289,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
     const long long tiles = static_cast<long long>(gridDim.x) * gridDim.y;
     bool from_ws = false;
-    // A tail tile of a row segment must not store the rows that belong to the next segment: those tiles (and
-    // fp32 outputs) take the per-thread store path below; everything else goes through smem + TMA.
-    const bool use_tma_epi = p.tma_epi && !(p.flat && x0 + kBlockM > x_end && x_end < p.W);
     if (p.splits > 1) {
       // layout [split][tile][BLOCK_N/4][128 rows] float4: a warp's 32 rows store 512 contiguous bytes
       float4* wp = reinterpret_cast<float4*>(p.ws_partial) +
@@ -356,7 +392,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       };
       if (use_tma_epi) {
         // ---------------- smem-staged epilogue: 64-column panels [128 rows x 128 B], SWIZZLE_128B ----------------
-        // The pipeline's smem is free (every MMA has retired), so the panels alias the stage buffers.
+        // The pipeline's smem is free (every MMA has retired), so the panels alias the stage buffers; the staged
+        // epilogue vector sits right behind them.
         constexpr int NOUT = BLOCK_N;                      // accumulator columns per tile
         const bool geglu = p.act == ES_ACT_GEGLU;
         const int n_tile_out = geglu ? NOUT / 2 : NOUT;    // output columns of this tile
@@ -369,42 +406,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int pn = 0; pn < full_panels; ++pn) tma_load_4d(smem + pn * 16384, &tmR, &res_bar, oc0 + pn * 64, x0, y0, i0);
           if (rem) tma_load_4d(smem + full_panels * 16384, &tmRp, &res_bar, oc0 + full_panels * 64, x0, y0, i0);
         }
-        if (has_res) mbar_wait(&res_bar, 0);
-        constexpr int HALF = NOUT / 2;
-#pragma unroll 1
-        for (int c = 0; c < n_tile_out; c += 16) {
-          float o[16];
-          if (geglu) {
-            float a[16], g[16];
-            load_cols(c, a);
-            load_cols(HALF + c, g);
+        float* vec_s = reinterpret_cast<float*>(smem + ((NOUT + 63) / 64) * 16384);  // [4 warps][BLOCK_N]
+        {
+          const int et = threadIdx.x - 64;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float av = a[j], gv = g[j];
-              if (p.bias) {
-                av += p.bias[b_noff + n0 + c + j];
-                gv += p.bias[b_noff + n0 + HALF + c + j];
-              }
-              o[j] = p.alpha * av * gelu_erf_f(gv);
+          for (int i = 0; i < kVPT; ++i) {
+            const int col = et + 128 * i;
+            if (col < BLOCK_N) {
+#pragma unroll
+              for (int w4 = 0; w4 < 4; ++w4) vec_s[w4 * BLOCK_N + col] = vpre[w4][i];
             }
-          } else {
-            load_cols(c, o);
-            const int valid = p.N - (n0 + c);  // columns past N are clipped by the TMA store
-            if (p.bias) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (j < valid) o[j] += p.bias[b_noff + n0 + c + j];
-            }
-            if (p.rowvec && row_ok) {
-              const float* rv = p.rowvec + static_cast<long long>(img) * p.rowvec_ld + n0 + c;
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (j < valid) o[j] += rv[j];
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] *= p.alpha;
           }
-          // smem location of this thread's 32 bytes (two 16 B chunks)
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (has_res) mbar_wait(&res_bar, 0);
+        const float* vrow = vec_s + q * BLOCK_N;
+        constexpr int HALF = NOUT / 2;
+        // one 16-column chunk: accumulator (+ gate) -> epilogue math -> this thread's 32 bytes of the smem panel
+        auto finish_chunk = [&](int c, float (&o)[16]) {
           const int pn = c >> 6;
           uint8_t* pbase = smem + pn * 16384;
           uint4* d0;
@@ -435,6 +454,87 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           w1.z = Cvt<T>::pack2(o[12], o[13]); w1.w = Cvt<T>::pack2(o[14], o[15]);
           *d0 = w0;
           *d1 = w1;
+        };
+        auto vec16 = [&](int col, float (&b)[16]) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 f = *reinterpret_cast<const float4*>(vrow + col + 4 * j);
+            b[4 * j] = f.x; b[4 * j + 1] = f.y; b[4 * j + 2] = f.z; b[4 * j + 3] = f.w;
+          }
+        };
+        if (from_ws) {
+          // split-K last arriver: the accumulator is the sum of the partial tiles in the workspace
+#pragma unroll 1
+          for (int c = 0; c < n_tile_out; c += 16) {
+            float o[16], b[16];
+            if (geglu) {
+              float a[16], g[16], bg[16];
+              load_cols(c, a);
+              load_cols(HALF + c, g);
+              vec16(c, b);
+              vec16(HALF + c, bg);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = p.alpha * (a[j] + b[j]) * gelu_erf_f(g[j] + bg[j]);
+            } else {
+              load_cols(c, o);
+              vec16(c, b);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = (o[j] + b[j]) * p.alpha;
+            }
+            finish_chunk(c, o);
+          }
+        } else if (geglu) {
+          // TMEM loads of chunk c+1 (value and gate columns) are in flight while chunk c is processed
+          uint32_t va[2][16], vg[2][16];
+          tmem_ld_x16(t_row, va[0]);
+          tmem_ld_x16(t_row + HALF, vg[0]);
+          auto geglu_chunk = [&](int c, const uint32_t (&a)[16], const uint32_t (&g)[16]) {
+            float o[16], b[16], bg[16];
+            vec16(c, b);
+            vec16(HALF + c, bg);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              o[j] = p.alpha * (__uint_as_float(a[j]) + b[j]) * gelu_erf_f(__uint_as_float(g[j]) + bg[j]);
+            finish_chunk(c, o);
+          };
+#pragma unroll 1
+          for (int c = 0; c < n_tile_out; c += 32) {
+            tmem_ld_wait();
+            if (c + 16 < n_tile_out) {
+              tmem_ld_x16(t_row + c + 16, va[1]);
+              tmem_ld_x16(t_row + HALF + c + 16, vg[1]);
+            }
+            geglu_chunk(c, va[0], vg[0]);
+            if (c + 16 < n_tile_out) {
+              tmem_ld_wait();
+              if (c + 32 < n_tile_out) {
+                tmem_ld_x16(t_row + c + 32, va[0]);
+                tmem_ld_x16(t_row + HALF + c + 32, vg[0]);
+              }
+              geglu_chunk(c + 16, va[1], vg[1]);
+            }
+          }
+        } else {
+          uint32_t v[2][16];
+          tmem_ld_x16(t_row, v[0]);
+          auto plain_chunk = [&](int c, const uint32_t (&a)[16]) {
+            float o[16], b[16];
+            vec16(c, b);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = (__uint_as_float(a[j]) + b[j]) * p.alpha;
+            finish_chunk(c, o);
+          };
+#pragma unroll 1
+          for (int c = 0; c < n_tile_out; c += 32) {
+            tmem_ld_wait();
+            if (c + 16 < n_tile_out) tmem_ld_x16(t_row + c + 16, v[1]);
+            plain_chunk(c, v[0]);
+            if (c + 16 < n_tile_out) {
+              tmem_ld_wait();
+              if (c + 32 < n_tile_out) tmem_ld_x16(t_row + c + 32, v[0]);
+              plain_chunk(c + 16, v[1]);
+            }
+          }
         }
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -636,6 +736,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return 0;
 }
 
+}  // namespace es
+#include "gemm_pair.cuh"
+namespace es {
+
 static int pick_block_n(int n, int m_tiles, int act, int kb_total) {
   // Measured on B200 (tools/smallm_sweep.py, tools/gemm_sweep.py):
   //  * small M with a long K (8x8-level convs, M <= 512): 64-wide tiles + split-K stream the weights best;
@@ -769,6 +873,12 @@ static int gemm_dispatch(const EsGemm* g, cudaStream_t stream) {
   if (g->act == ES_ACT_GEGLU) ES_CHECK(g->n % 2 == 0 && !g->out_fp32 && !g->residual && !g->rowvec, "es_gemm: bad GEGLU config");
 
   int bn_tile = g->block_n > 0 ? g->block_n : pick_block_n(g->n, m_tiles, g->act, g->taps * ceil_div(g->c1, kBlockK));
+  // block_n == 320 selects the CTA-pair kernel (256 x 320 tiles, cta_group::2); problems it cannot run fall back
+  bool pair = false;
+  if (bn_tile == kPairN) {
+    pair = gemm_pair_eligible(g, kp, m_tiles);
+    if (!pair) bn_tile = g->act == ES_ACT_GEGLU ? kPairNH : pick_block_n(g->n, m_tiles, g->act, g->taps * ceil_div(g->c1, kBlockK));
+  }
   const int n_tiles = ceil_div(g->n, bn_tile);
   if (g->act == ES_ACT_GEGLU) ES_CHECK(g->n % bn_tile == 0, "es_gemm: GEGLU needs n %% block_n == 0 (n=%d bn=%d)", g->n, bn_tile);
 
@@ -789,7 +899,9 @@ static int gemm_dispatch(const EsGemm* g, cudaStream_t stream) {
     if (encode_tmap_16b(&tmA, g->a, 4, dims, strides, box)) return -3;
   }
   kp.b_blocked = g->b_blocked;
-  if (g->b_blocked) {
+  if (pair) {
+    tmB = tmA;  // the pair launcher builds its own weight maps (80-row boxes)
+  } else if (g->b_blocked) {
     // K-block-major weights: [taps * kblocks1][n_total_b][64] -- every B tile is one contiguous BLOCK_N x 128 B chunk
     uint64_t dims[3] = {64, static_cast<uint64_t>(g->n_total_b), static_cast<uint64_t>(g->taps) * kp.kblocks1};
     uint64_t strides[3] = {0, 128, static_cast<uint64_t>(g->n_total_b) * 128};
@@ -819,7 +931,11 @@ static int gemm_dispatch(const EsGemm* g, cudaStream_t stream) {
     uint64_t dimsb[3] = {static_cast<uint64_t>(g->c2), 1, static_cast<uint64_t>(g->n_total_b2)};
     uint64_t stridesb[3] = {0, static_cast<uint64_t>(g->c2) * 2, static_cast<uint64_t>(g->c2) * 2};
     uint32_t boxb[3] = {static_cast<uint32_t>(kBlockK), 1u, static_cast<uint32_t>(bn_tile)};
-    if (encode_tmap_16b(&tmB2, g->b2, 3, dimsb, stridesb, boxb)) return -3;
+    if (!pair && encode_tmap_16b(&tmB2, g->b2, 3, dimsb, stridesb, boxb)) return -3;
+  }
+  if (pair) {
+    ES_CHECK(g->n_total_b >= g->n, "es_gemm: n_total_b < n");
+    return launch_gemm_pair<T>(tmA, tmA2, kp, m_tiles, g, stream);
   }
 
   switch (bn_tile) {

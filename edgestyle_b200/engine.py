@@ -61,7 +61,9 @@ def _pad8(n: int) -> int:
 
 
 def _geglu_block_n(n: int) -> int:
-    for bn in (256, 160, 128, 64, 32):
+    # 160 first: the CTA-pair kernel (block_n 320) reads the value/gate permutation in sub-tiles of 160 columns, so
+    # both kernels can run the same packed weights
+    for bn in (160, 256, 128, 64, 32):
         if n % bn == 0:
             return bn
     raise ValueError(f"GEGLU width {n} is not a multiple of 32")

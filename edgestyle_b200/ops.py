@@ -108,6 +108,13 @@ class GemmTuner:
             if tiles <= 148 and kb_total >= 16:
                 sks += sorted({s for s in (2, 3, 4, 6, 8, 12, 16, 24, 296 // tiles) if 2 <= s <= kb_total // 4 and s * tiles <= 2 * 296})
             out += [(bn, sk) for sk in sks]
+        # CTA-pair kernel (256 x 320 tiles, one persistent cluster per TPC); GEGLU weights must be packed in 160-tiles
+        if n % 320 == 0 and (not fixed_bn or fixed_bn in (160, 320)) and m_tiles >= 2:
+            units = ((m_tiles + 1) // 2) * (n // 320)
+            sks = [1]
+            if units <= 37 and kb_total >= 16:
+                sks += sorted({s for s in (2, 3, 4, 6, 8, 12, 74 // units) if 2 <= s <= kb_total // 4 and s * units <= 148})
+            out += [(320, sk) for sk in sks]
         return out
 
     def tune(self, key, run, M, n, kb_total, act, fixed_bn):

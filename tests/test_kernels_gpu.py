@@ -217,6 +217,99 @@ def test_conv3x3_fused_groupnorm_stats(n_img, h, w, cin, cout, split):
     _close(y, ref.permute(0, 2, 1).reshape(-1, cout), 5e-3, 5e-3, "gn apply with fused stats")
 
 
+# ------------------------------------------------------------------------------------------ CTA-pair GEMM (block_n = 320)
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K,split_k", [(256, 320, 320, 1), (1024, 640, 1280, 1), (384, 320, 64, 1), (300, 960, 200, 1),
+                                           (32768, 320, 320, 1), (20000, 640, 640, 1), (512, 1280, 5120, 4),
+                                           (256, 320, 2304, 5), (2048, 1280, 1280, 0)])
+def test_gemm_pair_flat(M, N, K, split_k, dtype):
+    """cta_group::2 persistent kernel: bias + residual epilogue, odd tile counts, tails, split-K, many units per cluster."""
+    from edgestyle_b200 import ops
+
+    ops.set_gemm_workspace(256 << 20)
+    a = _rand(M, K, dtype=dtype, seed=201)
+    b = _rand(N, K, dtype=dtype, scale=K ** -0.5, seed=202)
+    bias = _rand(N, dtype=torch.float32, seed=203)
+    res = _rand(M, N, dtype=dtype, seed=204)
+    want = a.float() @ b.float().t() + bias + res.float()
+    tol = 2e-2 if dtype == torch.bfloat16 else 5e-3
+    for _ in range(2):
+        out = torch.zeros(M, N, device=DEV, dtype=dtype)
+        ops.gemm(a, b, N, out=out, bias=bias, residual=res, block_n=320, split_k=split_k)
+        _close(out, want, tol, tol, f"pair gemm {M}x{N}x{K} sk={split_k}")
+
+
+def test_gemm_pair_geglu_rowvec_alpha_segments():
+    from edgestyle_b200 import ops
+
+    # GEGLU: value/gate columns permuted in tiles of 160 (80 value + 80 gate)
+    M, C, bn = 768, 320, 160
+    a = _rand(M, C, seed=205)
+    w = _rand(8 * C, C, scale=C ** -0.5, seed=206)
+    bias = _rand(8 * C, dtype=torch.float32, seed=207)
+    half = bn // 2
+    idx = []
+    for t in range(8 * C // bn):
+        idx += list(range(t * half, (t + 1) * half)) + list(range(4 * C + t * half, 4 * C + (t + 1) * half))
+    idx = torch.tensor(idx, device=DEV)
+    u = a.float() @ w.float().t() + bias
+    want = u[:, :4 * C] * F.gelu(u[:, 4 * C:])
+    for bn_launch in (160, 320):  # the single-CTA kernel and the pair kernel read the same permuted weights
+        out = torch.zeros(M, 4 * C, device=DEV, dtype=torch.float16)
+        ops.gemm(a, w[idx].contiguous(), 8 * C, out=out, bias=bias[idx].contiguous(), act=1, block_n=bn_launch)
+        _close(out, want, 6e-3, 6e-3, f"geglu bn={bn_launch}")
+    # per-image row vector + alpha
+    N, K = 640, 192
+    a = _rand(1024, K, seed=208)
+    b = _rand(N, K, scale=K ** -0.5, seed=209)
+    rowvec = _rand(4, N, dtype=torch.float32, seed=210)
+    out = torch.zeros(1024, N, device=DEV, dtype=torch.float16)
+    ops.gemm(a, b, N, out=out, rowvec=rowvec, rows_per_img=256, alpha=0.5, block_n=320)
+    _close(out, 0.5 * (a.float() @ b.float().t() + rowvec.repeat_interleave(256, 0)), 4e-3, 4e-3, "pair rowvec")
+    # row segments select weight copies (fused ControlLoRA): segment sizes are multiples of 256 rows
+    rows = [0, 512, 1024, 2048]
+    x = _rand(2048, 320, seed=211)
+    w3 = _rand(3 * 320, 320, scale=320 ** -0.5, seed=212)
+    b3 = _rand(3 * 320, dtype=torch.float32, seed=213)
+    out = torch.zeros(2048, 320, device=DEV, dtype=torch.float16)
+    ops.gemm(x, w3, 320, out=out, bias=b3, segs=(rows, [0, 320, 640], None), block_n=320)
+    for s in range(3):
+        sl = slice(rows[s], rows[s + 1])
+        _close(out[sl], x[sl].float() @ w3[s * 320:(s + 1) * 320].float().t() + b3[s * 320:(s + 1) * 320], 4e-3, 4e-3,
+               f"pair segment {s}")
+
+
+@pytest.mark.parametrize("n_img,h,w,cin,cout,split_k", [(2, 64, 64, 320, 320, 1), (3, 32, 32, 64, 640, 1), (2, 16, 16, 640, 320, 0),
+                                                        (8, 8, 8, 128, 640, 3), (3, 8, 8, 64, 320, 1), (1, 24, 128, 64, 320, 1)])
+def test_conv3x3_pair(n_img, h, w, cin, cout, split_k):
+    from edgestyle_b200 import ops
+
+    ops.set_gemm_workspace(256 << 20)
+    x = _rand(n_img * h * w, cin, seed=214)
+    wt = _rand(cout, 9 * cin, scale=(9 * cin) ** -0.5, seed=215)
+    bias = _rand(cout, dtype=torch.float32, seed=216)
+    rowvec = _rand(n_img, cout, dtype=torch.float32, seed=217)
+    res = _rand(n_img * h * w, cout, seed=218)
+    cx = 192
+    xs = _rand(n_img * h * w, cx, seed=219)
+    wsc = _rand(cout, cx, scale=cx ** -0.5, seed=220)
+    conv = F.conv2d(x.float().view(n_img, h, w, cin).permute(0, 3, 1, 2), wt.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2),
+                    bias, padding=1) + rowvec[:, :, None, None]
+    conv = conv.permute(0, 2, 3, 1).reshape(-1, cout)
+    ws = torch.zeros(n_img, 32, 2, device=DEV)
+    out = torch.zeros(n_img * h * w, cout, device=DEV, dtype=torch.float16)
+    ops.gemm(x, wt, cout, out=out, taps=9, whn=(w, h, n_img), bias=bias, rowvec=rowvec, residual=res, c1=cin, block_n=320,
+             split_k=split_k, gn_ws=ws if (h * w) % 32 == 0 else None, gn_groups=32)
+    _close(out, conv + res.float(), 6e-3, 6e-3, "pair conv3x3 + residual")
+    if (h * w) % 32 == 0:
+        o = out.float().view(n_img, h * w, 32, cout // 32)
+        _close(ws, torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1), 0.05, 2e-3, "pair fused gn stats")
+    out2 = torch.zeros(n_img * h * w, cout, device=DEV, dtype=torch.float16)
+    ops.gemm(x, wt, cout, out=out2, taps=9, whn=(w, h, n_img), bias=bias, rowvec=rowvec, a2=xs, b2=wsc, c1=cin, block_n=320,
+             split_k=split_k)
+    _close(out2, conv + xs.float() @ wsc.float().t(), 6e-3, 6e-3, "pair conv3x3 + shortcut")
+
+
 # ------------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("batch,heads,d,nq,nkv", [(2, 8, 40, 4096, 4096), (2, 8, 80, 1024, 1024), (3, 8, 160, 256, 256),

@@ -8,25 +8,32 @@ from edgestyle_b200 import ops  # noqa: E402
 lib = ext.load()
 lib.es_gemm_trace.restype = C.c_int
 lib.es_gemm_trace.argtypes = [C.c_void_p]
-names = ["start", "setup done", "first stage full (MMA)", "last MMA issued", "accum visible (epi)", "epilogue done", "dealloc"]
-for (M, N, K, res) in [(24576, 320, 320, True), (24576, 320, 320, False), (8192, 320, 320, True), (24576, 320, 1280, True),
-                       (2048, 1280, 1280, True), (512, 1280, 1280, True)]:
+names = ["start", "setup done", "first stage full (MMA)", "last MMA issued", "accum visible (epi)", "epilogue done", "dealloc/all units", "kb8 full", "kb24 full"]
+for (M, N, K, res, bn, conv) in [(32768, 320, 320, False, 320, (64, 64, 8)), (32768, 320, 320, False, 320, None), (32768, 320, 1280, False, 320, None),
+                                 (8192, 640, 640, False, 320, (32, 32, 8)), (32768, 320, 320, True, 160, None), (32768, 320, 320, False, 160, None), (32768, 320, 320, False, 32, None),
+                                 (8192, 320, 320, True, 32, None), (32768, 320, 1280, True, 160, None),
+                                 (2048, 1280, 1280, True, 128, None), (512, 1280, 1280, True, 32, None),
+                                 (32768, 320, 320, False, 160, (64, 64, 8)), (8192, 640, 640, False, 160, (32, 32, 8))]:
+    taps = 9 if conv else 1
     a = torch.randn(M, K, device="cuda", dtype=torch.float16)
-    b = torch.randn(N, K, device="cuda", dtype=torch.float16)
+    b = torch.randn(N, K * taps, device="cuda", dtype=torch.float16)
     out = torch.empty(M, N, device="cuda", dtype=torch.float16)
     r = torch.randn(M, N, device="cuda", dtype=torch.float16) if res else None
     bias = torch.zeros(N, device="cuda")
+    kw = dict(out=out, bias=bias, residual=r, block_n=bn, split_k=1)
+    if conv:
+        kw.update(taps=9, whn=conv, c1=K)
     for _ in range(3):
-        ops.gemm(a, b, N, out=out, bias=bias, residual=r)
+        ops.gemm(a, b, N, **kw)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(20):
-        ops.gemm(a, b, N, out=out, bias=bias, residual=r)
+        ops.gemm(a, b, N, **kw)
     e1.record()
     torch.cuda.synchronize()
     buf = (C.c_longlong * 16)()
     lib.es_gemm_trace(buf)
-    t = list(buf)[:7]
-    print(f"M={M} N={N} K={K} residual={res}: {e0.elapsed_time(e1) * 50:.1f} us/launch; CTA(1,0) cycles:",
+    t = list(buf)[:9]
+    print(f"M={M} N={N} K={K}x{taps} bn={bn} residual={res}: {e0.elapsed_time(e1) * 50:.1f} us/launch; CTA(1,0) cycles:",
           ", ".join(f"{n}=+{t[i] - t[0]}" for i, n in enumerate(names)))

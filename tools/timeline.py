@@ -78,10 +78,10 @@ for nm in ("small_linear", "im2col3x3", "upsample2x", "nchw_to_nhwc", "timestep_
 _enc = eng._encoder
 
 
-def enc_wrapped(E, x_, imgs, temb, ctx, seg, tag):
+def enc_wrapped(E, x_, imgs, temb, ctx, seg, tag, on_level=None):
     if torch.cuda.is_current_stream_capturing():
         stamp("PHASE", f"begin encoder {tag}")
-    r = _enc(E, x_, imgs, temb, ctx, seg, tag)
+    r = _enc(E, x_, imgs, temb, ctx, seg, tag, on_level)
     if torch.cuda.is_current_stream_capturing():
         stamp("PHASE", f"end encoder {tag}")
     return r
