@@ -20,6 +20,7 @@ namespace es {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kGemmThreads = 192;
+constexpr int kGnSlots = 34;  // GroupNorm groups one output tile can touch (fused statistics), per image of the tile
 
 // Optional event trace (clock64 stamps of CTA (1,0,0)) for pipeline analysis: build with -DES_GEMM_TRACE.
 #ifdef ES_GEMM_TRACE
@@ -407,8 +408,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (rem) tma_load_4d(smem + full_panels * 16384, &tmRp, &res_bar, oc0 + full_panels * 64, x0, y0, i0);
         }
         float* vec_s = reinterpret_cast<float*>(smem + ((NOUT + 63) / 64) * 16384);  // [4 warps][BLOCK_N]
+        float* gstat_s = vec_s + 4 * BLOCK_N;                                        // [4 images][kGnSlots][2]
+        // GroupNorm statistics of the finished tile are taken from the smem panels (the rounded values the consumer
+        // will read), one 8-column chunk per lane, reduced in smem and flushed with one atomic per (image, group)
+        const bool gn_panel = p.gn_ws && !geglu && p.gn_cpg >= 8 && BLOCK_N / p.gn_cpg + 2 <= kGnSlots;
         {
           const int et = threadIdx.x - 64;
+          if (gn_panel)
+            for (int i = et; i < 4 * kGnSlots * 2; i += 128) gstat_s[i] = 0.f;
 #pragma unroll
           for (int i = 0; i < kVPT; ++i) {
             const int col = et + 128 * i;
@@ -446,7 +453,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               o[2 * j + 1] += f.y;
             }
           }
-          if (p.gn_ws && !geglu) gn_accumulate(o, c);
+          if (p.gn_ws && !geglu && !gn_panel) gn_accumulate(o, c);
           uint4 w0, w1;
           w0.x = Cvt<T>::pack2(o[0], o[1]); w0.y = Cvt<T>::pack2(o[2], o[3]);
           w0.z = Cvt<T>::pack2(o[4], o[5]); w0.w = Cvt<T>::pack2(o[6], o[7]);
@@ -542,8 +549,64 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int pn = 0; pn < full_panels; ++pn) tma_store_4d(&tmO, smem + pn * 16384, oc0 + pn * 64, x0, y0, i0);
           if (rem) tma_store_4d(&tmOp, smem + full_panels * 16384, oc0 + full_panels * 64, x0, y0, i0);
           tma_store_commit();
-          tma_store_wait_read0();
         }
+        if (gn_panel) {
+          const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
+          const int img_w = __shfl_sync(0xffffffffu, img, 0);
+          const int img_t0 = p.flat ? (p.rows_per_img > 0 ? x0 / p.rows_per_img : 0) : i0;
+          const int g_t0 = n0 / p.gn_cpg;
+          const int cc = lane;  // 8-column chunk of the tile row owned by this lane
+          const int col0 = n0 + cc * 8;
+          if (cc < n_tile_out / 8 && okmask != 0 && col0 < p.N && img_w - img_t0 < 4) {
+            float sv[8], qv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sv[j] = qv[j] = 0.f;
+            const int pn = cc >> 3;
+            const uint8_t* pb = smem + pn * 16384;
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+              if ((okmask >> rr) & 1u) {
+                const int row = q * 32 + rr;
+                const uint4 u = (pn < full_panels)
+                                    ? *reinterpret_cast<const uint4*>(pb + row * 128 + (((cc & 7) ^ (row & 7)) << 4))
+                                    : *reinterpret_cast<const uint4*>(pb + row * (rem * 2) + (cc & 7) * 16);
+                const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = Cvt<T>::unpack2(uu[j]);
+                  sv[2 * j] += f.x; qv[2 * j] += f.x * f.x;
+                  sv[2 * j + 1] += f.y; qv[2 * j + 1] += f.y * f.y;
+                }
+              }
+            }
+            const int nval = min(8, p.N - col0);
+            const int g0 = col0 / p.gn_cpg;
+            const int bnd = (g0 + 1) * p.gn_cpg - col0;  // columns [0, bnd) belong to g0, the rest to g0 + 1
+            float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < nval) {
+                if (j < bnd) { s0 += sv[j]; q0 += qv[j]; }
+                else { s1 += sv[j]; q1 += qv[j]; }
+              }
+            float* gs = gstat_s + ((img_w - img_t0) * kGnSlots + (g0 - g_t0)) * 2;
+            atomicAdd(gs, s0);
+            atomicAdd(gs + 1, q0);
+            if (bnd < nval) {
+              atomicAdd(gs + 2, s1);
+              atomicAdd(gs + 3, q1);
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int i = threadIdx.x - 64; i < 4 * kGnSlots * 2; i += 128) {
+            const float v = gstat_s[i];
+            if (v != 0.f) {
+              const int il4 = i / (kGnSlots * 2), gl = (i >> 1) % kGnSlots;
+              atomicAdd(p.gn_ws + (static_cast<long long>(img_t0 + il4) * p.gn_groups + g_t0 + gl) * 2 + (i & 1), v);
+            }
+          }
+        }
+        if (threadIdx.x == 64) tma_store_wait_read0();
       } else if (p.act == ES_ACT_GEGLU) {
         constexpr int HALF = BLOCK_N / 2;
         const int oc0 = blockIdx.y * HALF;  // output column base

@@ -42,7 +42,8 @@ constexpr int kPairBBytes = 2 * kPairBHalf;            // 20 KB: this CTA's half
 constexpr int kPairStageBytes = kPairABytes + kPairBBytes;
 constexpr int kPairPanelBytes = 5 * 16384;             // 128 x 320 outputs as five 64-column panels
 constexpr int kPairVecBytes = 4 * kPairN * 4;
-constexpr int kPairSmem = kPairStages * kPairStageBytes + kPairPanelBytes + kPairVecBytes + 1024;
+constexpr int kPairGnBytes = 4 * kGnSlots * 2 * 4;    // fused GroupNorm statistics: [4 images][kGnSlots][2]
+constexpr int kPairSmem = kPairStages * kPairStageBytes + kPairPanelBytes + kPairVecBytes + kPairGnBytes + 1024;
 constexpr uint32_t kPairTmemCols = 512;
 
 struct PairUnit {
@@ -98,6 +99,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* panels = smem + kPairStages * kPairStageBytes;
   float* vec_s = reinterpret_cast<float*>(panels + kPairPanelBytes);  // [4 lane quarters][320]
+  float* gstat_s = vec_s + 4 * kPairN;
   __shared__ __align__(8) uint64_t full_bar[kPairStages];
   __shared__ __align__(8) uint64_t empty_bar[kPairStages];
   __shared__ __align__(8) uint64_t tmem_full_bar;   // MMA -> epilogue (both CTAs, multicast commit)
@@ -235,6 +237,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int n_tile_out = geglu ? kPairNH : kPairN;
     const int full_panels = n_tile_out / 64;
     const int rem = n_tile_out % 64;
+    const bool gn_panel = p.gn_ws && !geglu && p.gn_cpg >= 8 && kPairN / p.gn_cpg + 2 <= kGnSlots;
     int ui = 0, res_it = 0;
     for (int u = cluster_id; u < n_units; u += n_clusters, ++ui) {
       const PairUnit d = pair_decode(p, u, m_pairs, n_tiles, rank);
@@ -268,6 +271,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       };
       // the residual tile rides in the output panels; without split-K it is fetched while the MMAs still run
       if (p.splits == 1) issue_residual();
+      if (gn_panel)
+        for (int i = et; i < 4 * kGnSlots * 2; i += 256) gstat_s[i] = 0.f;
       // per-column epilogue vector: vec[quarter][col] = bias[col] + rowvec[image of the quarter's rows][col]
       for (int col = et; col < kPairN; col += 256) {
         const bool col_ok = n0 + col < p.N;
@@ -421,7 +426,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               o[2 * j + 1] += f.y;
             }
           }
-          if (p.gn_ws && !geglu) gn_accumulate(o, co);
+          if (p.gn_ws && !geglu && !gn_panel) gn_accumulate(o, co);
           uint4 w0, w1;
           w0.x = Cvt<T>::pack2(o[0], o[1]); w0.y = Cvt<T>::pack2(o[2], o[3]);
           w0.z = Cvt<T>::pack2(o[4], o[5]); w0.w = Cvt<T>::pack2(o[6], o[7]);
@@ -519,6 +524,66 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int pn = 0; pn < full_panels; ++pn) tma_store_4d(&tmO, panels + pn * 16384, oc0 + pn * 64, x0, y0, i0);
         if (rem) tma_store_4d(&tmOp, panels + full_panels * 16384, oc0 + full_panels * 64, x0, y0, i0);
         tma_store_commit();
+      }
+      if (gn_panel) {
+        // GroupNorm statistics of the finished tile from the smem panels: one 8-column chunk per lane over the
+        // warp's 32 rows, reduced in smem, one global atomic per (image, group, statistic)
+        const int img_t0 = p.flat ? (p.rows_per_img > 0 ? x0 / p.rows_per_img : 0) : i0;
+        const int g_t0 = n0 / p.gn_cpg;
+        if (!skip) {
+          const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
+          const int img_w = __shfl_sync(0xffffffffu, img, 0);
+          const int cc = half * (kPairNH / 8) + lane;
+          const int col0 = n0 + cc * 8;
+          if (lane < kPairNH / 8 && okmask != 0 && col0 < p.N && img_w - img_t0 < 4) {
+            float sv[8], qv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sv[j] = qv[j] = 0.f;
+            const uint8_t* pb = panels + (cc >> 3) * 16384;
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+              if ((okmask >> rr) & 1u) {
+                const int row = q * 32 + rr;
+                const uint4 u4 = *reinterpret_cast<const uint4*>(pb + row * 128 + (((cc & 7) ^ (row & 7)) << 4));
+                const uint32_t uu[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = Cvt<T>::unpack2(uu[j]);
+                  sv[2 * j] += f.x; qv[2 * j] += f.x * f.x;
+                  sv[2 * j + 1] += f.y; qv[2 * j + 1] += f.y * f.y;
+                }
+              }
+            }
+            const int nval = min(8, p.N - col0);
+            const int g0 = col0 / p.gn_cpg;
+            const int bnd = (g0 + 1) * p.gn_cpg - col0;
+            float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < nval) {
+                if (j < bnd) { s0 += sv[j]; q0 += qv[j]; }
+                else { s1 += sv[j]; q1 += qv[j]; }
+              }
+            float* gs = gstat_s + ((img_w - img_t0) * kGnSlots + (g0 - g_t0)) * 2;
+            atomicAdd(gs, s0);
+            atomicAdd(gs + 1, q0);
+            if (bnd < nval) {
+              atomicAdd(gs + 2, s1);
+              atomicAdd(gs + 3, q1);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (!skip)
+          for (int i = et; i < 4 * kGnSlots * 2; i += 256) {
+            const float v = gstat_s[i];
+            if (v != 0.f) {
+              const int il4 = i / (kGnSlots * 2), gl = (i >> 1) % kGnSlots;
+              atomicAdd(p.gn_ws + (static_cast<long long>(img_t0 + il4) * p.gn_groups + g_t0 + gl) * 2 + (i & 1), v);
+            }
+          }
+      }
+      if (!skip && threadIdx.x == 64) {
         tma_store_wait_read0();
         if (ui == 0) PAIR_TRACE(5);
       }

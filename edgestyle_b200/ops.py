@@ -79,8 +79,9 @@ class GemmTuner:
         self._scratch = {}
 
     @staticmethod
-    def key(a, n, c1, taps, whn, act, a2, residual, segs, out, gn_ws):
-        return "|".join(str(x) for x in (
+    def key(a, n, c1, taps, whn, act, a2, residual, segs, out, gn_ws, fixed_bn=0):
+        # fixed_bn: tile width the weights were packed for (GEGLU value/gate permutation); part of the signature
+        return ("" if not fixed_bn else f"bn{fixed_bn}|") + "|".join(str(x) for x in (
             str(a.dtype).split(".")[-1], a.shape[0], n, c1, taps, whn if taps == 9 else None, act,
             None if a2 is None else a2.shape[1], residual is not None,
             None if not segs else (tuple(segs[0]), tuple(segs[1]), None if segs[2] is None else tuple(segs[2])),
@@ -201,7 +202,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: i
     g.ldc = out.stride(0)
     g.out_fp32 = 1 if out.dtype == torch.float32 else 0
     if TUNER.enabled and stages == 0 and split_k == 0 and not torch.cuda.is_current_stream_capturing():
-        key = TUNER.key(a, n, g.c1, taps, whn, act, a2, residual, segs, out, gn_ws)
+        key = TUNER.key(a, n, g.c1, taps, whn, act, a2, residual, segs, out, gn_ws, block_n)
         hit = TUNER.table.get(key)
         if hit is None:
             # time candidates on scratch outputs so that in-place residual updates / statistics are not repeated
@@ -217,7 +218,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: i
             hit = TUNER.tune(key, run, M, n, kb_total, act, block_n)
         block_n, split_k = hit[0], hit[1]
     elif TUNER.table and stages == 0 and split_k == 0:
-        hit = TUNER.table.get(TUNER.key(a, n, g.c1, taps, whn, act, a2, residual, segs, out, gn_ws))
+        hit = TUNER.table.get(TUNER.key(a, n, g.c1, taps, whn, act, a2, residual, segs, out, gn_ws, block_n))
         if hit is not None:
             block_n, split_k = hit[0], hit[1]
     g.block_n = block_n
