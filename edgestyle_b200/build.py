@@ -20,6 +20,12 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--use_fast_math",
 ]
+# every kernel whose grid has at most this many CTAs lets its stream successor start its prologue (barrier init, TMEM
+# allocation, weight-tile loads) while it is still running; 0 disables the early trigger
+PDL_TRIGGER_MAX_CTAS = int(os.environ.get("ES_PDL_TRIGGER_MAX_CTAS", "0"))
+NVCC_FLAGS.append(f"-DES_PDL_TRIGGER_MAX_CTAS={PDL_TRIGGER_MAX_CTAS}")
+OUT = os.environ.get("ES_LIB_OUT", OUT)
+OBJ = os.environ.get("ES_OBJ_DIR", OBJ)
 
 
 def _nvcc() -> str:

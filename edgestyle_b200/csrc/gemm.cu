@@ -79,7 +79,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   constexpr int kStageBytes = kABytes + kBBytes;
   constexpr uint32_t kTmemCols = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
-  constexpr int kMaxStages = 8;
+  constexpr int kMaxStages = 12;
 
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B
@@ -133,14 +133,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   // ---- one-time setup ----------------------------------------------------------------------
   // TMA load of k-block kb into its ring slot (producer thread only)
-  auto produce = [&](int kb) {
+  // TMA load of k-block kb into its ring slot (producer thread only).  The weight tile (B) does not depend on the
+  // previous kernel of the stream, the activation tile (A) does: under programmatic dependent launch the first ring
+  // fill issues the B loads before griddepcontrol.wait and the A loads after it.
+  auto produce_b = [&](int kb) {
     const int it = kb - kb_begin;
     const int s = it % stages;
     const uint32_t ph = (it / stages) & 1;
     mbar_wait(&empty_bar[s], ph ^ 1);
-    uint8_t* sa = smem + s * kStageBytes;
-    uint8_t* sb = sa + kABytes;
+    uint8_t* sb = smem + s * kStageBytes + kABytes;
     mbar_expect_tx(&full_bar[s], kStageBytes);
+    if (kb < kb1) {
+      const int tap = kb / p.kblocks1;
+      const int cb = kb - tap * p.kblocks1;
+      if (p.b_blocked) tma_load_3d(sb, &tmB, &full_bar[s], 0, b_noff + n0, kb);
+      else tma_load_3d(sb, &tmB, &full_bar[s], cb * kBlockK, tap, b_noff + n0);
+    } else {
+      tma_load_3d(sb, &tmB2, &full_bar[s], (kb - kb1) * kBlockK, 0, b2_noff + n0);
+    }
+  };
+  auto produce_a = [&](int kb) {
+    const int it = kb - kb_begin;
+    const int s = it % stages;
+    uint8_t* sa = smem + s * kStageBytes;
     if (kb < kb1) {
       const int tap = kb / p.kblocks1;
       const int cb = kb - tap * p.kblocks1;
@@ -150,13 +165,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         dx = tap % 3 - 1;
       }
       tma_load_4d(sa, &tmA, &full_bar[s], cb * kBlockK, x0 + dx, y0 + dy, i0);
-      if (p.b_blocked) tma_load_3d(sb, &tmB, &full_bar[s], 0, b_noff + n0, kb);
-      else tma_load_3d(sb, &tmB, &full_bar[s], cb * kBlockK, tap, b_noff + n0);
     } else {
-      const int cb = kb - kb1;
-      tma_load_4d(sa, &tmA2, &full_bar[s], cb * kBlockK, x0, y0, i0);  // centre tap (1x1)
-      tma_load_3d(sb, &tmB2, &full_bar[s], cb * kBlockK, 0, b2_noff + n0);
+      tma_load_4d(sa, &tmA2, &full_bar[s], (kb - kb1) * kBlockK, x0, y0, i0);  // centre tap (1x1)
     }
+  };
+  auto produce = [&](int kb) {
+    produce_b(kb);
+    produce_a(kb);
   };
   const int kb_prefill = min(kb_end, kb_begin + stages);
   if (warp == 0 && lane == 0) {
@@ -174,7 +189,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     mbar_init(&res_bar, 1);
     fence_mbar_init();
     // The first ring fill needs neither TMEM nor the other warps: issue it now so that the load latency overlaps
-    // the TMEM allocation and the CTA-wide barrier below.  (PDL: inputs may only be read after griddepcontrol.wait.)
+    // the TMEM allocation and the CTA-wide barrier below.  (PDL: inputs may only be read after griddepcontrol.wait.
+    // Measured: issuing the constant weight tiles before the wait and the activation tiles after it, with or without
+    // an early launch_dependents trigger, is slower -- stage 0 completes later and parked successors starve the
+    // concurrent streams.)
     pdl_wait();
     for (int kb = kb_begin; kb < kb_prefill; ++kb) produce(kb);
   }
@@ -781,8 +799,11 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   kp.ws_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(g->workspace) + 65536);
   // ---- pipeline depth: default leaves room for two CTAs per SM so one CTA's epilogue overlaps the other's MMAs
   const int kb_cta = (kb_total + splits - 1) / splits;
-  int stages = g->stages > 0 ? g->stages : (108 * 1024) / kStageBytes;
-  if (stages > 8) stages = 8;
+  // (a deeper ring for single-wave grids was measured: slower in the multi-stream step, because a 200 KB CTA keeps the
+  // concurrent streams' CTAs off its SM)
+  const int budget = 108 * 1024;
+  int stages = g->stages > 0 ? g->stages : budget / kStageBytes;
+  if (stages > 12) stages = 12;
   if (stages < 2) stages = 2;
   if (stages > kb_cta) stages = kb_cta < 2 ? 2 : kb_cta;
   kp.stages = stages;

@@ -28,9 +28,15 @@ __device__ __forceinline__ bool elect_one() {
 // wait: blocks until the preceding kernel(s) in the stream have completed and flushed (no-op without PDL).
 // launch_dependents: lets the next kernel's CTAs start their prologue early.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Early trigger only for grids of at most ES_PDL_TRIGGER_MAX_CTAS CTAs (the latency-bound small layers, where the
+// successor's prologue -- barrier init, TMEM allocation, weight-tile loads -- is worth overlapping).  Measured: letting
+// the big grids trigger early parks their successors' CTAs on the SMs and starves the concurrent streams.
+#ifndef ES_PDL_TRIGGER_MAX_CTAS
+#define ES_PDL_TRIGGER_MAX_CTAS 0
+#endif
 __device__ __forceinline__ void pdl_launch_dependents() {
-#ifdef ES_PDL_EARLY_TRIGGER
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#if ES_PDL_TRIGGER_MAX_CTAS > 0
+  if (gridDim.x * gridDim.y * gridDim.z <= ES_PDL_TRIGGER_MAX_CTAS) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }
 

@@ -294,7 +294,11 @@ class DenoiseEngine:
         # ControlLoRA update: "fused" = one fused weight copy per LoRA group (default), "unfused" = rank-r update as
         # extra K-blocks of the accumulator (t = x down^T, then [x | t] [W | up]^T)
         self.fuse_lora = os.environ.get("ES_LORA", "fused") != "unfused"
-        self.merge_early = os.environ.get("ES_MERGE_EARLY", "0") != "0"
+        # zero-convs + merge on the side stream: 0 = after both encoders (in the order the decoder consumes them),
+        # 1 = level by level as the encoders produce them, 2 = hybrid: the small levels (32x32 and below) as they are
+        # produced, the three heavy 64x64-level merges afterwards, under the decoder's latency-bound deep levels
+        self.merge_mode = int(os.environ.get("ES_MERGE_EARLY", "2"))
+        self.merge_early = self.merge_mode != 0
         self._stats_of = {}
         self._kv_recompute = False  # True: redo the text K/V projections inside every step (reference behaviour)
         self.launches_per_step = 0
@@ -822,7 +826,13 @@ class DenoiseEngine:
 
         # early: level by level as the encoders produce them (only the mid level is left on the critical path between
         # the encoders and the decoder); late: after both encoders, in the order the decoder consumes them
-        order = range(len(self.res_shapes)) if self.merge_early else reversed(range(len(self.res_shapes)))
+        nlev = len(self.res_shapes)
+        if self.merge_mode == 2:
+            order = list(range(3, nlev)) + [2, 1, 0]
+        elif self.merge_early:
+            order = list(range(nlev))
+        else:
+            order = list(reversed(range(nlev)))
         with torch.cuda.stream(side):
             for li in order:
                 if self.merge_early:
@@ -865,7 +875,7 @@ class DenoiseEngine:
                 merged[li].record(side)
         if mode == "residuals":
             # the side stream is in order: the last event covers all levels
-            main.wait_event(merged[len(self.res_shapes) - 1 if self.merge_early else 0])
+            main.wait_event(merged[order[-1]])
             return
         main.wait_event(merged[len(self.res_shapes) - 1])
         # -- UNet decoder

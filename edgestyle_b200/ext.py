@@ -7,7 +7,7 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libedgestyle_b200.so")
+LIB_PATH = os.environ.get("ES_LIB", os.path.join(HERE, "libedgestyle_b200.so"))
 
 ES_MAX_SEG = 4
 DTYPE_F16, DTYPE_BF16 = 0, 1
