@@ -66,10 +66,18 @@ struct GemmKParams {
   int b_blocked;         // weights stored K-block-major: [tap*kblocks + cb][n][64] (contiguous 128 B x BLOCK_N tiles)
   int tma_epi;           // 1: epilogue goes regs -> swizzled smem panels -> TMA store (residual via TMA load)
   int n_out;             // output columns in total (N, or N/2 for GEGLU)
+  // LayerNorm folded around the GEMM (see EsGemm): producer side accumulates per-row (sum, sumsq) of the OUTPUT,
+  // consumer side normalises with the statistics of its INPUT rows: out = rstd (acc - mean colsum[n]) + bias'[n]
+  float* rowstat_out;
+  const float* ln_rowstat;
+  const float* ln_colsum;
+  float ln_inv_k, ln_eps;
 };
 
-template <typename T, int BLOCK_N>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// LN: compiled with the folded-LayerNorm epilogues (row statistics of the output / normalisation by the statistics
+// of the input rows); the plain instantiation keeps the lean epilogue.
+template <typename T, int BLOCK_N, bool LN>
+__global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmOp,
@@ -270,6 +278,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     //      vec[warp][col] = bias[col] + rowvec[image of the warp's rows][col]  (registers now, smem after the MMAs)
     constexpr int kVPT = (BLOCK_N + 127) / 128;
     float vpre[4][kVPT];
+    const bool ln_in = LN && p.ln_rowstat != nullptr;
+    const bool ln_out = LN && p.rowstat_out != nullptr;
+    float ln_mean = 0.f, ln_rstd = 1.f;
+    if (ln_in && row_ok) {  // LayerNorm statistics of this thread's INPUT row (accumulated by the producing GEMM)
+      const float2 sq = *reinterpret_cast<const float2*>(p.ln_rowstat + 2 * row);
+      ln_mean = sq.x * p.ln_inv_k;
+      ln_rstd = rsqrtf(fmaxf(sq.y * p.ln_inv_k - ln_mean * ln_mean, 0.f) + p.ln_eps);
+    }
     if (use_tma_epi) {
       const int et = threadIdx.x - 64;
 #pragma unroll
@@ -277,6 +293,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int col = et + 128 * i;
         const bool col_ok = col < BLOCK_N && n0 + col < p.N;
         const float bv = (col_ok && p.bias) ? p.bias[b_noff + n0 + col] : 0.f;
+        if (ln_in) {  // slot 0: folded bias, slot 1: column sums of the gamma-scaled weights
+          vpre[0][i] = bv;
+          vpre[1][i] = col_ok ? p.ln_colsum[b_noff + n0 + col] : 0.f;
+          vpre[2][i] = vpre[3][i] = 0.f;
+          continue;
+        }
 #pragma unroll
         for (int w4 = 0; w4 < 4; ++w4) {
           float rv = 0.f;
@@ -445,7 +467,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (has_res) mbar_wait(&res_bar, 0);
-        const float* vrow = vec_s + q * BLOCK_N;
+        const float* vrow = ln_in ? vec_s : vec_s + q * BLOCK_N;
+        const float* srow = vec_s + BLOCK_N;  // LayerNorm-folded GEMM: column sums
+        float rs_acc = 0.f, rq_acc = 0.f;     // producer side: (sum, sumsq) of this thread's output row
         constexpr int HALF = NOUT / 2;
         // one 16-column chunk: accumulator (+ gate) -> epilogue math -> this thread's 32 bytes of the smem panel
         auto finish_chunk = [&](int c, float (&o)[16]) {
@@ -472,6 +496,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           if (p.gn_ws && !geglu && !gn_panel) gn_accumulate(o, c);
+          if (ln_out) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              rs_acc += o[j];
+              rq_acc += o[j] * o[j];
+            }
+          }
           uint4 w0, w1;
           w0.x = Cvt<T>::pack2(o[0], o[1]); w0.y = Cvt<T>::pack2(o[2], o[3]);
           w0.z = Cvt<T>::pack2(o[4], o[5]); w0.w = Cvt<T>::pack2(o[6], o[7]);
@@ -487,24 +518,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             b[4 * j] = f.x; b[4 * j + 1] = f.y; b[4 * j + 2] = f.z; b[4 * j + 3] = f.w;
           }
         };
+        // accumulator -> pre-activation value: plain bias add, or the folded LayerNorm rstd (acc - mean colsum) + bias'
+        auto pre16 = [&](int col, float (&a)[16]) {
+          float b[16];
+          vec16(col, b);
+          if (ln_in) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 f = *reinterpret_cast<const float4*>(srow + col + 4 * j);
+              a[4 * j] = (a[4 * j] - ln_mean * f.x) * ln_rstd + b[4 * j];
+              a[4 * j + 1] = (a[4 * j + 1] - ln_mean * f.y) * ln_rstd + b[4 * j + 1];
+              a[4 * j + 2] = (a[4 * j + 2] - ln_mean * f.z) * ln_rstd + b[4 * j + 2];
+              a[4 * j + 3] = (a[4 * j + 3] - ln_mean * f.w) * ln_rstd + b[4 * j + 3];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] += b[j];
+          }
+        };
         if (from_ws) {
           // split-K last arriver: the accumulator is the sum of the partial tiles in the workspace
 #pragma unroll 1
           for (int c = 0; c < n_tile_out; c += 16) {
-            float o[16], b[16];
+            float o[16];
             if (geglu) {
-              float a[16], g[16], bg[16];
+              float a[16], g[16];
               load_cols(c, a);
               load_cols(HALF + c, g);
-              vec16(c, b);
-              vec16(HALF + c, bg);
+              pre16(c, a);
+              pre16(HALF + c, g);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = p.alpha * (a[j] + b[j]) * gelu_erf_f(g[j] + bg[j]);
+              for (int j = 0; j < 16; ++j) o[j] = p.alpha * a[j] * gelu_erf_f(g[j]);
             } else {
               load_cols(c, o);
-              vec16(c, b);
+              pre16(c, o);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = (o[j] + b[j]) * p.alpha;
+              for (int j = 0; j < 16; ++j) o[j] *= p.alpha;
             }
             finish_chunk(c, o);
           }
@@ -514,12 +563,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tmem_ld_x16(t_row, va[0]);
           tmem_ld_x16(t_row + HALF, vg[0]);
           auto geglu_chunk = [&](int c, const uint32_t (&a)[16], const uint32_t (&g)[16]) {
-            float o[16], b[16], bg[16];
-            vec16(c, b);
-            vec16(HALF + c, bg);
+            float o[16], av[16], gv[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              o[j] = p.alpha * (__uint_as_float(a[j]) + b[j]) * gelu_erf_f(__uint_as_float(g[j]) + bg[j]);
+            for (int j = 0; j < 16; ++j) {
+              av[j] = __uint_as_float(a[j]);
+              gv[j] = __uint_as_float(g[j]);
+            }
+            pre16(c, av);
+            pre16(HALF + c, gv);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = p.alpha * av[j] * gelu_erf_f(gv[j]);
             finish_chunk(c, o);
           };
 #pragma unroll 1
@@ -543,10 +596,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint32_t v[2][16];
           tmem_ld_x16(t_row, v[0]);
           auto plain_chunk = [&](int c, const uint32_t (&a)[16]) {
-            float o[16], b[16];
-            vec16(c, b);
+            float o[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = (__uint_as_float(a[j]) + b[j]) * p.alpha;
+            for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(a[j]);
+            pre16(c, o);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] *= p.alpha;
             finish_chunk(c, o);
           };
 #pragma unroll 1
@@ -560,6 +615,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               plain_chunk(c + 16, v[1]);
             }
           }
+        }
+        if (ln_out && row_ok) {
+          atomicAdd(p.rowstat_out + 2 * row, rs_acc);
+          atomicAdd(p.rowstat_out + 2 * row + 1, rq_acc);
         }
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -776,6 +835,14 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
       kp.tma_epi = 1;
     }
   }
+  if (g->ln_rowstat || g->rowstat_out) {
+    // the folded-LayerNorm epilogues exist on the smem/TMA path only
+    ES_CHECK(kp.tma_epi, "es_gemm: folded LayerNorm needs a 16-bit, 16-byte aligned output");
+    if (kp.flat && kp.nseg > 1)
+      for (int sgi = 0; sgi < kp.nseg; ++sgi)
+        ES_CHECK((kp.seg_row_start[sgi + 1] - kp.seg_row_start[sgi]) % kBlockM == 0 || sgi == kp.nseg - 1,
+                 "es_gemm: folded LayerNorm needs row segments that are multiples of 128 rows");
+  }
   constexpr int kStageBytes = kBlockM * kBlockK * 2 + BLOCK_N * kBlockK * 2;
   const int kb_total = kp.taps * kp.kblocks1 + kp.kblocks2;
   const int tiles = m_tiles * n_tiles;
@@ -808,14 +875,24 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   if (stages > kb_cta) stages = kb_cta < 2 ? 2 : kb_cta;
   kp.stages = stages;
   const size_t smem = static_cast<size_t>(stages) * kStageBytes + 1024;
-  auto kern = gemm_kernel<T, BLOCK_N>;
-  static size_t attr_smem = 0;  // per instantiation
-  if (smem > attr_smem) {
-    ES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_smem = smem;
-  }
   dim3 grid(m_tiles, n_tiles, splits);
-  ES_CUDA(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, tmA2, tmB2, tmO, tmOp, tmR, tmRp, kp));
+  if (g->ln_rowstat || g->rowstat_out) {
+    auto kern = gemm_kernel<T, BLOCK_N, true>;
+    static size_t attr_smem_ln = 0;  // per instantiation
+    if (smem > attr_smem_ln) {
+      ES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      attr_smem_ln = smem;
+    }
+    ES_CUDA(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, tmA2, tmB2, tmO, tmOp, tmR, tmRp, kp));
+  } else {
+    auto kern = gemm_kernel<T, BLOCK_N, false>;
+    static size_t attr_smem = 0;  // per instantiation
+    if (smem > attr_smem) {
+      ES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      attr_smem = smem;
+    }
+    ES_CUDA(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, tmA2, tmB2, tmO, tmOp, tmR, tmRp, kp));
+  }
   ES_CUDA(cudaGetLastError());
   return 0;
 }
@@ -944,6 +1021,12 @@ static int gemm_dispatch(const EsGemm* g, cudaStream_t stream) {
   kp.ldc = g->ldc;
   kp.out_fp32 = g->out_fp32;
   if (g->residual) ES_CHECK(g->ldr % 8 == 0, "es_gemm: ldr must be a multiple of 8");
+  kp.rowstat_out = g->rowstat_out;
+  kp.ln_rowstat = g->ln_rowstat;
+  kp.ln_colsum = g->ln_colsum;
+  kp.ln_inv_k = g->ln_features > 0 ? 1.0f / static_cast<float>(g->ln_features) : 0.f;
+  kp.ln_eps = g->ln_eps;
+  if (g->ln_rowstat) ES_CHECK(g->ln_colsum && g->ln_features > 0 && !g->rowvec, "es_gemm: bad folded-LayerNorm config");
   kp.gn_ws = g->gn_ws;
   kp.gn_groups = g->gn_groups;
   kp.gn_cpg = g->gn_groups > 0 ? g->n / g->gn_groups : 0;

@@ -260,6 +260,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool row_ok = (x < d.x_end) && (y < p.H) && (img_c < p.NI);
       const int img = p.flat ? (p.rows_per_img > 0 ? x / p.rows_per_img : 0) : img_c;
 
+      const bool ln_in = p.ln_rowstat != nullptr;
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (ln_in && row_ok) {  // LayerNorm statistics of this thread's INPUT row (accumulated by the producing GEMM)
+        const long long row = (static_cast<long long>(img_c) * p.H + y) * p.W + x;
+        const float2 sq = *reinterpret_cast<const float2*>(p.ln_rowstat + 2 * row);
+        ln_mean = sq.x * p.ln_inv_k;
+        ln_rstd = rsqrtf(fmaxf(sq.y * p.ln_inv_k - ln_mean * ln_mean, 0.f) + p.ln_eps);
+      }
       // (A) the previous unit's TMA stores have finished reading the panels (thread 64 waited before this barrier)
       asm volatile("bar.sync 1, 256;" ::: "memory");
       auto issue_residual = [&]() {
@@ -278,6 +286,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int col = et; col < kPairN; col += 256) {
         const bool col_ok = n0 + col < p.N;
         const float bv = (col_ok && p.bias) ? p.bias[b_noff + n0 + col] : 0.f;
+        if (ln_in) {  // slot 0: folded bias, slot 1: column sums of the gamma-scaled weights
+          vec_s[col] = bv;
+          vec_s[kPairN + col] = col_ok ? p.ln_colsum[b_noff + n0 + col] : 0.f;
+          continue;
+        }
 #pragma unroll
         for (int w4 = 0; w4 < 4; ++w4) {
           float rv = 0.f;
@@ -347,12 +360,31 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) mbar_arrive_cluster(lead_empty);
       }
       if (!skip) {
-        const float* vrow = vec_s + q * kPairN + half * kPairNH;
+        const float* vrow = (ln_in ? vec_s : vec_s + q * kPairN) + half * kPairNH;
+        const float* srow = vec_s + kPairN + half * kPairNH;  // LayerNorm-folded GEMM: column sums
+        float rs_acc = 0.f, rq_acc = 0.f;                     // producer side: (sum, sumsq) of this thread's output row
         auto vec16 = [&](int col, float (&b)[16]) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 f = *reinterpret_cast<const float4*>(vrow + col + 4 * j);
             b[4 * j] = f.x; b[4 * j + 1] = f.y; b[4 * j + 2] = f.z; b[4 * j + 3] = f.w;
+          }
+        };
+        auto pre16 = [&](int col, float (&a)[16]) {
+          float b[16];
+          vec16(col, b);
+          if (ln_in) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 f = *reinterpret_cast<const float4*>(srow + col + 4 * j);
+              a[4 * j] = (a[4 * j] - ln_mean * f.x) * ln_rstd + b[4 * j];
+              a[4 * j + 1] = (a[4 * j + 1] - ln_mean * f.y) * ln_rstd + b[4 * j + 1];
+              a[4 * j + 2] = (a[4 * j + 2] - ln_mean * f.z) * ln_rstd + b[4 * j + 2];
+              a[4 * j + 3] = (a[4 * j + 3] - ln_mean * f.w) * ln_rstd + b[4 * j + 3];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] += b[j];
           }
         };
         // partial-tile sum for accumulator columns [cg, cg + 16) of this thread's row (split-K last arriver)
@@ -428,6 +460,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if (p.gn_ws && !geglu && !gn_panel) gn_accumulate(o, co);
+          if (p.rowstat_out) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              rs_acc += o[j];
+              rq_acc += o[j] * o[j];
+            }
+          }
           uint4 w0, w1;
           w0.x = Cvt<T>::pack2(o[0], o[1]); w0.y = Cvt<T>::pack2(o[2], o[3]);
           w0.z = Cvt<T>::pack2(o[4], o[5]); w0.w = Cvt<T>::pack2(o[6], o[7]);
@@ -441,21 +480,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int nloc = geglu ? GH : kPairNH;
 #pragma unroll 1
           for (int c = 0; c < nloc; c += 16) {
-            float o[16], b[16];
+            float o[16];
             if (geglu) {
-              float a[16], g[16], bg[16];
+              float a[16], g[16];
               load_ws(half * kPairNH + c, a);
               load_ws(half * kPairNH + GH + c, g);
-              vec16(c, b);
-              vec16(GH + c, bg);
+              pre16(c, a);
+              pre16(GH + c, g);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = p.alpha * (a[j] + b[j]) * gelu_erf_f(g[j] + bg[j]);
+              for (int j = 0; j < 16; ++j) o[j] = p.alpha * a[j] * gelu_erf_f(g[j]);
               finish_chunk(half * GH + c, o);
             } else {
               load_ws(half * kPairNH + c, o);
-              vec16(c, b);
+              pre16(c, o);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = (o[j] + b[j]) * p.alpha;
+              for (int j = 0; j < 16; ++j) o[j] *= p.alpha;
               finish_chunk(half * kPairNH + c, o);
             }
           }
@@ -464,12 +503,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tmem_ld_x16(t_row, va[0]);
           tmem_ld_x16(t_row + GH, vg[0]);
           auto geglu_chunk = [&](int c, const uint32_t (&a)[16], const uint32_t (&g)[16]) {
-            float o[16], b[16], bg[16];
-            vec16(c, b);
-            vec16(GH + c, bg);
+            float o[16], av[16], gv[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              o[j] = p.alpha * (__uint_as_float(a[j]) + b[j]) * gelu_erf_f(__uint_as_float(g[j]) + bg[j]);
+            for (int j = 0; j < 16; ++j) {
+              av[j] = __uint_as_float(a[j]);
+              gv[j] = __uint_as_float(g[j]);
+            }
+            pre16(c, av);
+            pre16(GH + c, gv);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = p.alpha * av[j] * gelu_erf_f(gv[j]);
             finish_chunk(half * GH + c, o);
           };
 #pragma unroll 1
@@ -493,10 +536,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t v[2][16];
           tmem_ld_x16(t_row, v[0]);
           auto plain_chunk = [&](int c, const uint32_t (&a)[16]) {
-            float o[16], b[16];
-            vec16(c, b);
+            float o[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = (__uint_as_float(a[j]) + b[j]) * p.alpha;
+            for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(a[j]);
+            pre16(c, o);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] *= p.alpha;
             finish_chunk(half * kPairNH + c, o);
           };
 #pragma unroll 1
@@ -510,6 +555,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               plain_chunk(c + 16, v[1]);
             }
           }
+        }
+        if (p.rowstat_out && row_ok) {
+          const long long row = (static_cast<long long>(img_c) * p.H + y) * p.W + x;
+          atomicAdd(p.rowstat_out + 2 * row, rs_acc);
+          atomicAdd(p.rowstat_out + 2 * row + 1, rq_acc);
         }
         if (!from_ws) {
           // every tcgen05.ld of this warp has completed: hand TMEM back to the MMA issuer

@@ -81,6 +81,7 @@ class Lin:
     rp: int = 0
     block_n: int = 0
     groups: int = 1  # > 1: `w` / `bias` hold (1 + G) copies stacked along N: [W; W + up_1 down_1; ...] (LoRA fused)
+    colsum: Optional[torch.Tensor] = None  # folded LayerNorm: sum_k (W * gamma)[n, k] per stacked row (fp32)
 
 
 @dataclass
@@ -120,9 +121,11 @@ class Tfm:
 
 
 class _Packer:
-    def __init__(self, sd, loras: Sequence[Dict[str, torch.Tensor]], dtype, device, fuse_lora: bool = True):
+    def __init__(self, sd, loras: Sequence[Dict[str, torch.Tensor]], dtype, device, fuse_lora: bool = True,
+                 fold_ln: bool = False):
         self.sd, self.loras, self.dtype, self.device = sd, list(loras), dtype, device
         self.fuse_lora = fuse_lora
+        self.fold_ln = fold_ln
 
     def f32(self, k):
         return self.sd[k].to(device=self.device, dtype=torch.float32).contiguous()
@@ -152,8 +155,11 @@ class _Packer:
         return parts
 
     def lin(self, names: Sequence[str], bias_names: Sequence[Optional[str]] = (), perm: Optional[torch.Tensor] = None,
-            block_n: int = 0) -> Lin:
-        """Stack one or more Linear / 1x1-conv weights along N (fused QKV / KV); LoRA ups become block-diagonal."""
+            block_n: int = 0, ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Lin:
+        """Stack one or more Linear / 1x1-conv weights along N (fused QKV / KV); LoRA ups become block-diagonal.
+
+        ln = (gamma, beta) of the LayerNorm that feeds this projection: folded into the weights (W * gamma, bias +
+        W beta, column sums kept for the mean term) so the GEMM consumes the un-normalised hidden state."""
         ws = [self.sd[n + ".weight"].reshape(self.sd[n + ".weight"].shape[0], -1).float().cpu() for n in names]
         k_in = ws[0].shape[1]
         w = torch.cat(ws, 0)
@@ -195,13 +201,32 @@ class _Packer:
             G = len(up)
             rp = rp_tot
             ws_g = [w] + [w + up[g] @ down[g * rp:(g + 1) * rp] for g in range(G)]
-            bias_g = None if bias is None else torch.cat([bias] * (G + 1))
+            bias_g = [bias] * (G + 1)
+            if ln is not None:
+                return self._fold_ln(ws_g, bias_g, ln, n_tot, block_n)
+            bias_g = None if bias is None else torch.cat(bias_g)
             return Lin(self.mat(torch.cat(ws_g, 0)), None if bias_g is None else bias_g.to(self.device).contiguous(),
                        n_tot, None, None, 0, block_n, G + 1)
+        if ln is not None:
+            if up is not None:
+                raise NotImplementedError("folded LayerNorm with an unfused LoRA update")
+            return self._fold_ln([w], [bias], ln, n_tot, block_n)
         if up is not None:
             up = torch.cat(up, 0)
         return Lin(self.mat(w), None if bias is None else bias.to(self.device).contiguous(), n_tot,
                    None if down is None else self.mat(down), None if up is None else self.mat(up), rp_tot, block_n)
+
+    def _fold_ln(self, ws_g, bias_g, ln, n_tot, block_n) -> Lin:
+        """LayerNorm(x) W^T + b == rstd (x (W gamma)^T - mean colsum) + (b + W beta): one folded copy per weight group."""
+        gamma, beta = [t.float().cpu() for t in ln]
+        w_f, b_f, cs = [], [], []
+        for wg, bg in zip(ws_g, bias_g):
+            wf = (wg * gamma[None, :]).to(self.dtype)  # what the tensor cores multiply with
+            w_f.append(wf)
+            cs.append(wf.float().sum(1))
+            b_f.append(wg @ beta + (bg if bg is not None else 0.0))
+        return Lin(torch.cat(w_f, 0).to(self.device).contiguous(), torch.cat(b_f).to(self.device).contiguous(), n_tot,
+                   None, None, 0, block_n, len(ws_g), torch.cat(cs).to(self.device).contiguous())
 
     def res(self, p: str) -> Res:
         sd = self.sd
@@ -231,18 +256,19 @@ class _Packer:
             idx += list(range(4 * c + tile * half, 4 * c + (tile + 1) * half))
         perm = torch.tensor(idx)
         ln = lambda n: (self.f32(f"{t}.{n}.weight"), self.f32(f"{t}.{n}.bias"))
+        fold = (lambda n: (self.sd[f"{t}.{n}.weight"], self.sd[f"{t}.{n}.bias"])) if self.fold_ln else (lambda n: None)
         return Tfm(
             self.f32(f"{p}.norm.weight"), self.f32(f"{p}.norm.bias"),
             self.lin([f"{p}.proj_in"], [f"{p}.proj_in.bias"]),
             ln("norm1"),
-            self.lin([f"{t}.attn1.to_q", f"{t}.attn1.to_k", f"{t}.attn1.to_v"]),
+            self.lin([f"{t}.attn1.to_q", f"{t}.attn1.to_k", f"{t}.attn1.to_v"], ln=fold("norm1")),
             self.lin([f"{t}.attn1.to_out.0"], [f"{t}.attn1.to_out.0.bias"]),
             ln("norm2"),
-            self.lin([f"{t}.attn2.to_q"]),
+            self.lin([f"{t}.attn2.to_q"], ln=fold("norm2")),
             self.lin([f"{t}.attn2.to_k", f"{t}.attn2.to_v"]),
             self.lin([f"{t}.attn2.to_out.0"], [f"{t}.attn2.to_out.0.bias"]),
             ln("norm3"),
-            self.lin([f"{t}.ff.net.0.proj"], [f"{t}.ff.net.0.proj.bias"], perm=perm, block_n=bn),
+            self.lin([f"{t}.ff.net.0.proj"], [f"{t}.ff.net.0.proj.bias"], perm=perm, block_n=bn, ln=fold("norm3")),
             self.lin([f"{t}.ff.net.2"], [f"{t}.ff.net.2.bias"]),
             self.lin([f"{p}.proj_out"], [f"{p}.proj_out.bias"]),
             c,
@@ -297,6 +323,11 @@ class DenoiseEngine:
         # zero-convs + merge on the side stream: 0 = after both encoders (in the order the decoder consumes them),
         # 1 = level by level as the encoders produce them, 2 = hybrid: the small levels (32x32 and below) as they are
         # produced, the three heavy 64x64-level merges afterwards, under the decoder's latency-bound deep levels
+        # BasicTransformerBlock LayerNorms folded around the GEMMs (EsGemm.rowstat_out / ln_rowstat): the producing
+        # projection accumulates per-row (sum, sumsq), the consuming one normalises in its epilogue -- no LayerNorm
+        # kernel and no normalised copy of the hidden state in memory.  Needs whole 128-row tiles per row segment.
+        self.fold_ln = (os.environ.get("ES_FOLD_LN", "1") != "0" and self.fuse_lora
+                        and (rows * self.levels[-1][0] * self.levels[-1][1]) % 128 == 0)
         self.merge_mode = int(os.environ.get("ES_MERGE_EARLY", "2"))
         self.merge_early = self.merge_mode != 0
         self._stats_of = {}
@@ -335,7 +366,7 @@ class DenoiseEngine:
     # ------------------------------------------------------------------------------------ packing
     def _pack_encoder(self, sd, loras) -> EncoderW:
         cfg = self.cfg
-        P = _Packer(sd, loras, self.dtype, self.dev, self.fuse_lora)
+        P = _Packer(sd, loras, self.dtype, self.dev, self.fuse_lora, self.fold_ln)
         c0 = cfg.block_out_channels[0]
         wci = torch.zeros(c0, 64)
         wci[:, :9 * cfg.in_channels] = sd["conv_in.weight"].float().cpu().permute(0, 2, 3, 1).reshape(c0, -1)
@@ -390,7 +421,7 @@ class DenoiseEngine:
         self.enc_base = self._pack_encoder(unet_sd, lora_sds)
         self.enc_pose = self._pack_encoder(pose_sd, [])
         # UNet decoder
-        P = _Packer(unet_sd, [], self.dtype, self.dev)
+        P = _Packer(unet_sd, [], self.dtype, self.dev, True, self.fold_ln)
         nb = len(cfg.block_out_channels)
         self.up_res, self.up_tfm, self.up_conv = [], [], []
         rev_attn = list(reversed(cfg.down_has_attn))
@@ -461,11 +492,24 @@ class DenoiseEngine:
         # one pool of reduction scratch for the whole step, zeroed by ONE memset at the start of the step: every
         # GroupNorm call / merge block takes its own slot (no per-call memset launches inside the graph)
         self._gn_slot_floats = 4 * B * cfg.norm_num_groups * 2
-        self.scratch = torch.zeros(256 * self._gn_slot_floats * 4 + 32 * B * 4 * 8, device=self.dev, dtype=torch.uint8)
-        self.gn_pool = self.scratch[: 256 * self._gn_slot_floats * 4].view(torch.float32)
-        self.merge_pool = self.scratch[256 * self._gn_slot_floats * 4:].view(torch.float64).view(32, B, 4)
+        gn_bytes = 256 * self._gn_slot_floats * 4
+        merge_bytes = 32 * B * 4 * 8
+        # folded LayerNorm: [rows, 2] fp32 (sum, sumsq) per LayerNorm instance of the step
+        ln_rows = 0
+        if self.fold_ln:
+            n_lvl = len(cfg.block_out_channels)
+            for i, (H, W) in enumerate(self.levels):
+                if cfg.down_has_attn[i]:
+                    ln_rows += 3 * H * W * (7 * B * cfg.layers_per_block + B * (cfg.layers_per_block + 1))
+            H, W = self.levels[-1]
+            ln_rows += 3 * H * W * 7 * B  # mid blocks of the two encoder passes
+        self.scratch = torch.zeros(gn_bytes + merge_bytes + ln_rows * 8, device=self.dev, dtype=torch.uint8)
+        self.gn_pool = self.scratch[:gn_bytes].view(torch.float32)
+        self.merge_pool = self.scratch[gn_bytes:gn_bytes + merge_bytes].view(torch.float64).view(32, B, 4)
+        self.ln_pool = self.scratch[gn_bytes + merge_bytes:].view(torch.float32)
         self._gn_next = 0
         self._merge_next = 0
+        self._ln_next = 0
         self.coef = torch.zeros(4, device=self.dev, dtype=torch.float32)
         self.guidance = torch.ones(max(B // 2, 1), device=self.dev, dtype=torch.float32)
 
@@ -524,6 +568,16 @@ class DenoiseEngine:
         self.scratch.zero_()
         self._gn_next = 0
         self._merge_next = 0
+        self._ln_next = 0
+
+    def _ln_slot(self, rows: int):
+        """[rows, 2] fp32 (sum, sumsq), zero at the start of the step (one memset for the whole pool)."""
+        n = 2 * rows
+        if self._ln_next + n > self.ln_pool.numel():
+            raise RuntimeError("LayerNorm statistics pool exhausted")
+        t = self.ln_pool[self._ln_next:self._ln_next + n]
+        self._ln_next += n
+        return t
 
     def _merge_slot(self):
         s = self.merge_pool[self._merge_next]
@@ -558,10 +612,15 @@ class DenoiseEngine:
             ops.groupnorm(x, out, g, b, self._gn_slot(imgs), imgs, hw, G, eps, silu, zero_ws=False)
         return out
 
-    def _lin(self, L: Lin, a, out, rows_per_img: int, lora_seg_imgs: Optional[Sequence[int]], tag: str, **ep):
-        """out = a @ L.w^T (+ LoRA per row segment) with the fused epilogue `ep`."""
+    def _lin(self, L: Lin, a, out, rows_per_img: int, lora_seg_imgs: Optional[Sequence[int]], tag: str, ln_stat=None,
+             **ep):
+        """out = a @ L.w^T (+ LoRA per row segment) with the fused epilogue `ep`; ln_stat: row statistics of `a` when
+        the LayerNorm in front of this projection is folded into it (L.colsum)."""
         if ep.get("gn_ws") is not None:
             ep["rows_per_img"] = rows_per_img  # fused GroupNorm statistics are per image
+        if L.colsum is not None:
+            assert ln_stat is not None, "folded-LayerNorm projection called without row statistics"
+            ep["ln"] = (ln_stat, L.colsum, a.shape[1], 1e-5)
         if L.groups > 1:
             M = a.shape[0]
             if lora_seg_imgs is None:
@@ -608,29 +667,34 @@ class DenoiseEngine:
         g = self.buf(f"{tag}.tgn", M, c)
         self._gn(x, g, T.ng, T.nb, imgs, hw, False, eps=1e-6)
         hcur = self.buf(f"{tag}.th", M, c)
-        self._lin(T.proj_in, g, hcur, hw, None, tag)
-        ln = self.buf(f"{tag}.ln", M, c)
+        fold = self.fold_ln
+        st = [self._ln_slot(M) for _ in range(3)] if fold else [None] * 3
+        self._lin(T.proj_in, g, hcur, hw, None, tag, rowstat_out=st[0])
+        ln = hcur if fold else self.buf(f"{tag}.ln", M, c)  # folded: the projections read the raw hidden state
         att = self.buf(f"{tag}.att", M, c)
         # self-attention
-        ops.layernorm(hcur, ln, *T.ln1)
+        if not fold:
+            ops.layernorm(hcur, ln, *T.ln1)
         qkv = self.buf(f"{tag}.qkv", M, 3 * c)
-        self._lin(T.qkv, ln, qkv, hw, seg, tag + ".qkv")
+        self._lin(T.qkv, ln, qkv, hw, seg, tag + ".qkv", ln_stat=st[0])
         ops.attention(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], att, imgs, heads, hw, hw)
-        self._lin(T.o1, att, hcur, hw, seg, tag + ".o", residual=hcur)
+        self._lin(T.o1, att, hcur, hw, seg, tag + ".o", residual=hcur, rowstat_out=st[1])
         # cross-attention
-        ops.layernorm(hcur, ln, *T.ln2)
+        if not fold:
+            ops.layernorm(hcur, ln, *T.ln2)
         q = self.buf(f"{tag}.q2", M, c)
-        self._lin(T.q2, ln, q, hw, seg, tag + ".o")
+        self._lin(T.q2, ln, q, hw, seg, tag + ".o", ln_stat=st[1])
         # text K/V projections depend only on the prompt and the weights: computed once per set_prompt()
         kv = self.buf(f"kv.{tag.split('.')[0]}.{T.uid}", imgs * nt, 2 * c)
         if self._kv_recompute:
             self._lin(T.kv2, ctx, kv, nt, seg, tag + ".kv")
         ops.attention(q, kv[:, :c], kv[:, c:], att, imgs, heads, hw, nt)
-        self._lin(T.o2, att, hcur, hw, seg, tag + ".o", residual=hcur)
+        self._lin(T.o2, att, hcur, hw, seg, tag + ".o", residual=hcur, rowstat_out=st[2])
         # feed-forward (GEGLU fused in the first GEMM's epilogue)
-        ops.layernorm(hcur, ln, *T.ln3)
+        if not fold:
+            ops.layernorm(hcur, ln, *T.ln3)
         u = self.buf(f"{tag}.ff", M, 4 * c)
-        self._lin(T.ff1, ln, u, hw, seg, tag + ".o", act=ACT_GEGLU)
+        self._lin(T.ff1, ln, u, hw, seg, tag + ".o", ln_stat=st[2], act=ACT_GEGLU)
         self._lin(T.ff2, u, hcur, hw, seg, tag + ".ff2", residual=hcur)
         self._lin(T.proj_out, hcur, out, hw, None, tag, residual=x,
                   gn_ws=self._stats_for(out, imgs, hw), gn_groups=self.cfg.norm_num_groups)

@@ -79,9 +79,10 @@ class GemmTuner:
         self._scratch = {}
 
     @staticmethod
-    def key(a, n, c1, taps, whn, act, a2, residual, segs, out, gn_ws, fixed_bn=0):
-        # fixed_bn: tile width the weights were packed for (GEGLU value/gate permutation); part of the signature
-        return ("" if not fixed_bn else f"bn{fixed_bn}|") + "|".join(str(x) for x in (
+    def key(a, n, c1, taps, whn, act, a2, residual, segs, out, gn_ws, fixed_bn=0, ln=0):
+        # fixed_bn: tile width the weights were packed for (GEGLU value/gate permutation); ln: 1 = accumulates row
+        # statistics of its output, 2 = folded-LayerNorm consumer; both are part of the signature
+        return ("" if not fixed_bn else f"bn{fixed_bn}|") + ("" if not ln else f"ln{ln}|") + "|".join(str(x) for x in (
             str(a.dtype).split(".")[-1], a.shape[0], n, c1, taps, whn if taps == 9 else None, act,
             None if a2 is None else a2.shape[1], residual is not None,
             None if not segs else (tuple(segs[0]), tuple(segs[1]), None if segs[2] is None else tuple(segs[2])),
@@ -151,8 +152,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: i
          rowvec=None, rows_per_img: int = 0, residual=None, act: int = ACT_NONE, alpha: float = 1.0,
          a2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None, segs=None, block_n: int = 0,
          c1: Optional[int] = None, stages: int = 0, split_k: int = 0, workspace: Optional[torch.Tensor] = None,
-         gn_ws: Optional[torch.Tensor] = None, gn_groups: int = 0, b_blocked: bool = False):
+         gn_ws: Optional[torch.Tensor] = None, gn_groups: int = 0, b_blocked: bool = False,
+         rowstat_out: Optional[torch.Tensor] = None, ln=None):
     """out[m, :n] = epilogue(A (*) B^T).  a: [M, >=c1] (pitch = a.stride(0)); b: [n_total, taps*c1].
+
+    rowstat_out: fp32 [M, 2] (zeroed by the caller) accumulating per-row (sum, sumsq) of the output.
+    ln = (rowstat [M, 2] of the rows of `a`, colsum fp32 [n_total], features, eps): LayerNorm folded into this GEMM
+    (b must be W * gamma and bias = bias + W beta, see include/edgestyle_b200.h).
 
     whn=(w, h, n_img) for taps == 9.  segs = list of (row_start, b_noff, b2_noff) + final row end via segs_end.
     """
@@ -201,24 +207,35 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: i
     g.out = out.data_ptr()
     g.ldc = out.stride(0)
     g.out_fp32 = 1 if out.dtype == torch.float32 else 0
+    ln_flag = (1 if rowstat_out is not None else 0) + (2 if ln is not None else 0)
+    if rowstat_out is not None:
+        assert rowstat_out.dtype == torch.float32 and rowstat_out.is_contiguous() and rowstat_out.numel() >= 2 * M
+        g.rowstat_out = rowstat_out.data_ptr()
+    if ln is not None:
+        ln_stat, ln_colsum, ln_features, ln_eps = ln
+        assert ln_stat.dtype == torch.float32 and ln_stat.is_contiguous() and ln_stat.numel() >= 2 * M
+        assert ln_colsum.dtype == torch.float32 and ln_colsum.is_contiguous() and ln_colsum.numel() >= g.n_total_b
+        g.ln_rowstat, g.ln_colsum, g.ln_features, g.ln_eps = ln_stat.data_ptr(), ln_colsum.data_ptr(), ln_features, ln_eps
     if TUNER.enabled and stages == 0 and split_k == 0 and not torch.cuda.is_current_stream_capturing():
-        key = TUNER.key(a, n, g.c1, taps, whn, act, a2, residual, segs, out, gn_ws, block_n)
+        key = TUNER.key(a, n, g.c1, taps, whn, act, a2, residual, segs, out, gn_ws, block_n, ln_flag)
         hit = TUNER.table.get(key)
         if hit is None:
             # time candidates on scratch outputs so that in-place residual updates / statistics are not repeated
             sk_out = TUNER._scratch.setdefault(("o", out.shape, out.dtype), torch.empty_like(out.contiguous()))
             sk_gn = None if gn_ws is None else torch.zeros_like(gn_ws)
+            sk_rs = None if rowstat_out is None else torch.zeros_like(rowstat_out)
             kb_total = taps * ((g.c1 + 63) // 64) + (0 if a2 is None else (a2.shape[1] + 63) // 64)
 
             def run(bn, sk):
                 gemm(a, b, n, out=sk_out, taps=taps, whn=whn, bias=bias, rowvec=rowvec, rows_per_img=rows_per_img,
                      residual=residual, act=act, alpha=alpha, a2=a2, b2=b2, segs=segs, block_n=bn, c1=c1, stages=0,
-                     split_k=sk, workspace=workspace, gn_ws=sk_gn, gn_groups=gn_groups, b_blocked=b_blocked)
+                     split_k=sk, workspace=workspace, gn_ws=sk_gn, gn_groups=gn_groups, b_blocked=b_blocked,
+                     rowstat_out=sk_rs, ln=ln)
 
             hit = TUNER.tune(key, run, M, n, kb_total, act, block_n)
         block_n, split_k = hit[0], hit[1]
     elif TUNER.table and stages == 0 and split_k == 0:
-        hit = TUNER.table.get(TUNER.key(a, n, g.c1, taps, whn, act, a2, residual, segs, out, gn_ws, block_n))
+        hit = TUNER.table.get(TUNER.key(a, n, g.c1, taps, whn, act, a2, residual, segs, out, gn_ws, block_n, ln_flag))
         if hit is not None:
             block_n, split_k = hit[0], hit[1]
     g.block_n = block_n

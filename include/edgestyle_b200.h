@@ -89,6 +89,17 @@ typedef struct EsGemm {
                    by the caller) so the consuming GroupNorm skips its statistics pass; needs rows-per-image % 32 == 0
                    (flat mode: rows_per_img must be set) */
   int gn_groups;
+  /* LayerNorm folded around the GEMM (BasicTransformerBlock norm1/2/3 never touch memory):
+   *   producer: rowstat_out [M][2] fp32 (zeroed by the caller) receives per-row (sum, sumsq) of THIS GEMM's output
+   *             (after bias / residual), accumulated over its column tiles;
+   *   consumer: ln_rowstat [M][2] holds those sums for the rows of A; B must be W * gamma (per K column), `bias`
+   *             bias + W beta, ln_colsum[noff + n] = sum_k B[n, k]; the epilogue then computes
+   *             rstd_m * (acc - mean_m * ln_colsum[n]) + bias[n]  ==  LayerNorm(A)[m, :] . W[n, :] + bias. */
+  float* rowstat_out;
+  const float* ln_rowstat;
+  const float* ln_colsum;
+  int ln_features; /* number of features the statistics were taken over (C) */
+  float ln_eps;
   void* workspace; /* optional split-K scratch: first 64 KiB = tile counters (zero-initialised ONCE by the caller,
                       self-resetting), rest = fp32 partial tiles.  Must not be shared by concurrent launches. */
   long long workspace_bytes;

@@ -310,6 +310,49 @@ def test_conv3x3_pair(n_img, h, w, cin, cout, split_k):
     _close(out2, conv + xs.float() @ wsc.float().t(), 6e-3, 6e-3, "pair conv3x3 + shortcut")
 
 
+# ------------------------------------------------------------------------------------------ folded LayerNorm
+@pytest.mark.parametrize("M,C,N,bn,geglu", [(512, 320, 960, 0, False), (1024, 640, 640, 320, False), (256, 1280, 1280, 64, False),
+                                            (768, 320, 2560, 160, True), (768, 320, 2560, 320, True), (2048, 640, 1920, 320, False)])
+def test_gemm_folded_layernorm(M, C, N, bn, geglu):
+    """producer GEMM accumulates row (sum, sumsq) of its output; consumer GEMM == Linear(LayerNorm(x)) without a LayerNorm pass."""
+    from edgestyle_b200 import ops
+
+    ops.set_gemm_workspace(256 << 20)
+    # producer: x = a @ wp^T + bp + res (what proj_in / to_out produce), statistics taken in its epilogue
+    a = _rand(M, 192, seed=301)
+    wp = _rand(C, 192, scale=192 ** -0.5, seed=302)
+    bp = _rand(C, dtype=torch.float32, seed=303)
+    res = _rand(M, C, seed=304) * 3 + 1.5  # a mean well away from zero exercises the mean * colsum term
+    x = torch.empty(M, C, device=DEV, dtype=torch.float16)
+    stat = torch.zeros(M, 2, device=DEV)
+    ops.gemm(a, wp, C, out=x, bias=bp, residual=res, rowstat_out=stat, block_n=320 if C % 320 == 0 and bn == 320 else 0)
+    xf = x.float()
+    _close(stat[:, 0], xf.sum(1), 0.05, 2e-3, "row sums")
+    _close(stat[:, 1], (xf * xf).sum(1), 0.5, 2e-3, "row sums of squares")
+    # consumer
+    gamma = _rand(C, dtype=torch.float32, seed=305) * 0.2 + 1
+    beta = _rand(C, dtype=torch.float32, seed=306) * 0.2
+    w = _rand(N, C, dtype=torch.float32, scale=C ** -0.5, seed=307)
+    bias = _rand(N, dtype=torch.float32, seed=308)
+    u = F.layer_norm(xf, (C,), gamma, beta, 1e-5) @ w.t() + bias
+    if geglu:
+        half = 80
+        idx = []
+        for t in range(N // 160):
+            idx += list(range(t * half, (t + 1) * half)) + list(range(N // 2 + t * half, N // 2 + (t + 1) * half))
+        idx = torch.tensor(idx, device=DEV)
+        want = u[:, :N // 2] * F.gelu(u[:, N // 2:])
+    else:
+        idx = torch.arange(N, device=DEV)
+        want = u
+    wf = (w * gamma[None, :]).half()[idx].contiguous()
+    colsum = wf.float().sum(1).contiguous()
+    bf = (bias + w @ beta)[idx].contiguous()
+    out = torch.zeros(M, N // 2 if geglu else N, device=DEV, dtype=torch.float16)
+    ops.gemm(x, wf, N, out=out, bias=bf, act=1 if geglu else 0, block_n=bn, ln=(stat, colsum, C, 1e-5))
+    _close(out, want, 2e-2, 1e-2, f"folded LayerNorm GEMM bn={bn}")
+
+
 # ------------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("batch,heads,d,nq,nkv", [(2, 8, 40, 4096, 4096), (2, 8, 80, 1024, 1024), (3, 8, 160, 256, 256),
