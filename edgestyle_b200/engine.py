@@ -332,6 +332,7 @@ class DenoiseEngine:
         self.merge_early = self.merge_mode != 0
         self._stats_of = {}
         self._kv_recompute = False  # True: redo the text K/V projections inside every step (reference behaviour)
+        self._temb_ready = None     # event of the base pass's time path while it is pending on the side stream
         self.launches_per_step = 0
         for i, c in enumerate(cfg.block_out_channels):
             if c % 8 or c % cfg.norm_num_groups or (c // cfg.num_heads) % 8:
@@ -646,6 +647,11 @@ class DenoiseEngine:
         self._gn(x, g1, R.n1g, R.n1b, imgs, H * W, True)
         hbuf = self.buf(f"{tag}.h", M, R.cout)
         G = self.cfg.norm_num_groups
+        if self._temb_ready is not None and tag.startswith("base"):
+            st = torch.cuda.current_stream()
+            if st.cuda_stream not in self._temb_waited:  # time path of the base pass (enqueued on the side stream)
+                st.wait_event(self._temb_ready)
+                self._temb_waited.add(st.cuda_stream)
         ops.gemm(g1, R.w1, R.cout, out=hbuf, taps=9, whn=(W, H, imgs), bias=R.b1,
                  rowvec=temb[:, R.temb_off:R.temb_off + R.cout], c1=R.cin,
                  gn_ws=self._stats_for(hbuf, imgs, H * W), gn_groups=G)
@@ -786,16 +792,24 @@ class DenoiseEngine:
         ops.timestep_embedding(self.t_in, c0, self.buf("t_sin", B, c0, torch.float32))
         Eb, Ep = self.enc_base, self.enc_pose
         enc_cols = Eb.temb_cols
-        temb_base = self._time_path(Eb, [(0, B), (1, B), (2, 2 * B)], "base",
-                                    [enc_cols + self.dec_temb_cols, enc_cols, enc_cols])
+        # fork here: the other chains only need the sinusoidal embedding and the im2col of the sample.  The base
+        # chain's time path (a dozen weight-streaming GEMVs) runs on the otherwise idle merge stream while the main
+        # stream does conv_in and the first GroupNorm; the first resnet waits for it just before its conv1.
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        self._merge_stream.wait_event(fork)
+        with torch.cuda.stream(self._merge_stream):
+            temb_base = self._time_path(Eb, [(0, B), (1, B), (2, 2 * B)], "base",
+                                        [enc_cols + self.dec_temb_cols, enc_cols, enc_cols])
+            self._temb_ready = torch.cuda.Event()
+            self._temb_ready.record(self._merge_stream)
+            self._temb_waited = set()
         cond = lambda k: self.conds[k * B * hw:(k + 1) * B * hw]
         # -- encoder chains.  Image order of the base weight set: unet (B) | agn (B) | clo cond2 (B) | clo cond4 (B);
         #    of the pose set: cond1 | cond3 | cond5 (B each).  `self.chains` groups consecutive image blocks into
         #    independent traversals, each on its own stream: most layers at CFG batch 2 are latency / occupancy
         #    bound, so concurrent chains fill the SMs that one chain's partial waves leave idle.
-        main = torch.cuda.current_stream()
-        fork = torch.cuda.Event()
-        fork.record(main)
         xb = self.buf("base.x0", 4 * B * hw, c0)
         xp = self.buf("pose.x0", 3 * B * hw, c0)
         base_cond = (None, 0, 2, 4)   # conditioning net index of base image block 0..3
@@ -937,6 +951,7 @@ class DenoiseEngine:
                           zero_stats=False)
                 merged[li] = torch.cuda.Event()
                 merged[li].record(side)
+        self._temb_ready = None
         if mode == "residuals":
             # the side stream is in order: the last event covers all levels
             main.wait_event(merged[order[-1]])
