@@ -328,7 +328,7 @@ class DenoiseEngine:
         # kernel and no normalised copy of the hidden state in memory.  Needs whole 128-row tiles per row segment.
         self.fold_ln = (os.environ.get("ES_FOLD_LN", "1") != "0" and self.fuse_lora
                         and (rows * self.levels[-1][0] * self.levels[-1][1]) % 128 == 0)
-        self.merge_mode = int(os.environ.get("ES_MERGE_EARLY", "2"))
+        self.merge_mode = int(os.environ.get("ES_MERGE_EARLY", "0"))
         self.merge_early = self.merge_mode != 0
         self._stats_of = {}
         self._kv_recompute = False  # True: redo the text K/V projections inside every step (reference behaviour)
@@ -857,8 +857,9 @@ class DenoiseEngine:
                 sk, md = self._encoder(E, x_all[b0 * B * hw:(b0 + nb) * B * hw], imgs, temb_all[b0 * B:(b0 + nb) * B],
                                        ctx_all[b0 * B * nt:(b0 + nb) * B * nt], seg, tag,
                                        on_level if self.merge_early else None)
+                outs_chain = sk + [md]  # one list per chain: block_span() recognises blocks of the same traversal by it
                 for i, blk in enumerate(blocks):
-                    results[(kind, blk)] = (sk + [md], i * B)
+                    results[(kind, blk)] = (outs_chain, i * B)
                 ev = torch.cuda.Event()
                 ev.record(st)
                 done_events.append(ev)

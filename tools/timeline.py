@@ -81,9 +81,17 @@ _enc = eng._encoder
 def enc_wrapped(E, x_, imgs, temb, ctx, seg, tag, on_level=None):
     if torch.cuda.is_current_stream_capturing():
         stamp("PHASE", f"begin encoder {tag}")
-    r = _enc(E, x_, imgs, temb, ctx, seg, tag, on_level)
-    if torch.cuda.is_current_stream_capturing():
-        stamp("PHASE", f"end encoder {tag}")
+    capturing = torch.cuda.is_current_stream_capturing()
+    n_levels = len(eng.res_shapes)
+
+    def on_level2(li, t):
+        # the "end" probe must precede the event that joins this stream back into the graph
+        if capturing and li == n_levels - 1:
+            stamp("PHASE", f"end encoder {tag}")
+        if on_level is not None:
+            on_level(li, t)
+
+    r = _enc(E, x_, imgs, temb, ctx, seg, tag, on_level2)
     return r
 
 
