@@ -216,6 +216,140 @@ static int gn_apply_t(const EsGroupNorm* g, cudaStream_t s) {
   return 0;
 }
 
+// ---------------------------------------------------------------- GroupNorm in ONE pass over memory (cluster + DSMEM)
+// One thread-block cluster of 8 CTAs per (image, group): every CTA keeps its 1/8 of the group's hw x cpg slab in
+// registers, the eight partial (sum, sumsq) meet through distributed shared memory, and the normalised (+SiLU) values
+// are written from registers -- one read and one write of the tensor, one launch, no statistics buffer.  Used where
+// the producer could not accumulate the statistics itself (the decoder's [x | skip] concat inputs, the first resnet
+// of an encoder pass).
+constexpr int kGnfThreads = 512;
+constexpr int kGnfCluster = 8;
+
+template <typename T, int PPT, int JPT>
+__global__ void __cluster_dims__(kGnfCluster, 1, 1) __launch_bounds__(kGnfThreads, 1)
+gn_fused_kernel(const T* __restrict__ x, int C, long long ldx, int hw, int groups, float eps,
+                const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ out, long long ldo,
+                int silu) {
+  __shared__ float warp_part[kGnfThreads / 32][2];
+  __shared__ float cta_part[2];
+  pdl_launch_dependents();
+  pdl_wait();  // PDL: inputs are produced by the preceding kernel
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int g = blockIdx.x / kGnfCluster;
+  const int img = blockIdx.y;
+  const int cpg = C / groups;
+  const int pairs = cpg >> 1;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int px_per_cta = hw / kGnfCluster;
+  const int p_begin = rank * px_per_cta;
+  const int ch0 = g * cpg;
+  const T* src = x + (static_cast<long long>(img) * hw + p_begin) * ldx + ch0;
+  uint32_t v[PPT][JPT];
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int pi = 0; pi < PPT; ++pi) {
+    const int p = ty + 16 * pi;
+#pragma unroll
+    for (int jj = 0; jj < JPT; ++jj) {
+      const int j = tx + 32 * jj;
+      v[pi][jj] = 0u;
+      if (p < px_per_cta && j < pairs) v[pi][jj] = *reinterpret_cast<const uint32_t*>(src + static_cast<long long>(p) * ldx + 2 * j);
+    }
+  }
+#pragma unroll
+  for (int pi = 0; pi < PPT; ++pi)
+#pragma unroll
+    for (int jj = 0; jj < JPT; ++jj) {
+      const float2 f = Cvt<T>::unpack2(v[pi][jj]);  // elements that were not loaded are zero
+      s += f.x + f.y;
+      q += f.x * f.x + f.y * f.y;
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (tx == 0) {
+    warp_part[ty][0] = s;
+    warp_part[ty][1] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < kGnfThreads / 32; ++w) {
+      a += warp_part[w][0];
+      b += warp_part[w][1];
+    }
+    cta_part[0] = a;
+    cta_part[1] = b;
+  }
+  cluster_sync_all();  // every CTA's partial is visible cluster-wide
+  float ts = 0.f, tq = 0.f;
+#pragma unroll
+  for (int r = 0; r < kGnfCluster; ++r) {
+    const uint32_t a = mapa_u32(cta_part, static_cast<uint32_t>(r));
+    float ps, pq;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(ps) : "r"(a));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(pq) : "r"(a + 4));
+    ts += ps;
+    tq += pq;
+  }
+  cluster_sync_all();  // nobody exits (and releases its shared memory) while a peer still reads it
+  const float inv_n = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
+  const float mean = ts * inv_n;
+  const float rstd = rsqrtf(fmaxf(tq * inv_n - mean * mean, 0.f) + eps);
+  T* dst = out + (static_cast<long long>(img) * hw + p_begin) * ldo + ch0;
+#pragma unroll
+  for (int jj = 0; jj < JPT; ++jj) {
+    const int j = tx + 32 * jj;
+    if (j >= pairs) continue;
+    const float2 gm = *reinterpret_cast<const float2*>(gamma + ch0 + 2 * j);
+    const float2 bt = *reinterpret_cast<const float2*>(beta + ch0 + 2 * j);
+    const float a0 = rstd * gm.x, a1 = rstd * gm.y;
+    const float b0 = bt.x - mean * a0, b1 = bt.y - mean * a1;
+#pragma unroll
+    for (int pi = 0; pi < PPT; ++pi) {
+      const int p = ty + 16 * pi;
+      if (p < px_per_cta) {
+        const float2 f = Cvt<T>::unpack2(v[pi][jj]);
+        float y0 = f.x * a0 + b0, y1 = f.y * a1 + b1;
+        if (silu) {
+          y0 = silu_f(y0);
+          y1 = silu_f(y1);
+        }
+        *reinterpret_cast<uint32_t*>(dst + static_cast<long long>(p) * ldo + 2 * j) = Cvt<T>::pack2(y0, y1);
+      }
+    }
+  }
+}
+
+template <typename T>
+static int gn_fused_t(const EsGroupNorm* g, cudaStream_t s) {
+  const int C = g->c0;
+  const int cpg = C / g->groups;
+  ES_CHECK(g->c1 == 0 && g->hw % kGnfCluster == 0 && cpg % 2 == 0 && C % 2 == 0 && g->ld0 % 2 == 0 && g->ldo % 2 == 0,
+           "es_groupnorm_fused: unsupported geometry (hw %d, channels per group %d)", g->hw, cpg);
+  ES_CHECK(g->out && g->gamma && g->beta, "es_groupnorm_fused: bad output/affine");
+  const int ppt = ceil_div(g->hw / kGnfCluster, 16);
+  const int jpt = ceil_div(cpg / 2, 32);
+  dim3 grid(g->groups * kGnfCluster, g->n_img, 1), block(kGnfThreads);
+  const T* x = reinterpret_cast<const T*>(g->x0);
+  T* o = reinterpret_cast<T*>(g->out);
+#define ES_GNF(P, J)                                                                                                  \
+  ES_CUDA(launch_kernel(gn_fused_kernel<T, P, J>, dim3(grid), dim3(block), 0, s, x, C, g->ld0, g->hw, g->groups, g->eps, \
+                        g->gamma, g->beta, o, g->ldo, g->silu))
+  if (jpt == 1 && ppt <= 4) ES_GNF(4, 1);
+  else if (jpt == 1 && ppt <= 8) ES_GNF(8, 1);
+  else if (jpt == 1 && ppt <= 32) ES_GNF(32, 1);
+  else if (jpt == 2 && ppt <= 2) ES_GNF(2, 2);
+  else if (jpt == 2 && ppt <= 8) ES_GNF(8, 2);
+  else if (jpt == 2 && ppt <= 32) ES_GNF(32, 2);
+  else ES_CHECK(false, "es_groupnorm_fused: slab too large (hw %d, channels per group %d)", g->hw, cpg);
+#undef ES_GNF
+  ES_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ---------------------------------------------------------------- LayerNorm: warps own rows, R rows in flight
 template <typename T, int MAXV, int R>
 __global__ void layernorm_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ out, long long ldo,
@@ -320,6 +454,12 @@ extern "C" int es_groupnorm_apply(const EsGroupNorm* g, void* stream) {
   if (es::gn_check(g)) return -1;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   return g->dtype == ES_DTYPE_BF16 ? es::gn_apply_t<__nv_bfloat16>(g, s) : es::gn_apply_t<__half>(g, s);
+}
+extern "C" int es_groupnorm_fused(const EsGroupNorm* g, void* stream) {
+  ES_CHECK(g && g->x0, "es_groupnorm_fused: null pointer");
+  ES_CHECK(g->groups > 0 && g->c0 % g->groups == 0, "es_groupnorm_fused: bad channel count %d", g->c0);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return g->dtype == ES_DTYPE_BF16 ? es::gn_fused_t<__nv_bfloat16>(g, s) : es::gn_fused_t<__half>(g, s);
 }
 extern "C" int es_layernorm(int dtype, const void* x, long long ldx, void* out, long long ldo, const float* gamma,
                             const float* beta, int rows, int c, float eps, void* stream) {

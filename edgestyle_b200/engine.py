@@ -346,8 +346,10 @@ class DenoiseEngine:
         assert sorted(b for k, bl in self.chains if k == "base" for b in bl) == [0, 1, 2, 3], spec
         assert sorted(b for k, bl in self.chains if k == "pose" for b in bl) == [0, 1, 2], spec
         assert self.chains[0][0] == "base" and 0 in self.chains[0][1], "the first chain (main stream) must hold the UNet rows"
-        self._chain_streams = [torch.cuda.Stream(device=self.dev) for _ in range(len(self.chains) - 1)]
-        self._merge_stream = torch.cuda.Stream(device=self.dev)
+        # stream priorities (ES_PRIO = "<chains>,<merge>", lower number = higher priority, 0 = default)
+        prio = [int(v) for v in os.environ.get("ES_PRIO", "0,0").split(",")]
+        self._chain_streams = [torch.cuda.Stream(device=self.dev, priority=prio[0]) for _ in range(len(self.chains) - 1)]
+        self._merge_stream = torch.cuda.Stream(device=self.dev, priority=prio[1])
         self._side_ws = []
         for st in self._chain_streams + [self._merge_stream]:  # concurrent launches must not share split-K scratch
             ws = torch.zeros(128 << 20, dtype=torch.uint8, device=self.dev)

@@ -65,6 +65,7 @@ EXPORTS = {
     "es_attention": (C.c_int, [C.POINTER(EsAttention), vp]),
     "es_groupnorm_stats": (C.c_int, [C.POINTER(EsGroupNorm), vp]),
     "es_groupnorm_apply": (C.c_int, [C.POINTER(EsGroupNorm), vp]),
+    "es_groupnorm_fused": (C.c_int, [C.POINTER(EsGroupNorm), vp]),
     "es_layernorm": (C.c_int, [C.c_int, vp, ll, vp, ll, vp, vp, C.c_int, C.c_int, C.c_float, vp]),
     "es_merge_phase": (C.c_int, [C.POINTER(EsMerge), C.c_int, vp]),
     "es_timestep_embedding": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),

@@ -269,6 +269,14 @@ def attention(q, k, v, out, batch: int, heads: int, nq: int, nkv: int, scale: Op
     return out
 
 
+import os as _os
+
+# Single-launch cluster/DSMEM GroupNorm (es_groupnorm_fused) where no producer accumulated the statistics.  Parity-
+# tested, but measured slower inside the step than the stats + apply pair (11.55 vs 11.35 ms/step: 8-CTA clusters of
+# 4-byte loads schedule worse than the two wide streaming kernels), so it is off unless ES_FUSED_GN=1.
+FUSED_GROUPNORM = _os.environ.get("ES_FUSED_GN", "0") != "0"
+
+
 def groupnorm(x0, out, gamma, beta, ws, n_img: int, hw: int, groups: int, eps: float, silu: bool, x1=None,
               zero_ws: bool = True, stats_ready: bool = False):
     """GroupNorm(+SiLU) over [n_img*hw, c0(+c1)]; ws: fp32 [n_img, groups, 2] scratch (zeroed here unless the
@@ -288,6 +296,11 @@ def groupnorm(x0, out, gamma, beta, ws, n_img: int, hw: int, groups: int, eps: f
     if stats_ready:  # the producing GEMM already accumulated (sum, sumsq) into ws (EsGemm.gn_ws)
         _count(1)
         check(lib.es_groupnorm_apply(C.byref(g), _stream()), "es_groupnorm_apply")
+        return out
+    cpg = (g.c0 + g.c1) // groups
+    if FUSED_GROUPNORM and x1 is None and hw % 8 == 0 and cpg % 2 == 0 and cpg <= 128 and hw <= 8 * 16 * 32:
+        _count(1)  # one cluster per (image, group): statistics and normalisation in a single pass
+        check(lib.es_groupnorm_fused(C.byref(g), _stream()), "es_groupnorm_fused")
         return out
     if zero_ws:
         ws.zero_()

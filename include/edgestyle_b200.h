@@ -150,6 +150,10 @@ typedef struct EsGroupNorm {
 } EsGroupNorm;
 int es_groupnorm_stats(const EsGroupNorm* g, void* stream);
 int es_groupnorm_apply(const EsGroupNorm* g, void* stream);
+/* Single-launch GroupNorm(+SiLU) for inputs whose statistics no producer accumulated: a cluster of 8 CTAs per
+ * (image, group) holds the group's slab in registers and reduces through distributed shared memory (x1 must be NULL,
+ * hw % 8 == 0, even channels per group, hw * channels-per-group <= 262144; `ws` is not used). */
+int es_groupnorm_fused(const EsGroupNorm* g, void* stream);
 
 /* LayerNorm over the channel dim of [rows, c] (eps 1e-5, affine): BasicTransformerBlock.norm1/2/3. */
 int es_layernorm(int dtype, const void* x, long long ldx, void* out, long long ldo, const float* gamma,

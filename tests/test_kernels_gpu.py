@@ -414,6 +414,43 @@ def test_groupnorm(n_img, hw, c0, c1, silu):
     _close(out, want, 4e-3, 4e-3, "groupnorm")
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n_img,hw,C,ld,silu", [(2, 4096, 320, 320, True), (2, 4096, 960, 960, True), (2, 1024, 1920, 1920, True),
+                                                (2, 64, 2560, 2560, True), (3, 256, 2560, 2560, False), (2, 1024, 640, 1280, True),
+                                                (1, 8, 64, 64, True), (2, 4096, 640, 640, False)])
+def test_groupnorm_fused_cluster(n_img, hw, C, ld, silu, dtype):
+    """Single-launch GroupNorm (cluster of 8 CTAs per (image, group), DSMEM reduction) against torch, and against the
+    two-kernel path it replaces."""
+    from edgestyle_b200 import ops
+
+    buf = (_rand(n_img * hw, ld, seed=47) * 2 + 0.5).to(dtype)
+    x = buf[:, :C]  # pitch ld >= C: a column slice of a wider buffer
+    gamma = _rand(C, dtype=torch.float32, seed=48) * 0.1 + 1
+    beta = _rand(C, dtype=torch.float32, seed=49) * 0.1
+    ws = torch.zeros(n_img, 32, 2, device=DEV, dtype=torch.float32)
+    out = torch.zeros(n_img * hw, C, device=DEV, dtype=dtype)
+    prev = ops.FUSED_GROUPNORM
+    ops.FUSED_GROUPNORM = True
+    try:
+        n0 = ops.LAUNCHES
+        ops.groupnorm(x, out, gamma, beta, ws, n_img, hw, 32, 1e-5, silu)
+        assert ops.LAUNCHES - n0 == 1, "expected the single-launch path"
+    finally:
+        ops.FUSED_GROUPNORM = prev
+    want = F.group_norm(x.float().view(n_img, hw, C).permute(0, 2, 1), 32, gamma, beta, 1e-5)
+    if silu:
+        want = F.silu(want)
+    tol = 3e-2 if dtype == torch.bfloat16 else 4e-3
+    _close(out, want.permute(0, 2, 1).reshape(-1, C), tol, tol, "fused groupnorm")
+    ops.FUSED_GROUPNORM = False
+    try:
+        out2 = torch.zeros_like(out)
+        ops.groupnorm(x, out2, gamma, beta, ws, n_img, hw, 32, 1e-5, silu)
+    finally:
+        ops.FUSED_GROUPNORM = prev
+    _close(out, out2, tol, tol, "fused vs two-kernel groupnorm")
+
+
 @pytest.mark.parametrize("rows,c", [(8192, 320), (2048, 640), (512, 1280), (77, 32), (5, 2048)])
 def test_layernorm(rows, c):
     from edgestyle_b200 import ops
