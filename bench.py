@@ -273,7 +273,7 @@ def run_ours(args):
                      "peak_source": peak_src},
     }
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline(sample_steps=1)
+        line["cpu_baseline"] = cpu_baseline(sample_steps=3)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

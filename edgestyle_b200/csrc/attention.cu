@@ -35,6 +35,22 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA pipe (Cody-Waite split + degree-4 polynomial, relative error < 5e-5 -- below the 16-bit P it feeds):
+// the softmax is bound by the MUFU pipe (one ex2 per score), so a fraction of the exponentials is taken off it.
+#ifndef ES_ATT_POLY_EVERY
+#define ES_ATT_POLY_EVERY 0  // 0: all exponentials on MUFU; n: every n-th score of a row uses the polynomial
+#endif
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -120.f);
+  const float magic = 12582912.f;  // 1.5 * 2^23: adding it rounds x to the nearest integer in the low mantissa bits
+  const float xr = x + magic;
+  const float r = x - (xr - magic);  // [-0.5, 0.5]
+  float p = fmaf(r, 0.0096181291f, 0.0555041087f);
+  p = fmaf(p, r, 0.2402265070f);
+  p = fmaf(p, r, 0.6931471806f);
+  p = fmaf(p, r, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float y;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
@@ -212,8 +228,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (full_tile) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, neg_m));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, neg_m));
+          const float a0 = fmaf(__uint_as_float(v[i]), sl2, neg_m), a1 = fmaf(__uint_as_float(v[i + 1]), sl2, neg_m);
+          const float p0 = ex2_approx(a0);
+          const float p1 = (ES_ATT_POLY_EVERY > 0 && ((i + 1) % ES_ATT_POLY_EVERY) == ES_ATT_POLY_EVERY - 1)
+                               ? ex2_poly(a1) : ex2_approx(a1);
           s0 += p0;
           s1 += p1;
           pk[i >> 1] = Cvt<T>::pack2(p0, p1);

@@ -34,6 +34,15 @@ if what in ("attn", "all"):
         out = torch.empty(batch * n, C, device=dev, dtype=torch.float16)
         timeit(lambda: ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], out, batch, heads, n, n),
                f"attention b{batch} h{heads} d{d} n{n}", 4.0 * batch * heads * n * n * d)
+if what in ("pair", "all"):
+    # CTA-pair kernel (cta_group::2, 256 x 320 tiles) on the shapes the tuner gives it: GEGLU feed-forward, long-K linear
+    for (M, N, K, geglu) in [(32768, 2560, 320, True), (32768, 320, 1280, False)]:
+        x = torch.randn(M, K, device=dev, dtype=torch.float16)
+        wt = torch.randn(N, K, device=dev, dtype=torch.float16) * K ** -0.5
+        o = torch.empty(M, N // 2 if geglu else N, device=dev, dtype=torch.float16)
+        bias = torch.zeros(N, device=dev)
+        timeit(lambda: ops.gemm(x, wt, N, out=o, bias=bias, act=1 if geglu else 0, block_n=320),
+               f"pair gemm M={M} N={N} K={K}{' geglu' if geglu else ''}", 2.0 * M * N * K)
 if what in ("conv", "all"):
     for (imgs, h, w, cin, cout) in [(8, 64, 64, 320, 320), (8, 32, 32, 640, 640), (8, 8, 8, 1280, 1280)]:
         x = torch.randn(imgs * h * w, cin, device=dev, dtype=torch.float16)
