@@ -92,13 +92,11 @@ class EdgeStyleStableDiffusionControlNetPipeline:
         self.h2d_bytes = self.d2h_bytes = 0
         dev = torch.device("cuda", torch.cuda.current_device())
         self._guidance_scale = guidance_scale
-        cfg_on = self.do_classifier_free_guidance
-        if not cfg_on:
-            raise NotImplementedError("guidance_scale <= 1 (no CFG) is not implemented")
+        cfg_on = self.do_classifier_free_guidance  # guidance_scale <= 1 disables CFG (:319,329,443-447): one row per image
         n_img = prompt_embeds.shape[0]
-        if negative_prompt_embeds is None:
+        if cfg_on and negative_prompt_embeds is None:
             raise ValueError("negative_prompt_embeds is required when guidance_scale > 1")
-        B = 2 * n_img
+        B = 2 * n_img if cfg_on else n_img
         nets = 6
         # align control guidance (edgestyle_pipeline.py:264-283)
         if not isinstance(control_guidance_start, list):
@@ -108,12 +106,17 @@ class EdgeStyleStableDiffusionControlNetPipeline:
         if isinstance(controlnet_conditioning_scale, (int, float)):
             controlnet_conditioning_scale = [float(controlnet_conditioning_scale)] * nets
         # ---- inputs -> device ----
-        pe = torch.cat([self._to_dev(negative_prompt_embeds, dev), self._to_dev(prompt_embeds, dev)])  # :330
+        if cfg_on:
+            pe = torch.cat([self._to_dev(negative_prompt_embeds, dev), self._to_dev(prompt_embeds, dev)])  # :330
+        else:
+            pe = self._to_dev(prompt_embeds, dev)
         conds = []
         for c in image:
             c = self._to_dev(c, dev)
-            if c.shape[0] == n_img:  # CFG duplication of the cached embedding (:657-658)
+            if cfg_on and c.shape[0] == n_img:  # CFG duplication of the cached embedding (:657-658)
                 c = torch.cat([c] * 2)
+            if c.shape[0] != B:
+                raise ValueError(f"conditioning embedding has {c.shape[0]} rows, expected {B}")
             conds.append(c)
         h, w = conds[0].shape[-2:]
         if tuple(conds[0].shape[1:]) != (self.unet.config.block_out_channels[0], h, w):
@@ -128,17 +131,27 @@ class EdgeStyleStableDiffusionControlNetPipeline:
             latents = torch.randn((n_img, self.unet.config.in_channels, h, w), generator=generator,
                                   device=generator.device if generator is not None else "cpu")
         latents = self._to_dev(latents, dev).to(torch.float32).clone() * sch.init_noise_sigma
-        g = guidance_scale if torch.is_tensor(guidance_scale) else torch.full((n_img,), float(guidance_scale))
-        eng.guidance.copy_(self._to_dev(g.to(torch.float32), dev).reshape(-1).expand(n_img))
-        self.h2d_bytes += 0 if torch.is_tensor(guidance_scale) else 4 * n_img
+        if cfg_on:
+            g = guidance_scale if torch.is_tensor(guidance_scale) else torch.full((n_img,), float(guidance_scale))
+            eng.guidance.copy_(self._to_dev(g.to(torch.float32), dev).reshape(-1).expand(n_img))
+            self.h2d_bytes += 0 if torch.is_tensor(guidance_scale) else 4 * n_img
+        elif hasattr(sch, "device_step"):
+            raise NotImplementedError("guidance_scale <= 1 is implemented for the DDIM scheduler only")
         n_t = len(ts)
         for i, t in enumerate(ts):
             keeps = [1.0 - float(i / n_t < s or (i + 1) / n_t > e)
                      for s, e in zip(control_guidance_start, control_guidance_end)]  # :418-427
             cond_scale = [c * k for c, k in zip(controlnet_conditioning_scale, keeps)]
-            x = sch.scale_model_input(torch.cat([latents] * 2), t)  # :443-450
+            x = sch.scale_model_input(torch.cat([latents] * 2) if cfg_on else latents, t)  # :443-450
             eng.step(x, float(t), cond_scale)
-            if hasattr(sch, "device_step"):   # UniPC: x0-prediction + predictor/corrector linear combinations
+            if not cfg_on:                    # DDIM without CFG: x' = (a'/a) x + (s' - a' s / a) eps, a = sqrt(abar)
+                import math
+
+                from .. import ops
+                a_t, a_prev = sch.coefficients(int(t))
+                al, sg, alp, sgp = math.sqrt(a_t), math.sqrt(1 - a_t), math.sqrt(a_prev), math.sqrt(1 - a_prev)
+                ops.lincomb(latents, [(alp / al, latents), (sgp - alp * sg / al, eng.eps_out)])
+            elif hasattr(sch, "device_step"):   # UniPC: x0-prediction + predictor/corrector linear combinations
                 sch.device_step(eng.eps_out, latents, eng.guidance)
             else:                             # DDIM: fused CFG + update
                 a_t, a_prev = sch.coefficients(int(t))

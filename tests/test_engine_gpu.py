@@ -253,3 +253,58 @@ def test_unipc_pipeline_matches_oracle(spacing):
     psnr = _psnr(out.images, want)
     print(f"UniPC {spacing}: latent PSNR {psnr:.1f} dB")
     assert psnr >= 40.0
+
+
+def test_pipeline_without_cfg_matches_oracle():
+    """guidance_scale <= 1 disables classifier-free guidance (edgestyle_pipeline.py:319,443-447): one row per image,
+    odd row counts (64-row segments at the deepest level -> masked tiles, LayerNorm kernels instead of the folded path)."""
+    from edgestyle_b200 import config as C
+    from edgestyle_b200.model import (CachedControlNetModel, ControlLoRAModel, EdgeStyleMultiControlNetModel,
+                                      EdgeStyleStableDiffusionControlNetPipeline, UNet2DConditionModel)
+    from oracle.schedulers import DDIMScheduler
+    from oracle.sd15 import SD15Config
+    from oracle.step import build_models, fused_step, synthetic_inputs
+
+    ocfg = SD15Config(block_out_channels=(64, 128, 256, 256), cross_attention_dim=96)
+    h = w = 16
+    m = build_models(ocfg, (h, w), rank=4)
+    inp = synthetic_inputs(ocfg, 1, h, w)
+    cfg = C.UNetConfig.from_any(ocfg)
+    unet = UNet2DConditionModel(cfg, m.unet.state_dict())
+    agn = ControlLoRAModel(cfg, m.lora_agnostic.state_dict(), 4, unet=unet)
+    clo = ControlLoRAModel(cfg, m.lora_clothes.state_dict(), 4, unet=unet)
+    pose = CachedControlNetModel(cfg, m.openpose.state_dict())
+    multi = EdgeStyleMultiControlNetModel([agn, pose, clo, pose, clo, pose], m.controlnet.merge_state_dict(), (h, w))
+    pipe = EdgeStyleStableDiffusionControlNetPipeline(unet=unet, controlnet=multi)
+    conds1 = [c[1:] for c in inp.conds]  # the conditional row of each cached embedding
+    out = pipe(image=conds1, prompt_embeds=inp.prompt_embeds[1:], latents=inp.latents, num_inference_steps=4,
+               guidance_scale=1.0, output_type="latent")
+    m.unet.to(DEV)
+    m.controlnet.to(DEV)
+    sch = DDIMScheduler()
+    lat = inp.latents.to(DEV)
+    pe = inp.prompt_embeds[1:].to(DEV)
+    conds = [c.to(DEV) for c in conds1]
+    for t in sch.set_timesteps(4):
+        eps = fused_step(m, lat, t.to(DEV), pe, [1.0] * 6, conds)
+        lat = sch.step(eps, t, lat)
+    assert out.images.shape == lat.shape
+    assert _psnr(out.images, lat) >= 40.0
+
+
+def test_step_parity_768x1024_bf16(monkeypatch):
+    """BASELINE config 5: 96 x 128 latent (768 x 1024 image), bf16 storage, full SD1.5 widths -- long-sequence
+    self-attention (12288 tokens), 12 x 16 deepest level with masked conv tiles, merge blocks sized from the latent."""
+    from oracle.sd15 import SD15Config
+    from oracle.step import fused_step
+
+    monkeypatch.setenv("ES_AUTOTUNE", "0")  # heuristic tiles: tuning ~150 new shapes would dominate the test time
+    cfg = SD15Config()
+    m, inp, eng = _mk(cfg, 96, 128, rank=32, images=1, dtype=torch.bfloat16, use_graph=False)
+    x = torch.cat([inp.latents] * 2)
+    t = torch.tensor(701, device=DEV)
+    want = fused_step(m, x, t, inp.prompt_embeds, inp.conditioning_scale, inp.conds)
+    got = eng.step(x, t, inp.conditioning_scale)
+    cos, mx = _metrics(got, want)
+    print(f"768x1024 bf16: cos={cos:.6f} max_abs={mx:.4g}")
+    assert cos >= 0.999 and mx <= 8e-2, (cos, mx)
