@@ -33,9 +33,9 @@ UNIT = "steps/s"
 # 4.829 TFLOP) MINUS the step-invariant text K/V projections (5.56 GMAC/row = 0.022 TFLOP) that the engine computes
 # once per prompt instead of every step -- only executed work is credited.
 TFLOP_PER_STEP_B2 = 4.807
-# DRAM bytes per step of the dominant kernel family + the rest of the step, from profiles/r1_launches_final.csv
+# DRAM bytes per step of the dominant kernel family + the rest of the step, from profiles/r1c_launches_final.csv
 # (ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 673 launches of one step, caches flushed per kernel)
-DRAM_BYTES_PER_STEP_B2 = 9.04e9
+DRAM_BYTES_PER_STEP_B2 = 8.32e9
 
 
 def measured_peaks():
@@ -269,7 +269,7 @@ def run_ours(args):
                      "traffic": DRAM_BYTES_PER_STEP_B2 * images if images == 1 else None,
                      "kernel": "es::gemm_kernel (tcgen05 implicit GEMM) -- whole-step algorithmic FLOPs "
                                f"({TFLOP_PER_STEP_B2} TFLOP per CFG pair, SURVEY.md 8(d)) over the CUDA-event step time; "
-                               "traffic = DRAM bytes of all launches of one step (profiles/r1_launches_final.csv)",
+                               "traffic = DRAM bytes of all launches of one step (profiles/r1c_launches_final.csv)",
                      "peak_source": peak_src},
     }
     if not args.no_cpu_baseline and world == 1:
