@@ -26,6 +26,7 @@ PDL_TRIGGER_MAX_CTAS = int(os.environ.get("ES_PDL_TRIGGER_MAX_CTAS", "0"))
 NVCC_FLAGS.append(f"-DES_PDL_TRIGGER_MAX_CTAS={PDL_TRIGGER_MAX_CTAS}")
 # fraction of the softmax exponentials taken off the MUFU pipe (attention.cu): 0 = none, n = every n-th score
 NVCC_FLAGS.append(f"-DES_ATT_POLY_EVERY={int(os.environ.get('ES_ATT_POLY_EVERY', '0'))}")
+NVCC_FLAGS.append(f"-DES_PDL_LATE_TRIGGER={int(os.environ.get('ES_PDL_LATE_TRIGGER', '0'))}")
 OUT = os.environ.get("ES_LIB_OUT", OUT)
 OBJ = os.environ.get("ES_OBJ_DIR", OBJ)
 

@@ -68,6 +68,8 @@ struct GemmKParams {
   int n_out;             // output columns in total (N, or N/2 for GEGLU)
   // LayerNorm folded around the GEMM (see EsGemm): producer side accumulates per-row (sum, sumsq) of the OUTPUT,
   // consumer side normalises with the statistics of its INPUT rows: out = rstd (acc - mean colsum[n]) + bias'[n]
+  const void* prefetch;      // weights of the next GEMM of the stream: pulled into L2 while this kernel runs
+  long long prefetch_bytes;
   float* rowstat_out;
   const float* ln_rowstat;
   const float* ln_colsum;
@@ -182,6 +184,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     produce_a(kb);
   };
   const int kb_prefill = min(kb_end, kb_begin + stages);
+  if (warp == 2 && lane == 0)  // constant data: no need to wait for the previous kernel
+    l2_prefetch_slice(p.prefetch, p.prefetch_bytes, (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x,
+                      gridDim.x * gridDim.y * gridDim.z);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -247,6 +252,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       GEMM_TRACE(3);
       if (has_work) umma_commit(&accum_bar);  // accumulator complete
       else mbar_arrive(&accum_bar);
+      pdl_launch_dependents_late();
     }
   } else {
     // =============================== epilogue ===============================================
@@ -1021,6 +1027,8 @@ static int gemm_dispatch(const EsGemm* g, cudaStream_t stream) {
   kp.ldc = g->ldc;
   kp.out_fp32 = g->out_fp32;
   if (g->residual) ES_CHECK(g->ldr % 8 == 0, "es_gemm: ldr must be a multiple of 8");
+  kp.prefetch = g->prefetch;
+  kp.prefetch_bytes = g->prefetch_bytes;
   kp.rowstat_out = g->rowstat_out;
   kp.ln_rowstat = g->ln_rowstat;
   kp.ln_colsum = g->ln_colsum;

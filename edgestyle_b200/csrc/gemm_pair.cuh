@@ -116,6 +116,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int n_clusters = gridDim.x >> 1;
   const int kb1 = p.taps * p.kblocks1;
   pdl_launch_dependents();
+  if (warp == 2 && lane == 0) l2_prefetch_slice(p.prefetch, p.prefetch_bytes, blockIdx.x, gridDim.x);
   if (threadIdx.x == 0) PAIR_TRACE(0);
 
   if (warp == 0 && lane == 0) {

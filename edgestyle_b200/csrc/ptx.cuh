@@ -40,6 +40,17 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 #endif
 }
 
+// Late trigger: issued by a GEMM CTA once its last MMA has been committed, so the successor's prologue (launch, barrier
+// init, TMEM allocation, descriptor prefetch) overlaps this kernel's epilogue only.  Build with ES_PDL_LATE_TRIGGER=1.
+#ifndef ES_PDL_LATE_TRIGGER
+#define ES_PDL_LATE_TRIGGER 0
+#endif
+__device__ __forceinline__ void pdl_launch_dependents_late() {
+#if ES_PDL_LATE_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -87,6 +98,23 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 }
 
 // ---------------------------------------------------------------- TMA
+// Pull `bytes` (multiple of 16) of global memory into L2 without a destination: used to stream the NEXT layer's weights
+// from HBM while the current kernel runs.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
+}
+// CTA `cta` of `n_ctas` prefetches its slice of [base, base + total) in 32 KB pieces (one thread).
+__device__ __forceinline__ void l2_prefetch_slice(const void* base, long long total, int cta, int n_ctas) {
+  if (base == nullptr || total <= 0) return;
+  long long per = ((total + n_ctas - 1) / n_ctas + 15) & ~15ll;
+  long long lo = per * cta, hi = lo + per;
+  if (hi > total) hi = total & ~15ll;
+  const char* b = reinterpret_cast<const char*>(base);
+  for (long long o = lo; o < hi; o += 32768) {
+    const long long n = hi - o < 32768 ? hi - o : 32768;
+    l2_prefetch_bulk(b + o, static_cast<uint32_t>(n));
+  }
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }

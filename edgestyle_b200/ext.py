@@ -28,7 +28,8 @@ class EsGemm(C.Structure):
         ("rowvec_ld", C.c_int), ("residual", vp), ("ldr", ll), ("act", C.c_int), ("alpha", C.c_float),
         ("out", vp), ("ldc", ll), ("out_fp32", C.c_int), ("block_n", C.c_int), ("stages", C.c_int),
         ("split_k", C.c_int), ("b_blocked", C.c_int), ("gn_ws", vp), ("gn_groups", C.c_int), ("rowstat_out", vp), ("ln_rowstat", vp), ("ln_colsum", vp),
-        ("ln_features", C.c_int), ("ln_eps", C.c_float), ("workspace", vp), ("workspace_bytes", ll),
+        ("ln_features", C.c_int), ("ln_eps", C.c_float), ("prefetch", vp), ("prefetch_bytes", ll), ("workspace", vp),
+        ("workspace_bytes", ll),
     ]
 
 

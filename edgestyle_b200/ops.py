@@ -32,6 +32,48 @@ def set_stream_workspace(stream: "torch.cuda.Stream", ws: torch.Tensor) -> None:
     STREAM_WORKSPACES[stream.cuda_stream] = ws
 
 
+class WeightPrefetchPlan:
+    """Next-layer weight prefetch: the engine records, per stream, the weight tensors of the GEMMs of one eager step
+    ("record"); while the same step is captured into the CUDA graph ("use"), every GEMM is told the weights of the GEMM
+    that follows it on its stream and pulls them into L2 while it runs (EsGemm.prefetch)."""
+
+    MIN_BYTES = 1 << 20   # tiny weight sets are not worth a prefetch
+    MAX_BYTES = 48 << 20  # stay well inside the 126 MB L2 next to the running layer's own working set
+
+    def __init__(self):
+        self.mode = None
+        self.plan = {}
+        self.pos = {}
+
+    def begin(self, mode):
+        self.mode = mode
+        self.pos = {}
+        self.ids = {}  # stream handle -> ordinal of first appearance (graph capture runs on its own capture stream)
+        if mode == "record":
+            self.plan = {}
+
+    def end(self):
+        self.mode = None
+
+    def step(self, stream, ptr, nbytes):
+        """Called once per GEMM; returns (ptr, bytes) to prefetch or None."""
+        stream = self.ids.setdefault(stream, len(self.ids))
+        if self.mode == "record":
+            self.plan.setdefault(stream, []).append((ptr, nbytes))
+            return None
+        if self.mode == "use":
+            i = self.pos.get(stream, 0)
+            self.pos[stream] = i + 1
+            seq = self.plan.get(stream, [])
+            if i + 1 < len(seq) and seq[i][0] == ptr:
+                nptr, nb = seq[i + 1]
+                if nb >= self.MIN_BYTES and nptr != ptr:
+                    return nptr, min(nb, self.MAX_BYTES)
+        return None
+
+
+PREFETCH = WeightPrefetchPlan()
+
 LAUNCHES = 0  # native kernel launches issued through this module (bench.py reports it as gpu_launches)
 
 
@@ -244,6 +286,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: i
     if gn_ws is not None:
         g.gn_ws = gn_ws.data_ptr()
         g.gn_groups = gn_groups
+    if PREFETCH.mode is not None:
+        nxt = PREFETCH.step(_stream(), b.data_ptr(), b.numel() * b.element_size())
+        if nxt is not None:
+            g.prefetch, g.prefetch_bytes = nxt
     ws = workspace if workspace is not None else STREAM_WORKSPACES.get(_stream(), GEMM_WORKSPACE)
     if ws is not None:
         g.workspace = ws.data_ptr()

@@ -100,6 +100,9 @@ typedef struct EsGemm {
   const float* ln_colsum;
   int ln_features; /* number of features the statistics were taken over (C) */
   float ln_eps;
+  const void* prefetch; /* optional: `prefetch_bytes` of constant global memory (the next layer's weights) that this
+                           launch pulls into L2 while it runs (cp.async.bulk.prefetch.L2), spread over its CTAs */
+  long long prefetch_bytes;
   void* workspace; /* optional split-K scratch: first 64 KiB = tile counters (zero-initialised ONCE by the caller,
                       self-resetting), rest = fp32 partial tiles.  Must not be shared by concurrent launches. */
   long long workspace_bytes;
