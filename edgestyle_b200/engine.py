@@ -776,9 +776,15 @@ class DenoiseEngine:
         return skips, mid
 
     # ------------------------------------------------------------------------------------ the step
-    def _run_step(self, cond_scale: Sequence[float], mode: str = "step"):
+    def _run_step(self, cond_scale: Sequence[float], mode: str = "step", guess_mode: bool = False,
+                  zero_uncond: bool = False):
         """mode 'step': full fused step -> eps_out.  mode 'residuals': stop after the merge and leave the 13
-        merged residuals (what EdgeStyleMultiControlNetModel.forward returns) in self.res_out."""
+        merged residuals (what EdgeStyleMultiControlNetModel.forward returns) in self.res_out.
+
+        guess_mode: every ControlNet scales its 13 outputs by logspace(-1, 0, 13) * conditioning_scale
+        (controllora.py:257-265) instead of a uniform scale.  zero_uncond: the pipeline's guess mode under CFG
+        (edgestyle_pipeline.py:453-459, 487-497) -- the merged residuals of the unconditional rows (first half of the
+        batch) are dropped, i.e. those rows keep the plain UNet skips."""
         cfg, B = self.cfg, self.B
         h, w = self.h, self.w
         hw = h * w
@@ -889,6 +895,7 @@ class DenoiseEngine:
         #    stream in the order the decoder consumes them (mid, then skips 11..0): the large 64x64-level merges
         #    overlap the decoder's deep levels; the decoder waits on one event per level
         scale = [float(s) for s in cond_scale]
+        level_gain = torch.logspace(-1, 0, len(self.res_shapes)).tolist() if guess_mode else [1.0] * len(self.res_shapes)
         merged = {}
         side = self._merge_stream
         if not self.merge_early:
@@ -950,8 +957,14 @@ class DenoiseEngine:
                     dst, skip = cbuf[:, xc:], unet_rows
                 else:  # mid: becomes the x half of the first decoder concat
                     dst, skip = cats[(0, 0)][0][:, :c], unet_rows
-                ops.merge(res, scale, self.merge[li], self._merge_slot(), z, B, H * W, c, dst, skip=skip,
-                          zero_stats=False)
+                ops.merge(res, [sc * level_gain[li] for sc in scale], self.merge[li], self._merge_slot(), z, B, H * W, c,
+                          dst, skip=skip, zero_stats=False)
+                if zero_uncond:
+                    nu = (B // 2) * H * W  # rows of the unconditional images (negative prompt rows come first)
+                    if skip is not None:
+                        dst[:nu].copy_(skip[:nu])
+                    else:
+                        dst[:nu].zero_()
                 merged[li] = torch.cuda.Event()
                 merged[li].record(side)
         self._temb_ready = None
@@ -1005,11 +1018,17 @@ class DenoiseEngine:
 
     # ------------------------------------------------------------------------------------ public
     @torch.no_grad()
-    def step(self, sample: torch.Tensor, timestep, cond_scale: Sequence[float] = (1.0,) * 6) -> torch.Tensor:
+    def step(self, sample: torch.Tensor, timestep, cond_scale: Sequence[float] = (1.0,) * 6, guess_mode: bool = False,
+             zero_uncond: bool = False) -> torch.Tensor:
         """noise_pred = UNet(sample, t, ehs, residuals(6 ControlNets + merge)) -- the fused single-step form the
         reference defines at /root/reference/export_onnx.py:43-74.  Returns a view of the static output buffer."""
         self._load_sample_t(sample, timestep)
         key = tuple(float(s) for s in cond_scale)
+        if guess_mode or zero_uncond:  # the rare path: eager (no graph per flag combination)
+            n0 = ops.LAUNCHES
+            self._run_step(key, guess_mode=guess_mode, zero_uncond=zero_uncond)
+            self.launches_per_step = ops.LAUNCHES - n0
+            return self.eps_out
         if not self.use_graph:
             n0 = ops.LAUNCHES
             self._run_step(key)
@@ -1059,11 +1078,12 @@ class DenoiseEngine:
         self.t_in.copy_(t.expand(self.B) if t.numel() == 1 else t)
 
     @torch.no_grad()
-    def residuals(self, sample, timestep, cond_scale: Sequence[float]) -> Tuple[List[torch.Tensor], torch.Tensor]:
+    def residuals(self, sample, timestep, cond_scale: Sequence[float],
+                  guess_mode: bool = False) -> Tuple[List[torch.Tensor], torch.Tensor]:
         """EdgeStyleMultiControlNetModel.forward (edgestyle_multicontrolnet.py:116-171): 12 merged down residuals +
         mid as fresh NCHW fp32 tensors."""
         self._load_sample_t(sample, timestep)
-        self._run_step(tuple(float(s) for s in cond_scale), mode="residuals")
+        self._run_step(tuple(float(s) for s in cond_scale), mode="residuals", guess_mode=guess_mode)
         outs = []
         for li, (c, H, W) in enumerate(self.res_shapes):
             dst = torch.empty(self.B, c, H, W, device=self.dev, dtype=torch.float32)

@@ -85,15 +85,14 @@ class EdgeStyleMultiControlNetModel:
                           ("attention_mask", attention_mask), ("added_cond_kwargs", added_cond_kwargs)):
             if val is not None:
                 raise NotImplementedError(f"{name} is not used by SD1.5 and not implemented")
-        if guess_mode:
-            raise NotImplementedError("guess_mode through the batched path (row N4 of SURVEY.md 8(f))")
         if len(controlnet_cond) != 6 or len(conditioning_scale) != 6:
             raise ValueError("expected six conditioning tensors and six scales")
         B, _, h, w = sample.shape
         eng = self.engine(B, h, w)
         eng.set_prompt(encoder_hidden_states)
         eng.set_conditioning(controlnet_cond)
-        down, mid = eng.residuals(sample, timestep, conditioning_scale)
+        # guess_mode: each net scales its outputs by logspace(-1, 0, 13) * scale (controllora.py:257-265) before the merge
+        down, mid = eng.residuals(sample, timestep, conditioning_scale, guess_mode=guess_mode)
         return down, mid
 
     __call__ = forward

@@ -79,8 +79,6 @@ class EdgeStyleStableDiffusionControlNetPipeline:
         for name, val in (("ip_adapter_image", ip_adapter_image), ("clip_skip", clip_skip), ("timesteps", timesteps)):
             if val is not None:
                 raise NotImplementedError(f"{name} is not implemented")
-        if guess_mode:
-            raise NotImplementedError("guess_mode is not implemented")
         if eta != 0.0:
             raise NotImplementedError("eta != 0 (stochastic DDIM) is not implemented")
         if cross_attention_kwargs and cross_attention_kwargs.get("scale", 1.0) != 1.0:
@@ -143,7 +141,9 @@ class EdgeStyleStableDiffusionControlNetPipeline:
                      for s, e in zip(control_guidance_start, control_guidance_end)]  # :418-427
             cond_scale = [c * k for c, k in zip(controlnet_conditioning_scale, keeps)]
             x = sch.scale_model_input(torch.cat([latents] * 2) if cfg_on else latents, t)  # :443-450
-            eng.step(x, float(t), cond_scale)
+            # guess_mode (:453-459, 487-497): logspace-scaled ControlNet outputs; under CFG the ControlNets only act on
+            # the conditional rows, the unconditional rows keep the plain UNet skips
+            eng.step(x, float(t), cond_scale, guess_mode=guess_mode, zero_uncond=guess_mode and cfg_on)
             if not cfg_on:                    # DDIM without CFG: x' = (a'/a) x + (s' - a' s / a) eps, a = sqrt(abar)
                 import math
 

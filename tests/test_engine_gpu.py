@@ -308,3 +308,40 @@ def test_step_parity_768x1024_bf16(monkeypatch):
     cos, mx = _metrics(got, want)
     print(f"768x1024 bf16: cos={cos:.6f} max_abs={mx:.4g}")
     assert cos >= 0.999 and mx <= 8e-2, (cos, mx)
+
+
+def test_guess_mode_multi_and_pipeline():
+    """guess_mode: (1) EdgeStyleMultiControlNetModel.forward with logspace-scaled ControlNet outputs
+    (controllora.py:257-265) through the batched engine; (2) the pipeline's guess mode under CFG
+    (edgestyle_pipeline.py:453-459, 487-497): ControlNets act on the conditional rows only."""
+    from oracle.schedulers import DDIMScheduler
+    from oracle.sd15 import SD15Config
+    from oracle.step import cfg_combine
+
+    cfg = SD15Config(block_out_channels=(64, 128, 256, 256), cross_attention_dim=96)
+    h = w = 16
+    m, inp, eng = _mk(cfg, h, w, rank=4, images=1)
+    x = torch.cat([inp.latents] * 2)
+    t = torch.tensor(801, device=DEV)
+    scale = [1.0, 0.5, 2.0, 1.0, 0.7, 1.5]
+    wd, wm = m.controlnet(x, t, inp.prompt_embeds, inp.conds, scale, guess_mode=True)
+    gd, gm = eng.residuals(x, t, scale, guess_mode=True)
+    for a, b in zip(list(gd) + [gm], list(wd) + [wm]):
+        assert (a - b).abs().max().item() <= 1e-2 * max(1.0, b.abs().max().item())
+    # pipeline semantics, one step: ControlNets on the conditional row, zeros for the unconditional one
+    lat = inp.latents
+    pe = inp.prompt_embeds
+    cd, cm = m.controlnet(lat, t, pe[1:], [c[1:] for c in inp.conds], scale, guess_mode=True)
+    cd = [torch.cat([torch.zeros_like(d), d]) for d in cd]
+    cm = torch.cat([torch.zeros_like(cm), cm])
+    want_eps = m.unet(x, t, pe, down_block_additional_residuals=cd, mid_block_additional_residual=cm)
+    got_eps = eng.step(x, t, scale, guess_mode=True, zero_uncond=True)
+    cos, mx = _metrics(got_eps, want_eps)
+    assert cos >= 0.999 and mx <= 2e-2, (cos, mx)
+    sch = DDIMScheduler()
+    sch.set_timesteps(20)
+    want = sch.step(cfg_combine(want_eps, 4.5), 801, lat)
+    got = lat.clone().float()
+    a_t, a_p = sch.coefficients(801)
+    eng.cfg_ddim_update(got, float(a_t), float(a_p), 4.5)
+    assert (got - want).abs().max().item() <= 2e-2

@@ -125,7 +125,9 @@ def test_pipeline_rejects_out_of_scope_arguments(models):
     with pytest.raises(NotImplementedError):
         pipe(image=conds, prompt_embeds=pe, negative_prompt_embeds=pe, output_type="pil")
     with pytest.raises(NotImplementedError):
-        pipe(image=conds, prompt_embeds=pe, negative_prompt_embeds=pe, output_type="latent", guess_mode=True)
+        pipe(image=conds, prompt_embeds=pe, negative_prompt_embeds=pe, output_type="latent", eta=0.5)
+    with pytest.raises(NotImplementedError):
+        pipe(image=conds, prompt_embeds=pe, negative_prompt_embeds=pe, output_type="latent", clip_skip=1)
     with pytest.raises(ValueError):
         pipe(image=conds[:4], prompt_embeds=pe, negative_prompt_embeds=pe, output_type="latent")
 
