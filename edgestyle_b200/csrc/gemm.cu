@@ -443,6 +443,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // epilogue vector sits right behind them.
         constexpr int NOUT = BLOCK_N;                      // accumulator columns per tile
         const bool geglu = p.act == ES_ACT_GEGLU;
+        const bool silu_act = p.act == ES_ACT_SILU;        // applied before the residual add
         const int n_tile_out = geglu ? NOUT / 2 : NOUT;    // output columns of this tile
         const int oc0 = geglu ? blockIdx.y * (NOUT / 2) : n0;
         const int full_panels = n_tile_out / 64;
@@ -559,7 +560,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               load_cols(c, o);
               pre16(c, o);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] *= p.alpha;
+              for (int j = 0; j < 16; ++j) o[j] = silu_act ? silu_f(o[j] * p.alpha) : o[j] * p.alpha;
             }
             finish_chunk(c, o);
           }
@@ -607,7 +608,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(a[j]);
             pre16(c, o);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] *= p.alpha;
+            for (int j = 0; j < 16; ++j) o[j] = silu_act ? silu_f(o[j] * p.alpha) : o[j] * p.alpha;
             finish_chunk(c, o);
           };
 #pragma unroll 1
@@ -759,6 +760,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) o[j] *= p.alpha;
+            if (p.act == ES_ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = silu_f(o[j]);
+            }
             if (p.residual) {
               if (full) {
                 const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
@@ -1046,6 +1051,7 @@ static int gemm_dispatch(const EsGemm* g, cudaStream_t stream) {
     if (flat) ES_CHECK(g->nseg <= 1 || true, "es_gemm: ok");
   }
   if (g->act == ES_ACT_GEGLU) ES_CHECK(g->n % 2 == 0 && !g->out_fp32 && !g->residual && !g->rowvec, "es_gemm: bad GEGLU config");
+  ES_CHECK(g->act == ES_ACT_NONE || g->act == ES_ACT_GEGLU || g->act == ES_ACT_SILU, "es_gemm: unknown activation %d", g->act);
 
   int bn_tile = g->block_n > 0 ? g->block_n : pick_block_n(g->n, m_tiles, g->act, g->taps * ceil_div(g->c1, kBlockK));
   // block_n == 320 selects the CTA-pair kernel (256 x 320 tiles, cta_group::2); problems it cannot run fall back

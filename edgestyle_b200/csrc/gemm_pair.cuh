@@ -655,7 +655,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 // Host side.  Returns 1 when the pair kernel cannot run this problem (caller falls back to the single-CTA kernel).
 static bool gemm_pair_eligible(const EsGemm* g, const GemmKParams& kp, int m_tiles) {
-  if (g->n % kPairN != 0 || g->out_fp32 || g->b_blocked) return false;
+  if (g->n % kPairN != 0 || g->out_fp32 || g->b_blocked || g->act == ES_ACT_SILU) return false;
   if (g->act == ES_ACT_GEGLU && (g->n / 2) % 8 != 0) return false;
   const int n_out = g->act == ES_ACT_GEGLU ? g->n / 2 : g->n;
   const bool aligned = (reinterpret_cast<uintptr_t>(g->out) & 15) == 0 && g->ldc % 8 == 0 && n_out % 8 == 0 &&

@@ -28,7 +28,7 @@ import torch
 
 from . import config as C
 from . import ops
-from .ext import ACT_GEGLU
+from .ext import ACT_GEGLU, ACT_SILU
 
 SUPPORTED_PATTERN = (0, None, 1, None, 1, None)
 
@@ -415,6 +415,31 @@ class DenoiseEngine:
     def _mat(self, t):
         return t.to(device=self.dev, dtype=self.dtype).contiguous()
 
+    def _pack_pose_embedder(self, sd):
+        """ControlNetConditioningEmbedding of the openpose net (diffusers controlnet.py; reached from
+        CachedControlNetModel.preprocess_image, controllora.py:289-290, and :199-201 for raw images): conv_in, pairs
+        of (3x3, 3x3 stride 2) blocks, conv_out -- [(weight [cout, 9 * cin_pad], bias, cin_pad, cout, stride, silu)].
+        None when the checkpoint carries no embedder."""
+        p = "controlnet_cond_embedding"
+        if f"{p}.conv_in.weight" not in sd:
+            return None
+        names = [(f"{p}.conv_in", 1, True)]
+        i = 0
+        while f"{p}.blocks.{i}.weight" in sd:
+            names.append((f"{p}.blocks.{i}", 2 if i % 2 else 1, True))
+            i += 1
+        names.append((f"{p}.conv_out", 1, False))
+        layers = []
+        for name, stride, silu in names:
+            w = sd[name + ".weight"].float().cpu()  # [cout, cin, 3, 3]
+            cout, cin = w.shape[:2]
+            cin_pad = _pad8(cin)
+            wp = torch.zeros(cout, 3, 3, cin_pad)
+            wp[..., :cin] = w.permute(0, 2, 3, 1)
+            layers.append((self._mat(wp.reshape(cout, 9 * cin_pad)), self._f32(sd[name + ".bias"]), cin_pad, cout, stride,
+                           silu))
+        return layers
+
     def _f32(self, t):
         return t.to(device=self.dev, dtype=torch.float32).contiguous()
 
@@ -423,6 +448,7 @@ class DenoiseEngine:
         assert len(lora_sds) == 2, "expected [agnostic, clothes] ControlLoRA state dicts"
         self.enc_base = self._pack_encoder(unet_sd, lora_sds)
         self.enc_pose = self._pack_encoder(pose_sd, [])
+        self.pose_embed = self._pack_pose_embedder(pose_sd)
         # UNet decoder
         P = _Packer(unet_sd, [], self.dtype, self.dev, True, self.fold_ln)
         nb = len(cfg.block_out_channels)
@@ -1138,6 +1164,34 @@ class DenoiseEngine:
             ops.nhwc_to_nchw(r, dst)
             outs.append(dst)
         return outs[:-1], outs[-1]
+
+    @torch.no_grad()
+    def embed_openpose(self, image: torch.Tensor) -> torch.Tensor:
+        """ControlNetConditioningEmbedding of the openpose ControlNet: image [n, 3, 8h', 8w'] (fp32, NCHW, values as the
+        reference's image processor produces them) -> conditioning embedding [n, c0, h', w'] fp32 NCHW.  Runs once per
+        pipeline call (prepare_image, edgestyle_pipeline.py:629-664), not per step."""
+        if self.pose_embed is None:
+            raise ValueError("the openpose checkpoint carries no controlnet_cond_embedding weights")
+        n, cin, H, W = image.shape
+        x = self.buf(f"pemb.in.{n}x{H}x{W}", n * H * W, self.pose_embed[0][2])
+        ops.nchw_to_nhwc(image.to(device=self.dev, dtype=torch.float32).contiguous(), x)
+        for li, (wgt, bias, cin_pad, cout, stride, silu) in enumerate(self.pose_embed):
+            assert x.shape[1] == cin_pad, (x.shape, cin_pad)
+            act = ACT_SILU if silu else 0
+            if stride == 1:
+                out = self.buf(f"pemb.{li}.{n}x{H}x{W}", n * H * W, cout)
+                ops.gemm(x, wgt, cout, out=out, taps=9, whn=(W, H, n), bias=bias, c1=cin_pad, act=act)
+            else:
+                Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+                col = self.buf(f"pemb.col{li}.{n}x{H}x{W}", n * Ho * Wo, 9 * cin_pad)
+                ops.im2col3x3(x, col, n, H, W, cin_pad, 2)
+                out = self.buf(f"pemb.{li}.{n}x{H}x{W}", n * Ho * Wo, cout)
+                ops.gemm(col, wgt, cout, out=out, bias=bias, act=act)
+                H, W = Ho, Wo
+            x = out
+        dst = torch.empty(n, x.shape[1], H, W, device=self.dev, dtype=torch.float32)
+        ops.nhwc_to_nchw(x, dst)
+        return dst
 
     @torch.no_grad()
     def cfg_ddim_update(self, latents: torch.Tensor, a_t: float, a_prev: float, guidance=None):

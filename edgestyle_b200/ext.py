@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("ES_LIB", os.path.join(HERE, "libedgestyle_b200.so"))
 
 ES_MAX_SEG = 4
 DTYPE_F16, DTYPE_BF16 = 0, 1
-ACT_NONE, ACT_GEGLU = 0, 1
+ACT_NONE, ACT_GEGLU, ACT_SILU = 0, 1, 2
 
 vp = C.c_void_p
 ll = C.c_longlong

@@ -137,9 +137,10 @@ class CachedControlNetModel:
         if self._owner is None:
             raise RuntimeError("register this net in an EdgeStyleMultiControlNetModel before calling forward "
                                "(the CUDA engine is built per multi-ControlNet model)")
-        if tuple(controlnet_cond.shape[2:]) != tuple(sample.shape[2:]):
-            raise NotImplementedError("raw-image conditioning (the embedder runs every step, controllora.py:199-201) "
-                                      "is row N4 of SURVEY.md 8(f); pass the cached embedding from preprocess_image")
+        if tuple(controlnet_cond.shape[2:]) != tuple(sample.shape[2:]):  # raw image: run the embedder (:199-201)
+            if self.controlnet_conditioning_channel_order == "bgr":
+                controlnet_cond = torch.flip(controlnet_cond, dims=[1])
+            controlnet_cond = self.preprocess_image(controlnet_cond)
         down, mid = self._owner._single_forward(self, sample, timestep, encoder_hidden_states, controlnet_cond,
                                                 float(conditioning_scale), guess_mode)
         if not return_dict:
@@ -149,7 +150,15 @@ class CachedControlNetModel:
     __call__ = forward
 
     def preprocess_image(self, image):
-        raise NotImplementedError("the per-call precompute stage (VAE / openpose embedder) is row N2 of SURVEY.md 8(f)")
+        """controllora.py:289-290: the conditioning embedder on a raw control image [n, 3, H, W] -> [n, 320, H/8, W/8].
+        Implemented for plain ControlNets (openpose: ControlNetConditioningEmbedding, 8 convolutions on the GEMM
+        kernel); the ControlLoRA embedder needs the VAE encoder (row N2 of SURVEY.md 8(f))."""
+        if self.uses_lora:
+            raise NotImplementedError("VAEControlNetConditioningEmbedding (VAE encoder) is row N2 of SURVEY.md 8(f)")
+        if self._owner is None:
+            raise RuntimeError("register this net in an EdgeStyleMultiControlNetModel before calling preprocess_image")
+        n, _, H, W = image.shape
+        return self._owner.engine(n, H // 8, W // 8).embed_openpose(image)
 
     # -- checkpoint format (diffusers layout: <dir>/config.json + <dir>/diffusion_pytorch_model.safetensors) ------
     def _extra_config(self) -> dict:

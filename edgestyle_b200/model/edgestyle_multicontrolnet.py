@@ -90,12 +90,24 @@ class EdgeStyleMultiControlNetModel:
         B, _, h, w = sample.shape
         eng = self.engine(B, h, w)
         eng.set_prompt(encoder_hidden_states)
-        eng.set_conditioning(controlnet_cond)
+        eng.set_conditioning(self.embed_conditioning(controlnet_cond, (h, w)))
         # guess_mode: each net scales its outputs by logspace(-1, 0, 13) * scale (controllora.py:257-265) before the merge
         down, mid = eng.residuals(sample, timestep, conditioning_scale, guess_mode=guess_mode)
         return down, mid
 
     __call__ = forward
+
+    def embed_conditioning(self, controlnet_cond: List[torch.Tensor], latent_hw) -> List[torch.Tensor]:
+        """Raw control images (spatial size != latent) go through their net's conditioning embedder
+        (controllora.py:199-201 / preprocess_image :289-290); latent-sized entries are the cached embeddings."""
+        out = []
+        for net, c in zip(self.nets, controlnet_cond):
+            if tuple(c.shape[2:]) != tuple(latent_hw):
+                if getattr(net, "controlnet_conditioning_channel_order", "rgb") == "bgr":
+                    c = torch.flip(c, dims=[1])
+                c = net.preprocess_image(c)
+            out.append(c)
+        return out
 
     def _single_forward(self, net, sample, timestep, ehs, cond, scale, guess_mode):
         B, _, h, w = sample.shape

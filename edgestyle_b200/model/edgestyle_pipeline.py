@@ -108,18 +108,22 @@ class EdgeStyleStableDiffusionControlNetPipeline:
             pe = torch.cat([self._to_dev(negative_prompt_embeds, dev), self._to_dev(prompt_embeds, dev)])  # :330
         else:
             pe = self._to_dev(prompt_embeds, dev)
+        c0 = self.unet.config.block_out_channels[0]
         conds = []
-        for c in image:
+        for net, c in zip(self.controlnet.nets, image):
             c = self._to_dev(c, dev)
+            if c.shape[1] != c0:
+                # raw control image [n, 3, 8h, 8w]: the per-call precompute of prepare_image (:629-664) -- built for
+                # the openpose nets (ControlNetConditioningEmbedding); ControlLoRA nets need the VAE encoder (N2)
+                if getattr(net, "controlnet_conditioning_channel_order", "rgb") == "bgr":
+                    c = torch.flip(c, dims=[1])
+                c = net.preprocess_image(c)
             if cfg_on and c.shape[0] == n_img:  # CFG duplication of the cached embedding (:657-658)
                 c = torch.cat([c] * 2)
             if c.shape[0] != B:
                 raise ValueError(f"conditioning embedding has {c.shape[0]} rows, expected {B}")
             conds.append(c)
         h, w = conds[0].shape[-2:]
-        if tuple(conds[0].shape[1:]) != (self.unet.config.block_out_channels[0], h, w):
-            raise NotImplementedError("raw control images need the per-call precompute stage (SURVEY.md 8(f) N2): pass the "
-                                      "cached conditioning embeddings [B, 320, h, w]")
         eng = self.controlnet.engine(B, h, w, use_graph=self.use_graph)
         eng.set_prompt(pe)
         eng.set_conditioning(conds)

@@ -23,6 +23,7 @@ extern "C" {
 
 #define ES_ACT_NONE 0
 #define ES_ACT_GEGLU 1 /* out[:, j] = v[:, j'] * gelu_erf(v[:, j' + tile/2]); weights pre-permuted per tile */
+#define ES_ACT_SILU 2  /* out = silu(alpha * (acc + bias + rowvec)) + residual (ControlNetConditioningEmbedding convs) */
 
 #define ES_MAX_SEG 4
 

@@ -345,3 +345,47 @@ def test_guess_mode_multi_and_pipeline():
     a_t, a_p = sch.coefficients(801)
     eng.cfg_ddim_update(got, float(a_t), float(a_p), 4.5)
     assert (got - want).abs().max().item() <= 2e-2
+
+
+def test_openpose_raw_image_conditioning():
+    """Raw openpose control images through the ControlNetConditioningEmbedding (8 convolutions, three of them stride 2,
+    SiLU fused in the GEMM epilogue): preprocess_image (controllora.py:289-290), the raw-image branch of
+    CachedControlNetModel.forward (:199-201) and of the multi-ControlNet forward."""
+    from edgestyle_b200 import config as C
+    from edgestyle_b200.model import (CachedControlNetModel, ControlLoRAModel, EdgeStyleMultiControlNetModel,
+                                      UNet2DConditionModel)
+    from oracle.sd15 import SD15Config
+    from oracle.step import build_models, synthetic_inputs
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    ocfg = SD15Config(block_out_channels=(64, 128, 256, 256), cross_attention_dim=96)
+    h = w = 16
+    m = build_models(ocfg, (h, w), rank=4)
+    inp = synthetic_inputs(ocfg, 1, h, w)
+    cfg = C.UNetConfig.from_any(ocfg)
+    unet = UNet2DConditionModel(cfg, m.unet.state_dict())
+    agn = ControlLoRAModel(cfg, m.lora_agnostic.state_dict(), 4, unet=unet)
+    clo = ControlLoRAModel(cfg, m.lora_clothes.state_dict(), 4, unet=unet)
+    pose = CachedControlNetModel(cfg, m.openpose.state_dict())
+    multi = EdgeStyleMultiControlNetModel([agn, pose, clo, pose, clo, pose], m.controlnet.merge_state_dict(), (h, w))
+    g = torch.Generator().manual_seed(7)
+    raw = [torch.rand(2, 3, 8 * h, 8 * w, generator=g).to(DEV) for _ in range(3)]
+    m.unet.to(DEV)
+    m.controlnet.to(DEV)
+    with torch.no_grad():
+        want_emb = [m.openpose.controlnet_cond_embedding(r) for r in raw]
+    got = pose.preprocess_image(raw[0])
+    assert got.shape == want_emb[0].shape == (2, 64, h, w)
+    assert (got - want_emb[0]).abs().max().item() <= 2e-2 * max(1.0, want_emb[0].abs().max().item())
+    # multi forward: cached embeddings for the ControlLoRA nets, raw images for the three openpose entries
+    x = torch.cat([inp.latents] * 2).to(DEV)
+    t = torch.tensor(601, device=DEV)
+    pe = inp.prompt_embeds.to(DEV)
+    conds = [c.to(DEV) for c in inp.conds]
+    mixed = [conds[0], raw[0], conds[2], raw[1], conds[4], raw[2]]
+    with torch.no_grad():
+        wd, wm = m.controlnet(x, t, pe, mixed, [1.0] * 6)
+    gd, gm = multi.forward(x, t, pe, mixed, [1.0] * 6)
+    for a, b in zip(list(gd) + [gm], list(wd) + [wm]):
+        assert (a - b).abs().max().item() <= 1e-2 * max(1.0, b.abs().max().item())
