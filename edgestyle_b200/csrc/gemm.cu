@@ -380,15 +380,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) o[j] = 0.f;
-          for (int sp = 0; sp < p.splits; ++sp) {
-            const float4* wp = reinterpret_cast<const float4*>(p.ws_partial) +
-                               (static_cast<long long>(sp) * tiles + tile_id) * (kBlockM * BLOCK_N / 4) +
-                               static_cast<long long>(c / 4) * kBlockM + r;
+          // three partial tiles in flight per round trip to L2 (the loop was one dependent round trip per split);
+          // the summation order stays split 0, 1, 2, ... -> bit-identical, deterministic results
+          const long long sstride = tiles * (kBlockM * BLOCK_N / 4);
+          const float4* wp0 = reinterpret_cast<const float4*>(p.ws_partial) +
+                              static_cast<long long>(tile_id) * (kBlockM * BLOCK_N / 4) +
+                              static_cast<long long>(c / 4) * kBlockM + r;
+          for (int sp = 0; sp < p.splits; sp += 3) {
+            float4 f[3][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 f = __ldcg(wp + j * kBlockM);
-              o[4 * j] += f.x; o[4 * j + 1] += f.y; o[4 * j + 2] += f.z; o[4 * j + 3] += f.w;
+            for (int u = 0; u < 3; ++u) {
+              const float4* wp = wp0 + static_cast<long long>(sp + u) * sstride;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                f[u][j] = (sp + u < p.splits) ? __ldcg(wp + j * kBlockM) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                o[4 * j] += f[u][j].x; o[4 * j + 1] += f[u][j].y; o[4 * j + 2] += f[u][j].z; o[4 * j + 3] += f[u][j].w;
+              }
           }
         }
       };
