@@ -63,6 +63,7 @@ struct GemmKParams {
   int* ws_counter;       // [tiles] arrival counters (zero on entry, reset by the finishing CTA)
   float* gn_ws;          // optional: GroupNorm statistics of the OUTPUT accumulated here, [img][groups][2] (sum, sumsq)
   int gn_cpg, gn_groups; // channels per group, groups
+  int gn_col0;           // channel of the normalised tensor that column 0 of this GEMM writes (concat halves)
   int b_blocked;         // weights stored K-block-major: [tap*kblocks + cb][n][64] (contiguous 128 B x BLOCK_N tiles)
   int tma_epi;           // 1: epilogue goes regs -> swizzled smem panels -> TMA store (residual via TMA load)
   int n_out;             // output columns in total (N, or N/2 for GEGLU)
@@ -653,7 +654,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
           const int img_w = __shfl_sync(0xffffffffu, img, 0);
           const int img_t0 = p.flat ? (p.rows_per_img > 0 ? x0 / p.rows_per_img : 0) : i0;
-          const int g_t0 = n0 / p.gn_cpg;
+          const int g_t0 = (p.gn_col0 + n0) / p.gn_cpg;
           const int cc = lane;  // 8-column chunk of the tile row owned by this lane
           const int col0 = n0 + cc * 8;
           if (cc < n_tile_out / 8 && okmask != 0 && col0 < p.N && img_w - img_t0 < 4) {
@@ -679,8 +680,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
             const int nval = min(8, p.N - col0);
-            const int g0 = col0 / p.gn_cpg;
-            const int bnd = (g0 + 1) * p.gn_cpg - col0;  // columns [0, bnd) belong to g0, the rest to g0 + 1
+            const int g0 = (p.gn_col0 + col0) / p.gn_cpg;
+            const int bnd = (g0 + 1) * p.gn_cpg - (p.gn_col0 + col0);  // columns [0, bnd) belong to g0, the rest to g0 + 1
             float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -861,6 +862,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
       kp.tma_epi = 1;
     }
   }
+  if (g->gn_ws && (g->gn_cpg > 0 || g->gn_col0 != 0))
+    ES_CHECK(kp.tma_epi, "es_gemm: GroupNorm statistics of a column slice need a 16-bit, 16-byte aligned output");
   if (g->ln_rowstat || g->rowstat_out) {
     // the folded-LayerNorm epilogues exist on the smem/TMA path only
     ES_CHECK(kp.tma_epi, "es_gemm: folded LayerNorm needs a 16-bit, 16-byte aligned output");
@@ -1061,9 +1064,16 @@ static int gemm_dispatch(const EsGemm* g, cudaStream_t stream) {
   if (g->ln_rowstat) ES_CHECK(g->ln_colsum && g->ln_features > 0 && !g->rowvec, "es_gemm: bad folded-LayerNorm config");
   kp.gn_ws = g->gn_ws;
   kp.gn_groups = g->gn_groups;
-  kp.gn_cpg = g->gn_groups > 0 ? g->n / g->gn_groups : 0;
+  kp.gn_cpg = g->gn_cpg > 0 ? g->gn_cpg : (g->gn_groups > 0 ? g->n / g->gn_groups : 0);
+  kp.gn_col0 = g->gn_col0;
   if (g->gn_ws) {
-    ES_CHECK(g->gn_groups > 0 && g->n % g->gn_groups == 0 && g->act == ES_ACT_NONE, "es_gemm: bad fused-GroupNorm config");
+    ES_CHECK(g->gn_groups > 0 && g->act == ES_ACT_NONE, "es_gemm: bad fused-GroupNorm config");
+    if (g->gn_cpg > 0 || g->gn_col0 != 0)  // this GEMM writes a column slice of the normalised tensor (concat half)
+      ES_CHECK(g->gn_cpg >= 8 && g->gn_col0 >= 0 && (g->gn_col0 + g->n + g->gn_cpg - 1) / g->gn_cpg <= g->gn_groups,
+               "es_gemm: bad GroupNorm slice (cpg %d, first channel %d, n %d, groups %d)", g->gn_cpg, g->gn_col0, g->n,
+               g->gn_groups);
+    else
+      ES_CHECK(g->n % g->gn_groups == 0, "es_gemm: n %% gn_groups != 0");
     // a warp's 32 tile rows must belong to one image
     const long long rpi = flat ? g->rows_per_img : static_cast<long long>(g->w) * g->h;
     ES_CHECK(rpi > 0 && rpi % 32 == 0, "es_gemm: fused GroupNorm statistics need rows-per-image %% 32 == 0 (got %lld)", rpi);

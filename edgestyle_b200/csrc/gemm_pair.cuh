@@ -581,7 +581,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // GroupNorm statistics of the finished tile from the smem panels: one 8-column chunk per lane over the
         // warp's 32 rows, reduced in smem, one global atomic per (image, group, statistic)
         const int img_t0 = p.flat ? (p.rows_per_img > 0 ? x0 / p.rows_per_img : 0) : i0;
-        const int g_t0 = n0 / p.gn_cpg;
+        const int g_t0 = (p.gn_col0 + n0) / p.gn_cpg;
         if (!skip) {
           const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
           const int img_w = __shfl_sync(0xffffffffu, img, 0);
@@ -607,8 +607,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
             const int nval = min(8, p.N - col0);
-            const int g0 = col0 / p.gn_cpg;
-            const int bnd = (g0 + 1) * p.gn_cpg - col0;
+            const int g0 = (p.gn_col0 + col0) / p.gn_cpg;
+            const int bnd = (g0 + 1) * p.gn_cpg - (p.gn_col0 + col0);
             float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j)

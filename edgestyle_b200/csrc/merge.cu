@@ -26,6 +26,8 @@ struct MergeK {
   long long lds;
   void* dst;
   long long ldd;
+  float* gn_ws;
+  int gn_groups, gn_cpg, gn_col0;
 };
 
 __device__ __forceinline__ void block_reduce2_to_global(float a, float b, double* dst) {
@@ -149,6 +151,16 @@ __global__ void merge_kernel(const MergeK k) {
       w3[j] = k.w3[ch + j];
       b3[j] = k.b3[ch + j];
     }
+    // optional GroupNorm statistics of the written rows (this thread's 8 channels touch at most two groups)
+    __shared__ float gstat[66][2];
+    const int g_lo = k.gn_ws ? (k.gn_col0 + ch) / k.gn_cpg : 0;
+    const int g_split = k.gn_ws ? (g_lo + 1) * k.gn_cpg - (k.gn_col0 + ch) : 8;  // channels [0, g_split) -> g_lo
+    const int g_base = k.gn_ws ? k.gn_col0 / k.gn_cpg : 0;
+    float gs0 = 0.f, gq0 = 0.f, gs1 = 0.f, gq1 = 0.f;
+    if (k.gn_ws) {
+      for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 66 * 2; i += blockDim.x * blockDim.y) (&gstat[0][0])[i] = 0.f;
+      __syncthreads();
+    }
     for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
       const long long off = img_off + static_cast<long long>(p) * C + ch;
       const float4 z0 = reinterpret_cast<const float4*>(k.z + off)[0];
@@ -168,10 +180,31 @@ __global__ void merge_kernel(const MergeK k) {
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = sk[j] + w3[j] * silu_f((zz[j] - mu2) * r2 * g[j] + be[j]) + b3[j];
+      if (k.gn_ws) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = Cvt<T>::to_f(Cvt<T>::from_f(o[j]));  // the rounded value the consumer will read
+          if (j < g_split) { gs0 += v; gq0 += v * v; }
+          else { gs1 += v; gq1 += v * v; }
+        }
+      }
       uint4 u;
       u.x = Cvt<T>::pack2(o[0], o[1]); u.y = Cvt<T>::pack2(o[2], o[3]);
       u.z = Cvt<T>::pack2(o[4], o[5]); u.w = Cvt<T>::pack2(o[6], o[7]);
       *reinterpret_cast<uint4*>(reinterpret_cast<T*>(k.dst) + row * k.ldd + ch) = u;
+    }
+    if (k.gn_ws) {
+      atomicAdd(&gstat[g_lo - g_base][0], gs0);
+      atomicAdd(&gstat[g_lo - g_base][1], gq0);
+      if (g_split < 8) {
+        atomicAdd(&gstat[g_lo - g_base + 1][0], gs1);
+        atomicAdd(&gstat[g_lo - g_base + 1][1], gq1);
+      }
+      __syncthreads();
+      for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 66 * 2; i += blockDim.x * blockDim.y) {
+        const float v = (&gstat[0][0])[i];
+        if (v != 0.f) atomicAdd(k.gn_ws + (static_cast<long long>(b) * k.gn_groups + g_base + (i >> 1)) * 2 + (i & 1), v);
+      }
     }
   }
 }
@@ -187,6 +220,8 @@ static int merge_t(const EsMerge* m, int phase, cudaStream_t s) {
   k.w1 = m->w1; k.b1 = m->b1; k.w2 = m->w2; k.b2 = m->b2; k.w3 = m->w3; k.b3 = m->b3;
   k.g1 = m->g1; k.be1 = m->be1; k.g2 = m->g2; k.be2 = m->be2;
   k.stats = m->stats; k.z = m->z; k.skip = m->skip; k.lds = m->lds; k.dst = m->dst; k.ldd = m->ldd;
+  k.gn_ws = phase == 3 ? m->gn_ws : nullptr;
+  k.gn_groups = m->gn_groups; k.gn_cpg = m->gn_cpg; k.gn_col0 = m->gn_col0;
   const int vpp = m->C / 8;
   int ny = 256 / vpp;
   if (ny < 1) ny = 1;
@@ -210,6 +245,10 @@ extern "C" int es_merge_phase(const EsMerge* m, int phase, void* stream) {
   ES_CHECK(m && phase >= 1 && phase <= 3, "es_merge_phase: bad arguments");
   ES_CHECK(m->C % 8 == 0 && m->C / 8 <= 1024 && m->stats && m->z, "es_merge_phase: bad shape/workspace");
   if (phase == 3) ES_CHECK(m->dst && m->ldd % 8 == 0 && (!m->skip || m->lds % 8 == 0), "es_merge_phase: bad dst");
+  if (phase == 3 && m->gn_ws)
+    ES_CHECK(m->gn_cpg >= 8 && m->gn_col0 >= 0 && m->gn_groups > 0 && m->C / m->gn_cpg + 2 <= 66 &&
+                 (m->gn_col0 + m->C + m->gn_cpg - 1) / m->gn_cpg <= m->gn_groups,
+             "es_merge_phase: bad GroupNorm slice");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   return m->dtype == ES_DTYPE_BF16 ? es::merge_t<__nv_bfloat16>(m, phase, s) : es::merge_t<__half>(m, phase, s);
 }

@@ -331,6 +331,7 @@ class DenoiseEngine:
         self.merge_mode = int(os.environ.get("ES_MERGE_EARLY", "0"))
         self.merge_early = self.merge_mode != 0
         self._stats_of = {}
+        self._cat_slot = {}
         self._kv_recompute = False  # True: redo the text K/V projections inside every step (reference behaviour)
         self._temb_ready = None     # event of the base pass's time path while it is pending on the side stream
         self.launches_per_step = 0
@@ -594,6 +595,7 @@ class DenoiseEngine:
 
     def _begin_step_scratch(self):
         self._stats_of = {}
+        self._cat_slot = {}
         self.scratch.zero_()
         self._gn_next = 0
         self._merge_next = 0
@@ -630,6 +632,30 @@ class DenoiseEngine:
         ws = self._gn_slot(imgs)
         self._stats_of[(out.data_ptr(), out.shape[0], out.shape[1])] = ws
         return ws
+
+    def _gn_kw(self, out, imgs, hw) -> dict:
+        """GroupNorm-statistics arguments for the GEMM that produces `out`: a dense tensor gets its own slot; the
+        x half of a registered decoder concat buffer accumulates into the concat's slot (EsGemm.gn_cpg / gn_col0)."""
+        G = self.cfg.norm_num_groups
+        if out.stride(0) != out.shape[1]:
+            reg = self._cat_slot.get(out.data_ptr())
+            if reg is None:
+                return {}
+            ws, cpg = reg
+            return dict(gn_ws=ws, gn_groups=G, gn_cpg=cpg, gn_col0=0)
+        return dict(gn_ws=self._stats_for(out, imgs, hw), gn_groups=G)
+
+    def _register_cat(self, cbuf, imgs, hw) -> bool:
+        """Decoder [x | skip] concat buffer: both halves are written by kernels that can accumulate the GroupNorm
+        statistics of the first resnet norm (GEMM epilogue for x, merge phase 3 for skip) -> no statistics pass."""
+        G = self.cfg.norm_num_groups
+        C = cbuf.shape[1]
+        if not self.fuse_gn_stats or hw % 32 != 0 or C % G or (C // G) < 8 or (C // G) % 2:
+            return False
+        ws = self._gn_slot(imgs)
+        self._stats_of[(cbuf.data_ptr(), cbuf.shape[0], C)] = ws
+        self._cat_slot[cbuf.data_ptr()] = (ws, C // G)
+        return True
 
     def _gn(self, x, out, g, b, imgs, hw, silu, eps=None):
         G = self.cfg.norm_num_groups
@@ -685,13 +711,11 @@ class DenoiseEngine:
                  gn_ws=self._stats_for(hbuf, imgs, H * W), gn_groups=G)
         g2 = self.buf(f"{tag}.gn2", M, R.cout)
         self._gn(hbuf, g2, R.n2g, R.n2b, imgs, H * W, True)
-        ows = self._stats_for(out, imgs, H * W)
+        okw = self._gn_kw(out, imgs, H * W)
         if R.wsc is not None:
-            ops.gemm(g2, R.w2, R.cout, out=out, taps=9, whn=(W, H, imgs), bias=R.b2, a2=x, b2=R.wsc, c1=R.cout,
-                     gn_ws=ows, gn_groups=G)
+            ops.gemm(g2, R.w2, R.cout, out=out, taps=9, whn=(W, H, imgs), bias=R.b2, a2=x, b2=R.wsc, c1=R.cout, **okw)
         else:
-            ops.gemm(g2, R.w2, R.cout, out=out, taps=9, whn=(W, H, imgs), bias=R.b2, residual=x, c1=R.cout,
-                     gn_ws=ows, gn_groups=G)
+            ops.gemm(g2, R.w2, R.cout, out=out, taps=9, whn=(W, H, imgs), bias=R.b2, residual=x, c1=R.cout, **okw)
         return out
 
     def _transformer(self, T: Tfm, x, imgs, H, W, ctx, out, tag, seg):
@@ -730,8 +754,7 @@ class DenoiseEngine:
         u = self.buf(f"{tag}.ff", M, 4 * c)
         self._lin(T.ff1, ln, u, hw, seg, tag + ".o", ln_stat=st[2], act=ACT_GEGLU)
         self._lin(T.ff2, u, hcur, hw, seg, tag + ".ff2", residual=hcur)
-        self._lin(T.proj_out, hcur, out, hw, None, tag, residual=x,
-                  gn_ws=self._stats_for(out, imgs, hw), gn_groups=self.cfg.norm_num_groups)
+        self._lin(T.proj_out, hcur, out, hw, None, tag, residual=x, **self._gn_kw(out, imgs, hw))
         return out
 
     def _time_path(self, E: EncoderW, groups: Sequence[Tuple[int, int]], tag: str, ncols: Sequence[int], out=None):
@@ -917,6 +940,13 @@ class DenoiseEngine:
                 x_ch = rev[i]
                 sidx -= 1
         cat_of_skip = {v[2]: (v[0], v[1]) for v in cats.values()}
+        # GroupNorm statistics of the concat inputs come from their two producers (no statistics pass in the decoder)
+        cat_gn = {}
+        if mode == "step" and not zero_uncond and os.environ.get("ES_CAT_GN", "1") != "0":
+            for (i, j), (cbuf, xc, sidx_ij) in cats.items():
+                H, W = self.levels[len(boc) - 1 - i]
+                if self._register_cat(cbuf, B, H * W):
+                    cat_gn[sidx_ij] = (self._cat_slot[cbuf.data_ptr()], xc)
         # -- zero convs (controllora.py:240-254) + EdgeStyle merge (edgestyle_multicontrolnet.py:160-169), on the side
         #    stream in the order the decoder consumes them (mid, then skips 11..0): the large 64x64-level merges
         #    overlap the decoder's deep levels; the decoder waits on one event per level
@@ -983,8 +1013,16 @@ class DenoiseEngine:
                     dst, skip = cbuf[:, xc:], unet_rows
                 else:  # mid: becomes the x half of the first decoder concat
                     dst, skip = cats[(0, 0)][0][:, :c], unet_rows
+                gn = None
+                G = cfg.norm_num_groups
+                if mode == "step" and li < len(self.res_shapes) - 1 and li in cat_gn:
+                    (ws_c, cpg_c), xc_c = cat_gn[li]          # skip half of the concat that consumes level li
+                    gn = (ws_c, G, cpg_c, xc_c)
+                elif mode == "step" and li == len(self.res_shapes) - 1 and cats[(0, 0)][0].data_ptr() in self._cat_slot:
+                    ws_c, cpg_c = self._cat_slot[cats[(0, 0)][0].data_ptr()]  # merged mid = x half of the first concat
+                    gn = (ws_c, G, cpg_c, 0)
                 ops.merge(res, [sc * level_gain[li] for sc in scale], self.merge[li], self._merge_slot(), z, B, H * W, c,
-                          dst, skip=skip, zero_stats=False)
+                          dst, skip=skip, zero_stats=False, gn=gn)
                 if zero_uncond:
                     nu = (B // 2) * H * W  # rows of the unconditional images (negative prompt rows come first)
                     if skip is not None:
@@ -1026,8 +1064,9 @@ class DenoiseEngine:
                 assert (Hn, Wn) == (2 * H, 2 * W), "odd latent sizes are not supported by the x2 upsample path"
                 up = self.buf(f"dec{i}.up", B * Hn * Wn, cout)
                 ops.upsample2x(self.buf(f"dec{i}.out", M, cout), up, B, H, W)
-                ops.gemm(up, self.up_conv[i][0], cout, out=cats[(i + 1, 0)][0][:, :cout], taps=9, whn=(Wn, Hn, B),
-                         bias=self.up_conv[i][1], c1=cout)
+                up_out = cats[(i + 1, 0)][0][:, :cout]
+                ops.gemm(up, self.up_conv[i][0], cout, out=up_out, taps=9, whn=(Wn, Hn, B),
+                         bias=self.up_conv[i][1], c1=cout, **self._gn_kw(up_out, B, Hn * Wn))
         # -- conv_norm_out + SiLU + conv_out
         fin = self.buf("dec.final", B * hw, c0)
         g = self.buf("dec.gn_out", B * hw, c0)

@@ -27,7 +27,7 @@ class EsGemm(C.Structure):
         ("seg_b2_noff", C.c_int * ES_MAX_SEG), ("bias", vp), ("rowvec", vp), ("rows_per_img", C.c_int),
         ("rowvec_ld", C.c_int), ("residual", vp), ("ldr", ll), ("act", C.c_int), ("alpha", C.c_float),
         ("out", vp), ("ldc", ll), ("out_fp32", C.c_int), ("block_n", C.c_int), ("stages", C.c_int),
-        ("split_k", C.c_int), ("b_blocked", C.c_int), ("gn_ws", vp), ("gn_groups", C.c_int), ("rowstat_out", vp), ("ln_rowstat", vp), ("ln_colsum", vp),
+        ("split_k", C.c_int), ("b_blocked", C.c_int), ("gn_ws", vp), ("gn_groups", C.c_int), ("gn_cpg", C.c_int), ("gn_col0", C.c_int), ("rowstat_out", vp), ("ln_rowstat", vp), ("ln_colsum", vp),
         ("ln_features", C.c_int), ("ln_eps", C.c_float), ("prefetch", vp), ("prefetch_bytes", ll), ("workspace", vp),
         ("workspace_bytes", ll),
     ]
@@ -54,7 +54,7 @@ class EsMerge(C.Structure):
         ("dtype", C.c_int), ("res", vp * 6), ("scale", C.c_float * 6), ("B", C.c_int), ("hw", C.c_int),
         ("C", C.c_int), ("w1", vp), ("b1", vp), ("w2", vp), ("b2", vp), ("w3", vp), ("b3", vp), ("g1", vp),
         ("be1", vp), ("g2", vp), ("be2", vp), ("stats", vp), ("z", vp), ("skip", vp), ("lds", ll), ("dst", vp),
-        ("ldd", ll),
+        ("ldd", ll), ("gn_ws", vp), ("gn_groups", C.c_int), ("gn_cpg", C.c_int), ("gn_col0", C.c_int),
     ]
 
 

@@ -195,7 +195,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: i
          a2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None, segs=None, block_n: int = 0,
          c1: Optional[int] = None, stages: int = 0, split_k: int = 0, workspace: Optional[torch.Tensor] = None,
          gn_ws: Optional[torch.Tensor] = None, gn_groups: int = 0, b_blocked: bool = False,
-         rowstat_out: Optional[torch.Tensor] = None, ln=None):
+         rowstat_out: Optional[torch.Tensor] = None, ln=None, gn_cpg: int = 0, gn_col0: int = 0):
     """out[m, :n] = epilogue(A (*) B^T).  a: [M, >=c1] (pitch = a.stride(0)); b: [n_total, taps*c1].
 
     rowstat_out: fp32 [M, 2] (zeroed by the caller) accumulating per-row (sum, sumsq) of the output.
@@ -272,7 +272,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: i
                 gemm(a, b, n, out=sk_out, taps=taps, whn=whn, bias=bias, rowvec=rowvec, rows_per_img=rows_per_img,
                      residual=residual, act=act, alpha=alpha, a2=a2, b2=b2, segs=segs, block_n=bn, c1=c1, stages=0,
                      split_k=sk, workspace=workspace, gn_ws=sk_gn, gn_groups=gn_groups, b_blocked=b_blocked,
-                     rowstat_out=sk_rs, ln=ln)
+                     rowstat_out=sk_rs, ln=ln, gn_cpg=gn_cpg, gn_col0=gn_col0)
 
             hit = TUNER.tune(key, run, M, n, kb_total, act, block_n)
         block_n, split_k = hit[0], hit[1]
@@ -286,6 +286,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: i
     if gn_ws is not None:
         g.gn_ws = gn_ws.data_ptr()
         g.gn_groups = gn_groups
+        g.gn_cpg, g.gn_col0 = gn_cpg, gn_col0  # non-zero: `out` is a column slice of the tensor the GroupNorm covers
     if PREFETCH.mode is not None:
         nxt = PREFETCH.step(_stream(), b.data_ptr(), b.numel() * b.element_size())
         if nxt is not None:
@@ -365,8 +366,11 @@ def layernorm(x, out, gamma, beta, eps: float = 1e-5):
 
 
 def merge(res: Sequence[torch.Tensor], scale: Sequence[float], prm: dict, stats, z, B: int, hw: int, Cc: int, dst,
-          skip=None, zero_stats: bool = True):
-    """EdgeStyle ControlNetBlock over six [B*hw, C] residual slabs; dst = skip + block(res)."""
+          skip=None, zero_stats: bool = True, gn=None):
+    """EdgeStyle ControlNetBlock over six [B*hw, C] residual slabs; dst = skip + block(res).
+
+    gn = (ws [B, groups, 2] fp32, groups, channels per group, first channel): also accumulate the GroupNorm statistics
+    of the rows written to dst, which is a column slice of the tensor the consumer normalises."""
     m = EsMerge()
     m.dtype = _dt(res[0])
     for i in range(6):
@@ -379,6 +383,9 @@ def merge(res: Sequence[torch.Tensor], scale: Sequence[float], prm: dict, stats,
     if skip is not None:
         m.skip, m.lds = skip.data_ptr(), skip.stride(0)
     m.dst, m.ldd = dst.data_ptr(), dst.stride(0)
+    if gn is not None:
+        gws, m.gn_groups, m.gn_cpg, m.gn_col0 = gn
+        m.gn_ws = gws.data_ptr()
     if zero_stats:
         stats.zero_()
     lib = load()

@@ -90,6 +90,9 @@ typedef struct EsGemm {
                    by the caller) so the consuming GroupNorm skips its statistics pass; needs rows-per-image % 32 == 0
                    (flat mode: rows_per_img must be set) */
   int gn_groups;
+  int gn_cpg;  /* 0: n / gn_groups.  > 0: this GEMM writes a column SLICE of the normalised tensor (one half of an
+                  [x | skip] concat): channels per group of the whole tensor ... */
+  int gn_col0; /* ... and the channel of that tensor its column 0 lands on; gn_groups = groups of the whole tensor */
   /* LayerNorm folded around the GEMM (BasicTransformerBlock norm1/2/3 never touch memory):
    *   producer: rowstat_out [M][2] fp32 (zeroed by the caller) receives per-row (sum, sumsq) of THIS GEMM's output
    *             (after bias / residual), accumulated over its column tiles;
@@ -186,6 +189,11 @@ typedef struct EsMerge {
   long long lds;
   void* dst;
   long long ldd;
+  /* optional (phase 3): accumulate GroupNorm statistics of what is written to dst, for a consumer that normalises the
+   * tensor dst is a column slice of: ws [B][gn_groups][2] (sum, sumsq; zeroed by the caller), channels per group of the
+   * whole tensor, channel of that tensor column 0 of dst lands on */
+  float* gn_ws;
+  int gn_groups, gn_cpg, gn_col0;
 } EsMerge;
 int es_merge_phase(const EsMerge* m, int phase, void* stream);
 
