@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libedgestyle_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "gemm.cu", "attention.cu", "norm.cu", "merge.cu", "elementwise.cu"]
+SOURCES = ["api.cu", "gemm.cu", "attention.cu", "norm.cu", "merge.cu", "elementwise.cu", "vae.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--use_fast_math",

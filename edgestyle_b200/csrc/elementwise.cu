@@ -43,11 +43,11 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, long long lds, fl
   }
 }
 
-// ---------------------------------------------------------------- im2col 3x3 pad 1 stride s
+// ---------------------------------------------------------------- im2col 3x3, stride s, `pad` zero rows/columns before the image
 // out[(n, yo, xo)][tap*c + ch]; one thread per (row, tap, 8-channel vector) when c % 8 == 0, scalar otherwise.
 template <typename T>
 __global__ void im2col3x3_kernel(const T* __restrict__ src, long long lds, T* __restrict__ dst, long long ldo, int n,
-                                 int h, int w, int c, int stride, int ho, int wo) {
+                                 int h, int w, int c, int stride, int pad, int ho, int wo) {
   pdl_launch_dependents();
   pdl_wait();  // PDL: inputs are produced by the preceding kernel
   const long long rows = static_cast<long long>(n) * ho * wo;
@@ -61,7 +61,7 @@ __global__ void im2col3x3_kernel(const T* __restrict__ src, long long lds, T* __
       const long long row = i / (9 * vpt);
       const int xo = static_cast<int>(row % wo), yo = static_cast<int>((row / wo) % ho);
       const int img = static_cast<int>(row / (static_cast<long long>(wo) * ho));
-      const int y = yo * stride + tap / 3 - 1, x = xo * stride + tap % 3 - 1;
+      const int y = yo * stride + tap / 3 - pad, x = xo * stride + tap % 3 - pad;
       uint4 val = make_uint4(0, 0, 0, 0);
       if (y >= 0 && y < h && x >= 0 && x < w)
         val = *reinterpret_cast<const uint4*>(src + ((static_cast<long long>(img) * h + y) * w + x) * lds + v * 8);
@@ -78,7 +78,7 @@ __global__ void im2col3x3_kernel(const T* __restrict__ src, long long lds, T* __
         const int tap = col / c, ch = col % c;
         const int xo = static_cast<int>(row % wo), yo = static_cast<int>((row / wo) % ho);
         const int img = static_cast<int>(row / (static_cast<long long>(wo) * ho));
-        const int y = yo * stride + tap / 3 - 1, x = xo * stride + tap % 3 - 1;
+        const int y = yo * stride + tap / 3 - pad, x = xo * stride + tap % 3 - pad;
         if (y >= 0 && y < h && x >= 0 && x < w) val = src[((static_cast<long long>(img) * h + y) * w + x) * lds + ch];
       }
       dst[i] = val;
@@ -302,23 +302,33 @@ extern "C" int es_nhwc_to_nchw(int dtype, const void* src, long long lds, float*
   ES_CUDA(cudaGetLastError());
   return 0;
 }
-extern "C" int es_im2col3x3(int dtype, const void* src, long long lds, void* dst, long long ldo, int n, int h, int w,
-                            int c, int stride, void* stream) {
+static int im2col3x3_launch(int dtype, const void* src, long long lds, void* dst, long long ldo, int n, int h, int w,
+                            int c, int stride, int pad_lo, int pad_hi, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   ES_CHECK(stride == 1 || stride == 2, "es_im2col3x3: stride must be 1 or 2");
+  ES_CHECK(pad_lo >= 0 && pad_lo <= 1 && pad_hi >= 0 && pad_hi <= 1, "es_im2col3x3: padding must be 0 or 1 per side");
+  ES_CHECK(h + pad_lo + pad_hi >= 3 && w + pad_lo + pad_hi >= 3, "es_im2col3x3: image smaller than the window");
   ES_CHECK(ldo >= 9ll * c, "es_im2col3x3: ldo too small");
   if (c % 8 == 0) ES_CHECK(lds % 8 == 0 && ldo == 9ll * c, "es_im2col3x3: vector path needs lds%%8==0 and ldo==9c");
-  const int ho = (h + 2 - 3) / stride + 1, wo = (w + 2 - 3) / stride + 1;
+  const int ho = (h + pad_lo + pad_hi - 3) / stride + 1, wo = (w + pad_lo + pad_hi - 3) / stride + 1;
   const long long total = static_cast<long long>(n) * ho * wo * ((c % 8 == 0) ? 9 * (c / 8) : ldo);
   const int g = grid_for(total, 256);
   if (dtype == ES_DTYPE_BF16)
     ES_CUDA(launch_kernel(im2col3x3_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, s, reinterpret_cast<const __nv_bfloat16*>(src), lds,
-                                                      reinterpret_cast<__nv_bfloat16*>(dst), ldo, n, h, w, c, stride, ho, wo));
+                                                      reinterpret_cast<__nv_bfloat16*>(dst), ldo, n, h, w, c, stride, pad_lo, ho, wo));
   else
     ES_CUDA(launch_kernel(im2col3x3_kernel<__half>, dim3(g), dim3(256), 0, s, reinterpret_cast<const __half*>(src), lds, reinterpret_cast<__half*>(dst),
-                                               ldo, n, h, w, c, stride, ho, wo));
+                                               ldo, n, h, w, c, stride, pad_lo, ho, wo));
   ES_CUDA(cudaGetLastError());
   return 0;
+}
+extern "C" int es_im2col3x3(int dtype, const void* src, long long lds, void* dst, long long ldo, int n, int h, int w,
+                            int c, int stride, void* stream) {
+  return im2col3x3_launch(dtype, src, lds, dst, ldo, n, h, w, c, stride, 1, 1, stream);
+}
+extern "C" int es_im2col3x3_pad(int dtype, const void* src, long long lds, void* dst, long long ldo, int n, int h,
+                                int w, int c, int stride, int pad_lo, int pad_hi, void* stream) {
+  return im2col3x3_launch(dtype, src, lds, dst, ldo, n, h, w, c, stride, pad_lo, pad_hi, stream);
 }
 extern "C" int es_upsample2x(int dtype, const void* src, long long lds, void* dst, long long ldd, int n, int h, int w,
                              int c, void* stream) {

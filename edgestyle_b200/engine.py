@@ -1233,6 +1233,26 @@ class DenoiseEngine:
         return dst
 
     @torch.no_grad()
+    def embed_vae_latent(self, z: torch.Tensor) -> torch.Tensor:
+        """Tail of VAEControlNetConditioningEmbedding.forward (controllora.py:40-41): `conv_vae_out(z)` where z is the
+        scaled VAE latent [n, 4, h, w] fp32 NCHW.  `conv_vae_out` IS the net's `conv_in` module (:36), whose parameters
+        `tie_weights` points at the UNet's conv_in (:624), so this runs the UNet conv_in weights (SURVEY.md appendix,
+        quirk 1) -> [n, c0, h, w] fp32 NCHW.  Once per pipeline call, not per step."""
+        cfg = self.cfg
+        n, c, h, w = z.shape
+        assert c == cfg.in_channels, (c, cfg.in_channels)
+        c0 = cfg.block_out_channels[0]
+        s16 = self.buf(f"vemb.in.{n}x{h}x{w}", n * h * w, 8)
+        ops.nchw_to_nhwc(z.to(device=self.dev, dtype=torch.float32).contiguous(), s16)
+        col = self.buf(f"vemb.col.{n}x{h}x{w}", n * h * w, 64)
+        ops.im2col3x3(s16, col, n, h, w, cfg.in_channels, 1)
+        out = self.buf(f"vemb.out.{n}x{h}x{w}", n * h * w, c0)
+        ops.gemm(col, self.enc_base.conv_in, c0, out=out, bias=self.enc_base.conv_in_b)
+        dst = torch.empty(n, c0, h, w, device=self.dev, dtype=torch.float32)
+        ops.nhwc_to_nchw(out, dst)
+        return dst
+
+    @torch.no_grad()
     def cfg_ddim_update(self, latents: torch.Tensor, a_t: float, a_prev: float, guidance=None):
         """CFG combine (edgestyle_pipeline.py:513-517) + DDIM update (:520-522) on eps_out, in place on `latents`."""
         import math

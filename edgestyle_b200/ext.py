@@ -75,6 +75,10 @@ EXPORTS = {
     "es_nchw_to_nhwc": (C.c_int, [C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, ll, vp]),
     "es_nhwc_to_nchw": (C.c_int, [C.c_int, vp, ll, vp, C.c_int, C.c_int, C.c_int, vp]),
     "es_im2col3x3": (C.c_int, [C.c_int, vp, ll, vp, ll, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "es_im2col3x3_pad": (C.c_int, [C.c_int, vp, ll, vp, ll, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, vp]),
+    "es_softmax_rows": (C.c_int, [C.c_int, vp, ll, vp, ll, C.c_int, C.c_int, C.c_float, vp]),
+    "es_gaussian_sample": (C.c_int, [vp, ll, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp]),
     "es_upsample2x": (C.c_int, [C.c_int, vp, ll, vp, ll, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "es_add": (C.c_int, [C.c_int, vp, ll, vp, ll, vp, ll, C.c_int, C.c_int, vp]),
     "es_cfg_ddim": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]),

@@ -149,16 +149,31 @@ class CachedControlNetModel:
 
     __call__ = forward
 
-    def preprocess_image(self, image):
+    def preprocess_image(self, image, repeats: int = 1, noise=None, generator=None):
         """controllora.py:289-290: the conditioning embedder on a raw control image [n, 3, H, W] -> [n, 320, H/8, W/8].
-        Implemented for plain ControlNets (openpose: ControlNetConditioningEmbedding, 8 convolutions on the GEMM
-        kernel); the ControlLoRA embedder needs the VAE encoder (row N2 of SURVEY.md 8(f))."""
-        if self.uses_lora:
-            raise NotImplementedError("VAEControlNetConditioningEmbedding (VAE encoder) is row N2 of SURVEY.md 8(f)")
+
+        Plain ControlNets (openpose): ControlNetConditioningEmbedding, 8 convolutions on the GEMM kernel.
+        ControlLoRA nets: VAEControlNetConditioningEmbedding (:38-42) = `conv_vae_out(vae.encode(image).latent_dist
+        .sample() * scaling_factor)` on `edgestyle_b200.vae.AutoencoderKL` (set with `set_autoencoder`, :634).
+        `repeats` > 1 draws that many independent samples per image from ONE encoder pass (rows ordered like
+        `torch.cat([image] * repeats)`): the reference duplicates the image for CFG before embedding it
+        (edgestyle_pipeline.py:657-662), so its two CFG rows carry independently sampled embeddings.
+        `noise` ([repeats * n, 4, H/8, W/8]) replaces the RNG draw (parity tests); the openpose path ignores both."""
         if self._owner is None:
             raise RuntimeError("register this net in an EdgeStyleMultiControlNetModel before calling preprocess_image")
         n, _, H, W = image.shape
-        return self._owner.engine(n, H // 8, W // 8).embed_openpose(image)
+        if not self.uses_lora:
+            emb = self._owner.engine(n, H // 8, W // 8).embed_openpose(image)
+            return torch.cat([emb] * repeats) if repeats > 1 else emb
+        vae = getattr(self, "autoencoder", None)
+        if vae is None:
+            raise RuntimeError("ControlLoRAModel.preprocess_image needs the VAE: call set_autoencoder(vae) first "
+                               "(controllora.py:634; app.py passes vae= to from_pretrained)")
+        dist = vae.encode(image).latent_dist
+        if repeats > 1:
+            dist = dist.repeat(repeats)
+        z = dist.sample(generator=generator, noise=noise, scale=vae.config.scaling_factor)  # :39-40
+        return self._owner.engine(z.shape[0], H // 8, W // 8).embed_vae_latent(z)             # :41
 
     # -- checkpoint format (diffusers layout: <dir>/config.json + <dir>/diffusion_pytorch_model.safetensors) ------
     def _extra_config(self) -> dict:

@@ -3,8 +3,10 @@
 `__call__` keeps the reference's keyword surface (:92-120).  The hot-path subset is implemented
 (`prompt_embeds` / `negative_prompt_embeds` / `latents` / cached conditioning embeddings / `guidance_scale`
 / `num_inference_steps` / `controlnet_conditioning_scale` / `control_guidance_start|end` / `generator` /
-`output_type="latent"` / `callback_on_step_end`); everything outside the denoise loop (CLIP text encoding, VAE,
-PIL post-processing -- SURVEY.md 8(f) rows N2) raises NotImplementedError instead of being silently ignored.
+`output_type` / `callback_on_step_end`); the per-call stages either side of the loop run on
+`edgestyle_b200.vae.AutoencoderKL` (raw control images of the ControlLoRA nets -> VAE conditioning embedding; final
+latents -> image for `output_type` "pt" / "np" / "pil"); CLIP text encoding and the safety checker are outside the
+path and raise NotImplementedError instead of being silently ignored.
 
 Per step (reference loop body :434-543): CFG duplicate -> 6 ControlNets + merge -> UNet -> CFG combine ->
 scheduler.step.  Here: one captured CUDA graph (DenoiseEngine.step) + one es_cfg_ddim launch.
@@ -74,8 +76,10 @@ class EdgeStyleStableDiffusionControlNetPipeline:
             raise NotImplementedError("text encoding is outside the hot path: pass prompt_embeds / negative_prompt_embeds")
         if prompt_embeds is None:
             raise ValueError("prompt_embeds is required")
-        if output_type != "latent":
-            raise NotImplementedError('VAE decode / PIL output is outside the hot path: use output_type="latent"')
+        if output_type not in ("latent", "pt", "np", "pil"):
+            raise ValueError(f"unknown output_type {output_type!r}")
+        if output_type != "latent" and self.vae is None:
+            raise ValueError('output_type != "latent" needs the pipeline\'s vae (edgestyle_b200.vae.AutoencoderKL)')
         for name, val in (("ip_adapter_image", ip_adapter_image), ("clip_skip", clip_skip), ("timesteps", timesteps)):
             if val is not None:
                 raise NotImplementedError(f"{name} is not implemented")
@@ -113,11 +117,13 @@ class EdgeStyleStableDiffusionControlNetPipeline:
         for net, c in zip(self.controlnet.nets, image):
             c = self._to_dev(c, dev)
             if c.shape[1] != c0:
-                # raw control image [n, 3, 8h, 8w]: the per-call precompute of prepare_image (:629-664) -- built for
-                # the openpose nets (ControlNetConditioningEmbedding); ControlLoRA nets need the VAE encoder (N2)
+                # raw control image [n, 3, 8h, 8w]: the per-call precompute of prepare_image (:629-664): openpose nets
+                # run their ControlNetConditioningEmbedding, ControlLoRA nets the VAE encoder + conv_vae_out.  The
+                # reference embeds AFTER the CFG duplication (:657-662), so the two CFG rows of a ControlLoRA net
+                # carry independently sampled VAE latents: one encoder pass, `repeats` draws.
                 if getattr(net, "controlnet_conditioning_channel_order", "rgb") == "bgr":
                     c = torch.flip(c, dims=[1])
-                c = net.preprocess_image(c)
+                c = net.preprocess_image(c, repeats=2 if (cfg_on and c.shape[0] == n_img) else 1)
             if cfg_on and c.shape[0] == n_img:  # CFG duplication of the cached embedding (:657-658)
                 c = torch.cat([c] * 2)
             if c.shape[0] != B:
@@ -164,6 +170,25 @@ class EdgeStyleStableDiffusionControlNetPipeline:
             if callback_on_step_end is not None:
                 out = callback_on_step_end(self, i, t, {k: locals()[k] for k in callback_on_step_end_tensor_inputs})
                 latents = out.pop("latents", latents) if out else latents
+        images = latents
+        if output_type != "latent":  # :552-572 (no safety checker: has_nsfw_concept is None, every image denormalised)
+            images = self.vae.decode(latents / self.vae.config.scaling_factor, return_dict=False, generator=generator)[0]
+            images = self._postprocess(images, output_type)
         if not return_dict:
-            return (latents, None)
-        return StableDiffusionPipelineOutput(images=latents, nsfw_content_detected=None)
+            return (images, None)
+        return StableDiffusionPipelineOutput(images=images, nsfw_content_detected=None)
+
+    def _postprocess(self, image: torch.Tensor, output_type: str):
+        """VaeImageProcessor.postprocess (diffusers image_processor.py): denormalise to [0, 1], then "pt" (NCHW
+        tensor), "np" (NHWC float32 array, a device->host copy) or "pil".  Host-side image formatting of the decoded
+        tensor, outside the kernels."""
+        image = (image / 2 + 0.5).clamp(0, 1)
+        if output_type == "pt":
+            return image
+        arr = image.cpu().permute(0, 2, 3, 1).float().numpy()
+        self.d2h_bytes += arr.nbytes
+        if output_type == "np":
+            return arr
+        from PIL import Image
+
+        return [Image.fromarray((a * 255).round().astype("uint8")) for a in arr]

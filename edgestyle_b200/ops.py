@@ -440,6 +440,41 @@ def im2col3x3(src, dst, n: int, h: int, w: int, c: int, stride: int):
     return dst
 
 
+def im2col3x3_pad(src, dst, n: int, h: int, w: int, c: int, stride: int, pad_lo: int, pad_hi: int):
+    """3x3 window matrix with explicit zero padding per side (VAE Downsample2D: pad (0, 1), stride 2)."""
+    _need_cuda(src, dst)
+    _count()
+    check(load().es_im2col3x3_pad(_dt(src), src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), n, h, w, c,
+                                  stride, pad_lo, pad_hi, _stream()), "es_im2col3x3_pad")
+    return dst
+
+
+def softmax_rows(s: torch.Tensor, p: torch.Tensor, scale: float = 1.0):
+    """p[r] = softmax(scale * s[r]); s fp32 [rows, cols], p 16-bit [rows, cols] (row pitches = stride(0))."""
+    _need_cuda(s, p)
+    assert s.dtype == torch.float32 and s.shape == p.shape
+    _count()
+    check(load().es_softmax_rows(_dt(p), s.data_ptr(), s.stride(0), p.data_ptr(), p.stride(0), s.shape[0], s.shape[1],
+                                 float(scale), _stream()), "es_softmax_rows")
+    return p
+
+
+def gaussian_sample(moments: torch.Tensor, noise: Optional[torch.Tensor], out: torch.Tensor, scale: float = 1.0):
+    """out NCHW fp32 [n, L, h, w] = (mean + std * noise) * scale from moments fp32 [n*h*w, >= 2L] (noise None: mode)."""
+    _need_cuda(moments, out)
+    n, L = out.shape[0], out.shape[1]
+    hw = out[0, 0].numel()
+    assert moments.dtype == torch.float32 and out.dtype == torch.float32 and out.is_contiguous()
+    assert moments.shape[0] == n * hw
+    if noise is not None:
+        _need_cuda(noise)
+        assert noise.dtype == torch.float32 and noise.is_contiguous() and noise.shape == out.shape
+    _count()
+    check(load().es_gaussian_sample(moments.data_ptr(), moments.stride(0), _p(noise), out.data_ptr(), n, L, hw,
+                                    float(scale), _stream()), "es_gaussian_sample")
+    return out
+
+
 def upsample2x(src, dst, n: int, h: int, w: int):
     c = src.shape[1]
     _count()

@@ -210,6 +210,11 @@ int es_nhwc_to_nchw(int dtype, const void* src, long long lds, float* dst, int n
 /* im2col for 3x3 pad 1 stride s over NHWC: out [n*ho*wo][ldo] with column = tap*c + ch (zero padded to ldo). */
 int es_im2col3x3(int dtype, const void* src, long long lds, void* dst, long long ldo, int n, int h, int w, int c,
                  int stride, void* stream);
+/* same with explicit zero padding per side (0 or 1): pad_lo rows/columns before, pad_hi after the image.  The VAE
+ * encoder's Downsample2D(padding=0) pads (0, 1, 0, 1) and then runs a stride-2 conv (diffusers AutoencoderKL, reached
+ * from /root/reference/model/controllora.py:39). */
+int es_im2col3x3_pad(int dtype, const void* src, long long lds, void* dst, long long ldo, int n, int h, int w, int c,
+                     int stride, int pad_lo, int pad_hi, void* stream);
 /* nearest-neighbour x2 upsample NHWC (Upsample2D before its conv). */
 int es_upsample2x(int dtype, const void* src, long long lds, void* dst, long long ldd, int n, int h, int w, int c,
                   void* stream);
@@ -229,6 +234,20 @@ int es_cfg_x0(const float* eps, const float* sample, const float* guidance, floa
               int imgs, int chw, void* stream);
 int es_lincomb4(float* out, float c0, const float* x0, float c1, const float* x1, float c2, const float* x2, float c3,
                 const float* x3, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------ VAE (per-call stages)
+ * The AutoencoderKL encoder (/root/reference/model/controllora.py:38-42, reached once per call from
+ * /root/reference/model/edgestyle_pipeline.py:660-662) and decoder (edgestyle_pipeline.py:552-557) run on es_gemm /
+ * es_groupnorm; their mid-block attention has ONE head as wide as the block (512), beyond es_attention's TMEM budget,
+ * so its scores go through es_gemm (fp32 out), this row softmax, and es_gemm again.
+ *   p[r][0..cols) = softmax(scale * s[r][0..cols)); s fp32 pitch lds, p `dtype` pitch ldp. */
+int es_softmax_rows(int dtype, const float* s, long long lds, void* p, long long ldp, int rows, int cols, float scale,
+                    void* stream);
+/* DiagonalGaussianDistribution.sample() of the encoder moments (controllora.py:39) times `scale` (:40):
+ * moments fp32 [n*hw][ldm] with columns (mean[0..L), logvar[0..L)); noise fp32 NCHW [n][L][hw] or NULL (= mode());
+ * out fp32 NCHW [n][L][hw] = (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise) * scale. */
+int es_gaussian_sample(const float* moments, long long ldm, const float* noise, float* out, int n, int latent_channels,
+                       int hw, float scale, void* stream);
 
 /* Profiling probe (tools/timeline.py): a 1-thread kernel that stores the GPU's %globaltimer (ns) into *slot once all
  * earlier work of `stream` has completed -- lets a captured multi-stream step be timed op by op. */
