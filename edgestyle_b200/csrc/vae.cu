@@ -106,13 +106,13 @@ extern "C" int es_softmax_rows(int dtype, const float* s, long long lds, void* p
   ES_CHECK(smem <= 200 * 1024, "es_softmax_rows: row of %d columns does not fit in shared memory", cols);
   const float sl2 = scale * 1.4426950408889634f;
   if (dtype == ES_DTYPE_BF16) {
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024)  // 48 KB default limit covers dynamic + static shared memory
       ES_CUDA(cudaFuncSetAttribute(softmax_rows_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(smem)));
     ES_CUDA(launch_kernel(softmax_rows_kernel<__nv_bfloat16>, dim3(rows), dim3(kSmThreads), smem, st, s, lds,
                           reinterpret_cast<__nv_bfloat16*>(p), ldp, cols, sl2));
   } else {
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024)  // 48 KB default limit covers dynamic + static shared memory
       ES_CUDA(cudaFuncSetAttribute(softmax_rows_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(smem)));
     ES_CUDA(launch_kernel(softmax_rows_kernel<__half>, dim3(rows), dim3(kSmThreads), smem, st, s, lds,

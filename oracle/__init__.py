@@ -18,5 +18,9 @@ fixtures for this path, and its arithmetic lives in the third-party ``diffusers=
 * algebraic identities (LoRA fuse == unfused, zero zero-convs => cond-independent UNet, DDIM
   schedule constants).
 
+``oracle.vae`` (AutoencoderKL: the per-call VAE stages either side of the loop) is likewise a
+restatement of diffusers 0.26.3 with no golden vectors in the reference: parity unpinned; pinned on the published SD1.5
+VAE parameter count (83 653 863) and the diffusers ``vae/`` state-dict key names.
+
 Everything else follows SURVEY.md Appendix A (diffusers 0.26.3 semantics for SD1.5).
 """

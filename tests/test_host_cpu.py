@@ -122,8 +122,10 @@ def test_pipeline_rejects_out_of_scope_arguments(models):
     conds = [torch.zeros(2, 64, 8, 8)] * 6
     with pytest.raises(NotImplementedError):
         pipe(prompt="a photo", image=conds, prompt_embeds=pe, negative_prompt_embeds=pe, output_type="latent")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):  # decoded output needs the pipeline's vae (edgestyle_pipeline.py:552-557)
         pipe(image=conds, prompt_embeds=pe, negative_prompt_embeds=pe, output_type="pil")
+    with pytest.raises(ValueError):
+        pipe(image=conds, prompt_embeds=pe, negative_prompt_embeds=pe, output_type="jpeg")
     with pytest.raises(NotImplementedError):
         pipe(image=conds, prompt_embeds=pe, negative_prompt_embeds=pe, output_type="latent", eta=0.5)
     with pytest.raises(NotImplementedError):

@@ -126,7 +126,8 @@ def test_vae_encode_decode_parity(chans, n, H, W, dtype):
     with tempfile.TemporaryDirectory() as d:
         vae.save_pretrained(d)
         again = AutoencoderKL.from_pretrained(d, torch_dtype=dtype)
-    assert torch.equal(again.decode(z.to(DEV)).sample, gimg)
+    # same weights, same schedule; not bit-identical run to run (GroupNorm statistics are accumulated with fp32 atomics)
+    assert (again.decode(z.to(DEV)).sample - gimg).abs().max().item() <= tol * max(1.0, gimg.abs().max().item())
 
 
 def test_controllora_vae_conditioning_and_pipeline_decode():
@@ -187,6 +188,7 @@ def test_controllora_vae_conditioning_and_pipeline_decode():
     assert ok, f"pipeline decode: {msg}"
     torch.manual_seed(123)
     arr = pipe(output_type="np", **kw).images
-    assert arr.shape == (1, 8 * h, 8 * w, 3) and abs(arr - out.images.cpu().permute(0, 2, 3, 1).numpy()).max() == 0
+    assert arr.shape == (1, 8 * h, 8 * w, 3) and arr.dtype.name == "float32"
+    assert abs(arr - out.images.cpu().permute(0, 2, 3, 1).numpy()).max() <= 2e-2  # two runs: fp32-atomic statistics
     with pytest.raises(ValueError):
         EdgeStyleStableDiffusionControlNetPipeline(unet=unet, controlnet=multi)(output_type="pt", **kw)

@@ -30,3 +30,28 @@ for rows, c, imgs in [(32768, 320, 8), (8192, 640, 8), (2048, 1280, 8), (512, 12
         tg = t(lambda: ops.groupnorm(x, y, g, b, ws, imgs, rows // imgs, 32, 1e-5, True), cold=cold)
         print(f"[{rows}x{c}] {'cold' if cold else 'warm'}: copy {tc:6.1f} us ({2*nbytes/tc/1e3:5.0f} GB/s)  layernorm {tl:6.1f} us ({2*nbytes/tl/1e3:5.0f} GB/s)"
               f"  groupnorm(memset+stats+apply) {tg:6.1f} us ({3*nbytes/tg/1e3:5.0f} GB/s)", flush=True)
+
+# GroupNorm apply alone (statistics already accumulated by the producing GEMM's epilogue: the common case in the step)
+for rows, c, imgs in [(32768, 320, 8), (8192, 640, 8), (262144, 128, 1)]:
+    x = torch.randn(rows, c, device=dev, dtype=torch.float16)
+    y = torch.empty_like(x)
+    g = torch.ones(c, device=dev); b = torch.zeros(c, device=dev)
+    ws = torch.zeros(imgs, 32, 2, device=dev)
+    ops.groupnorm(x, y, g, b, ws, imgs, rows // imgs, 32, 1e-5, True)  # leaves valid statistics in ws
+    nbytes = x.numel() * 2
+    for cold in (True, False):
+        tc = t(lambda: y.copy_(x), cold=cold)
+        ta = t(lambda: ops.groupnorm(x, y, g, b, ws, imgs, rows // imgs, 32, 1e-5, True, stats_ready=True), cold=cold)
+        print(f"[{rows}x{c}] {'cold' if cold else 'warm'}: copy {tc:6.1f} us ({2*nbytes/tc/1e3:5.0f} GB/s)  gn_apply {ta:6.1f} us "
+              f"({2*nbytes/ta/1e3:5.0f} GB/s)", flush=True)
+
+# row softmax of the VAE mid-block attention (fp32 scores in, fp16 probabilities out): 6 B per score
+for n in (1024, 4096):
+    s = torch.randn(n, n, device=dev)
+    p = torch.empty(n, n, device=dev, dtype=torch.float16)
+    nb = s.numel() * 6
+    for cold in (True, False):
+        tc = t(lambda: p.copy_(s), cold=cold)
+        ts_ = t(lambda: ops.softmax_rows(s, p), cold=cold)
+        print(f"[softmax {n}x{n}] {'cold' if cold else 'warm'}: fp32->fp16 copy {tc:6.1f} us ({nb/tc/1e3:5.0f} GB/s)  softmax_rows {ts_:6.1f} us "
+              f"({nb/ts_/1e3:5.0f} GB/s)", flush=True)
