@@ -12,7 +12,7 @@ What it restates: `diffusers==0.26.3` `AutoencoderKL` (models/autoencoders/autoe
 third-party dependency absent from /root/reference and from this image, and the reference holds no golden vectors
 for this stage: **parity unpinned** (the restatement is anchored on the published layer list and the
 diffusers state-dict key names, which `state_dict()` reproduces so that a real `vae/` checkpoint loads unchanged:
-SD1.5 VAE = 83 653 863 parameters, checked in tests/test_oracle_golden.py).
+SD1.5 VAE = 83 653 863 parameters, checked in tests/test_oracle_golden.py and tests/test_vae_host_cpu.py).
 """
 from __future__ import annotations
 

@@ -138,3 +138,40 @@ def test_denoise_teacher_forced_equals_free_running():
     lat, trace = denoise(m, inp, 3, 4.5, return_eps=True)
     lat2 = denoise(m, inp, 3, 4.5, override_latents=[tr[0] for tr in trace])
     assert torch.equal(lat, lat2)
+
+
+def test_vae_oracle_published_counts_and_identities():
+    """oracle/vae.py (parity unpinned): published SD1.5 VAE parameter count and diffusers key names; the deterministic
+    algebra the product path relies on (quant_conv folded into conv_out; V bias folded into the attention output bias)
+    holds in fp64."""
+    from oracle.vae import AutoencoderKL, VaeConfig
+
+    full = AutoencoderKL()
+    assert sum(p.numel() for p in full.parameters()) == 83_653_863
+    keys = set(full.state_dict())
+    for k in ("encoder.down_blocks.0.downsamplers.0.conv.weight", "encoder.mid_block.attentions.0.to_out.0.bias",
+              "decoder.up_blocks.2.upsamplers.0.conv.bias", "decoder.up_blocks.3.resnets.0.conv_shortcut.weight",
+              "encoder.mid_block.attentions.0.group_norm.weight", "quant_conv.weight", "post_quant_conv.bias"):
+        assert k in keys, k
+    assert len(keys) == 248
+    torch.manual_seed(0)
+    m = AutoencoderKL(VaeConfig(block_out_channels=(32, 32, 64, 64))).double().eval()
+    x = torch.randn(1, 3, 32, 32, dtype=torch.float64)
+    with torch.no_grad():
+        d = m.encode(x).latent_dist
+        assert d.mean.shape == (1, 4, 4, 4) and torch.equal(d.mode(), d.mean)
+        n = torch.randn(1, 4, 4, 4, dtype=torch.float64)
+        assert torch.allclose(d.sample(noise=n), d.mean + torch.exp(0.5 * d.logvar) * n)
+        # a 1x1 after a conv is a conv
+        h = torch.randn(1, 64, 4, 4, dtype=torch.float64)
+        wq = m.quant_conv.weight.reshape(8, 8)
+        w = torch.einsum("om,mikl->oikl", wq, m.encoder.conv_out.weight)
+        b = wq @ m.encoder.conv_out.bias + m.quant_conv.bias
+        assert torch.allclose(torch.nn.functional.conv2d(h, w, b, padding=1), m.quant_conv(m.encoder.conv_out(h)), atol=1e-10)
+        # rows of softmax sum to 1: the V bias moves into the output bias
+        a = m.encoder.mid_block.attentions[0]
+        t = a.group_norm(h).view(1, 64, 16).transpose(1, 2)
+        p = torch.softmax(a.to_q(t) @ a.to_k(t).transpose(1, 2) * 64 ** -0.5, -1)
+        folded = (p @ (t @ a.to_v.weight.t())) @ a.to_out[0].weight.t() + (a.to_out[0].bias + a.to_out[0].weight @ a.to_v.bias)
+        assert torch.allclose(h + folded.transpose(1, 2).reshape(1, 64, 4, 4), a(h), atol=1e-10)
+        assert m.decode(d.mode()).sample.shape == (1, 3, 32, 32)
