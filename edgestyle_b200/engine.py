@@ -298,7 +298,7 @@ class DenoiseEngine:
 
     def __init__(self, cfg, unet_sd, lora_sds, pose_sd, merge_sd, *, rows: int, h: int, w: int,
                  dtype=torch.float16, device="cuda", n_text: int = 77, pattern=SUPPORTED_PATTERN,
-                 use_graph: bool = False):
+                 use_graph: bool = False, fuse_lora: Optional[bool] = None):
         if tuple(pattern) != SUPPORTED_PATTERN:
             raise NotImplementedError(f"load_pattern {pattern}: only {SUPPORTED_PATTERN} (app.py:40) is supported")
         if not torch.cuda.is_available():
@@ -319,7 +319,7 @@ class DenoiseEngine:
         self.fuse_gn_stats = os.environ.get("ES_FUSE_GN", "1") != "0"
         # ControlLoRA update: "fused" = one fused weight copy per LoRA group (default), "unfused" = rank-r update as
         # extra K-blocks of the accumulator (t = x down^T, then [x | t] [W | up]^T)
-        self.fuse_lora = os.environ.get("ES_LORA", "fused") != "unfused"
+        self.fuse_lora = os.environ.get("ES_LORA", "fused") != "unfused" if fuse_lora is None else bool(fuse_lora)
         # zero-convs + merge on the side stream: 0 = after both encoders (in the order the decoder consumes them),
         # 1 = level by level as the encoders produce them, 2 = hybrid: the small levels (32x32 and below) as they are
         # produced, the three heavy 64x64-level merges afterwards, under the decoder's latency-bound deep levels

@@ -37,7 +37,7 @@ def _save_dir(directory, state_dict, config: dict):
     if os.path.isfile(directory):
         raise ValueError(f"Provided path ({directory}) should be a directory, not a file")
     os.makedirs(directory, exist_ok=True)
-    save_file({k: v.detach().cpu().contiguous() for k, v in state_dict.items()}, os.path.join(directory, WEIGHTS_NAME),
+    save_file({k: v.detach().cpu().contiguous().clone() for k, v in state_dict.items()}, os.path.join(directory, WEIGHTS_NAME),
               metadata={"format": "pt"})
     json.dump(config, open(os.path.join(directory, CONFIG_NAME), "w"), indent=2)
 
@@ -257,7 +257,56 @@ class ControlLoRAModel(CachedControlNetModel):
         return cls(_config_from_dict(cfg), sd, lora_linear_rank=cfg.get("lora_linear_rank", 4),
                    lora_conv2d_rank=cfg.get("lora_conv2d_rank", 0), unet=unet)
 
+    def fused_state_dict(self, lora_scale: float = 1.0) -> "OrderedDict[str, torch.Tensor]":
+        """Full diffusers-layout ControlNet state dict of this net with the LoRA folded in: every tied base tensor of the
+        UNet encoder, `W + lora_scale * up @ down` for each LoRA'd Linear (diffusers `LoRACompatibleLinear._fuse_lora`,
+        reached from controllora.py:728-737), plus the net's own tensors (zero-convs).  fp32 host math; the UNet is not
+        modified."""
+        if self._unet is None:
+            raise RuntimeError("tie_weights(unet) first: the base weights of a ControlLoRA net are the UNet's (controllora.py:623-632)")
+        usd = self._unet.state_dict()
+        out = OrderedDict()
+        for k in C.encoder_spec(self.config):
+            w = usd[k]
+            if k.endswith(".weight"):
+                base = k[:-len(".weight")]
+                dn, up = self._sd.get(f"{base}.lora_layer.down.weight"), self._sd.get(f"{base}.lora_layer.up.weight")
+                if dn is not None and up is not None:
+                    w = (w.float() + lora_scale * (up.float() @ dn.float())).to(w.dtype)
+            out[k] = w
+        for k, v in self._sd.items():  # conv_vae_out is an alias of the (tied) conv_in module (controllora.py:36)
+            if ".lora_layer." not in k and k not in out and not k.startswith("controlnet_cond_embedding.conv_vae_out."):
+                out[k] = v
+        return out
+
+    def fuse(self) -> "FusedControlLoRAModel":
+        """controllora.py:739-777: a plain ControlNet holding W + up @ down (e.g. to export one self-contained
+        checkpoint).  Unlike the reference -- whose `fuse_lora` writes through the tied Parameters and so also rewrites
+        the UNet (and stacks both nets' updates when two ControlLoRAs share it) -- the UNet is left untouched."""
+        net = FusedControlLoRAModel(self.config, self.fused_state_dict(1.0))
+        net.controlnet_conditioning_channel_order = self.controlnet_conditioning_channel_order
+        if getattr(self, "autoencoder", None) is not None:
+            net.autoencoder = self.autoencoder
+        return net
+
     def fuse_lora(self, lora_scale: float = 1.0, safe_fusing: bool = False):
         raise NotImplementedError(
-            "fusing would un-tie the base weights from the UNet and forfeit the batched base pass; the engine "
-            "applies the LoRA update inside the GEMM instead (es_gemm source 2)")
+            "in-place fusing would write through the tied UNet weights (the reference's fuse_lora does, corrupting the "
+            "UNet); use fuse() / fused_state_dict() for a fused copy, or EdgeStyleMultiControlNetModel.fuse() to run "
+            "the engine on fused weight copies (its default)")
+
+
+class FusedControlLoRAModel(CachedControlNetModel):
+    """controllora.py:292-375: a plain ControlNet whose weights already contain the LoRA update (`ControlLoRAModel
+    .fuse()`).  A weight container in diffusers ControlNet layout (save_pretrained / from_pretrained); inside an
+    EdgeStyleMultiControlNetModel the fused path is selected with `multi.fuse()` instead, which keeps the tied base
+    pass and the cached conditioning embeddings."""
+
+    uses_lora = False
+
+    def preprocess_image(self, image, **_):
+        raise NotImplementedError("FusedControlLoRAModel is a weight container here: embed control images with the "
+                                  "ControlLoRAModel it came from (its embedder is the VAE, not the openpose convs)")
+
+    def _extra_config(self) -> dict:
+        return {"_class_name": "FusedControlLoRAModel", "uses_vae": True}

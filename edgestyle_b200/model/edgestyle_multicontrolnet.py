@@ -51,6 +51,7 @@ class EdgeStyleMultiControlNetModel:
             if slot not in net._slots:
                 net._slots.append(slot)
         self._engines: Dict[tuple, DenoiseEngine] = {}
+        self._fused = False  # fuse(): engines built afterwards use fused LoRA weight copies regardless of ES_LORA
 
     # ---------------------------------------------------------------------------------------
     def state_dict(self):
@@ -72,7 +73,7 @@ class EdgeStyleMultiControlNetModel:
             eng = DenoiseEngine(self.config, self.unet().state_dict(),
                                 [self.nets[0].state_dict(), self.nets[2].state_dict()], self.nets[1].state_dict(),
                                 self._merge_sd, rows=rows, h=h, w=w, dtype=self.dtype, n_text=self.n_text,
-                                use_graph=use_graph)
+                                use_graph=use_graph, fuse_lora=True if self._fused else None)
             self._engines[key] = eng
         return eng
 
@@ -116,7 +117,13 @@ class EdgeStyleMultiControlNetModel:
         return eng.single_controlnet(group, sample, timestep, ehs, cond, scale, guess_mode)
 
     def fuse(self):
-        raise NotImplementedError("see ControlLoRAModel.fuse_lora: LoRA is applied inside the GEMM")
+        """edgestyle_multicontrolnet.py:284-287 replaces every ControlLoRA net by `net.fuse()`.  Here the nets stay
+        (so their conditioning embeddings remain cacheable, which the reference loses after fusing: SURVEY.md appendix,
+        quirk 11) and the engine is pinned to one fused weight copy `W + up @ down` per LoRA group -- the same
+        arithmetic as running the fused nets, whatever ES_LORA says."""
+        if not self._fused:
+            self._fused = True
+            self._engines.clear()
 
     # -- checkpoint directory format of the reference (edgestyle_multicontrolnet.py:213-282, 289-430) ----------------
     def save_pretrained(self, save_directory, save_pattern: Optional[Sequence[Optional[int]]] = None, **_):

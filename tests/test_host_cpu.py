@@ -176,3 +176,49 @@ def test_checkpoint_directory_roundtrip(models, tmp_path):
         EdgeStyleMultiControlNetModel.from_pretrained(d, controlnet_class=ControlLoRAModel)  # load_pattern required
     with pytest.raises(ValueError):
         EdgeStyleMultiControlNetModel.from_pretrained(d, load_pattern=pattern, controlnet_class=ControlLoRAModel)
+
+
+def test_fuse_matches_oracle_fuse_lora(models, tmp_path):
+    """ControlLoRAModel.fuse() / fused_state_dict() (controllora.py:728-777) against the oracle's fuse_lora, the
+    FusedControlLoRAModel checkpoint round trip, and multi.fuse() pinning the engine to fused weight copies."""
+    import copy
+
+    from edgestyle_b200.model import (CachedControlNetModel, ControlLoRAModel, EdgeStyleMultiControlNetModel,
+                                      FusedControlLoRAModel, UNet2DConditionModel)
+
+    cfg = C.UNetConfig.from_any(TINY)
+    unet = UNet2DConditionModel(cfg, models.unet.state_dict())
+    agn = ControlLoRAModel(cfg, models.lora_agnostic.state_dict(), lora_linear_rank=4)
+    with pytest.raises(RuntimeError):
+        agn.fused_state_dict()  # not tied yet
+    agn.tie_weights(unet)
+    before = {k: v.clone() for k, v in unet.state_dict().items()}
+    fused = agn.fuse()
+    assert isinstance(fused, FusedControlLoRAModel) and isinstance(fused, CachedControlNetModel) and not fused.uses_lora
+    ref = copy.deepcopy(models.lora_agnostic)
+    ref.fuse_lora()
+    want = ref.full_state_dict()
+    got = fused.state_dict()
+    changed = 0
+    for k, v in want.items():
+        if k.startswith("controlnet_cond_embedding."):
+            continue
+        assert k in got, k
+        assert torch.allclose(got[k].float(), v.float(), atol=1e-6), k
+        changed += int(k in before and not torch.equal(got[k], before[k]))
+    assert changed > 0, "the LoRA update must change at least one tied weight"
+    assert all(".lora_layer." not in k for k in got)
+    assert all(torch.equal(v, before[k]) for k, v in unet.state_dict().items())  # the UNet is left untouched
+    half = agn.fused_state_dict(0.5)
+    k = next(k for k in got if k in before and not torch.equal(got[k], before[k]))
+    assert torch.allclose(half[k].float() - before[k].float(), 0.5 * (got[k].float() - before[k].float()), atol=1e-6)
+    fused.save_pretrained(tmp_path / "fused")
+    again = FusedControlLoRAModel.from_pretrained(tmp_path / "fused")
+    assert all(torch.equal(again.state_dict()[k], v) for k, v in got.items())
+    with pytest.raises(NotImplementedError):
+        agn.fuse_lora()
+    clo = ControlLoRAModel(cfg, models.lora_clothes.state_dict(), lora_linear_rank=4, unet=unet)
+    pose = CachedControlNetModel(cfg, models.openpose.state_dict())
+    multi = EdgeStyleMultiControlNetModel([agn, pose, clo, pose, clo, pose], models.controlnet.merge_state_dict(), (8, 8))
+    multi.fuse()
+    assert multi._fused and multi.nets[0] is agn  # nets stay ControlLoRA objects: conditioning stays cacheable
