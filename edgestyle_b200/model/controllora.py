@@ -163,7 +163,7 @@ class CachedControlNetModel:
             raise RuntimeError("register this net in an EdgeStyleMultiControlNetModel before calling preprocess_image")
         n, _, H, W = image.shape
         if not self.uses_lora:
-            emb = self._owner.engine(n, H // 8, W // 8).embed_openpose(image)
+            emb = self._owner.embed_engine(n, H // 8, W // 8).embed_openpose(image)
             return torch.cat([emb] * repeats) if repeats > 1 else emb
         vae = getattr(self, "autoencoder", None)
         if vae is None:
@@ -173,7 +173,7 @@ class CachedControlNetModel:
         if repeats > 1:
             dist = dist.repeat(repeats)
         z = dist.sample(generator=generator, noise=noise, scale=vae.config.scaling_factor)  # :39-40
-        return self._owner.engine(z.shape[0], H // 8, W // 8).embed_vae_latent(z)             # :41
+        return self._owner.embed_engine(z.shape[0], H // 8, W // 8).embed_vae_latent(z)       # :41
 
     # -- checkpoint format (diffusers layout: <dir>/config.json + <dir>/diffusion_pytorch_model.safetensors) ------
     def _extra_config(self) -> dict:

@@ -77,6 +77,15 @@ class EdgeStyleMultiControlNetModel:
             self._engines[key] = eng
         return eng
 
+    def embed_engine(self, rows: int, h: int, w: int) -> DenoiseEngine:
+        """Engine for the per-call conditioning embedders (`embed_openpose`, `embed_vae_latent`): they only use the
+        packed embedder / conv_in weights and scratch keyed by their own batch size, so any engine already built for
+        this latent size serves (no second weight replica for a different row count)."""
+        for (_, hh, ww, _), eng in self._engines.items():
+            if (hh, ww) == (h, w):
+                return eng
+        return self.engine(rows, h, w)
+
     # -- reference surface ----------------------------------------------------------------------
     def forward(self, sample, timestep, encoder_hidden_states, controlnet_cond: List[torch.Tensor],
                 conditioning_scale: List[float], class_labels=None, timestep_cond=None, attention_mask=None,

@@ -113,6 +113,10 @@ class EdgeStyleStableDiffusionControlNetPipeline:
         else:
             pe = self._to_dev(prompt_embeds, dev)
         c0 = self.unet.config.block_out_channels[0]
+        # latent size from the first conditioning entry (cached embedding [*, c0, h, w] or raw image [*, 3, 8h, 8w]);
+        # the step engine is built first so that the per-call embedders below share its weights
+        h, w = image[0].shape[-2:] if image[0].shape[1] == c0 else (image[0].shape[-2] // 8, image[0].shape[-1] // 8)
+        eng = self.controlnet.engine(B, h, w, use_graph=self.use_graph)
         conds = []
         for net, c in zip(self.controlnet.nets, image):
             c = self._to_dev(c, dev)
@@ -129,8 +133,8 @@ class EdgeStyleStableDiffusionControlNetPipeline:
             if c.shape[0] != B:
                 raise ValueError(f"conditioning embedding has {c.shape[0]} rows, expected {B}")
             conds.append(c)
-        h, w = conds[0].shape[-2:]
-        eng = self.controlnet.engine(B, h, w, use_graph=self.use_graph)
+        if tuple(conds[0].shape[-2:]) != (h, w):
+            raise ValueError(f"conditioning embeddings are {tuple(conds[0].shape[-2:])}, expected latent size {(h, w)}")
         eng.set_prompt(pe)
         eng.set_conditioning(conds)
         sch = self.scheduler

@@ -10,7 +10,9 @@ edgestyle_pipeline.py:552-557.  The class keeps the diffusers surface those line
 Everything runs channels-last on the library's kernels (no torch arithmetic):
   * 3x3 convolutions: es_gemm implicit GEMM (tcgen05); the stride-2 `Downsample2D(padding=0)` convs pad (0, 1, 0, 1):
     es_im2col3x3_pad + flat es_gemm; `Upsample2D`: es_upsample2x + es_gemm.
-  * GroupNorm(32, eps 1e-6) + SiLU: es_groupnorm_stats / _apply; the residual add rides in the conv2 epilogue.
+  * GroupNorm(32, eps 1e-6) + SiLU: the statistics come from the epilogue of the GEMM that produced the tensor
+    (EsGemm.gn_ws), so only es_groupnorm_apply runs; the residual add rides in the conv2 epilogue and a resnet's 1x1
+    shortcut is a second K source of its conv2 (EsGemm.a2 / b2).
   * mid-block attention: ONE head of C = 512 channels over h*w tokens -- wider than es_attention's TMEM budget (192),
     so S = Q K^T (es_gemm, fp32 out, scale as `alpha`), P = es_softmax_rows(S), O = P V (es_gemm against V^T, which
     a GEMM with swapped operands produces directly: V^T = W_v X^T).  The V bias is folded into the output bias
@@ -21,6 +23,7 @@ There is no CPU path: construction without CUDA raises.
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 from dataclasses import dataclass, fields
 from typing import Dict, List, Mapping, Optional, Tuple
@@ -189,7 +192,7 @@ class _Res:
     c1: _Conv3
     n2: Tuple[torch.Tensor, torch.Tensor]
     c2: _Conv3
-    sc: Optional[Tuple[torch.Tensor, torch.Tensor]]  # 1x1 shortcut (weight [cout, cin], bias)
+    sc: Optional[torch.Tensor]  # 1x1 shortcut weight [cout, cin]: second K source of conv2 (its bias rides in c2.b)
     cin: int
     cout: int
 
@@ -234,6 +237,9 @@ class AutoencoderKL:
         self.dtype = dtype
         self._sd = OrderedDict((k, state_dict[k]) for k in spec)
         self._bufs: Dict[str, torch.Tensor] = {}
+        self._stats_of: Dict[tuple, torch.Tensor] = {}  # tensor -> statistics slot filled by its producing GEMM
+        self._ws_next = 0
+        self.fuse_gn_stats = os.environ.get("ES_VAE_FUSE_GN", "1") != "0"
         ops.set_gemm_workspace(256 << 20, self.dev)
         self._pack()
 
@@ -266,12 +272,12 @@ class AutoencoderKL:
         return self._f32(self._w(name + ".weight")), self._f32(self._w(name + ".bias"))
 
     def _res(self, name, cin, cout) -> _Res:
-        sc = None
-        if cin != cout:
-            sc = (self._mat(self._w(name + ".conv_shortcut.weight").reshape(cout, cin)),
-                  self._f32(self._w(name + ".conv_shortcut.bias")))
+        sc, b2 = None, self._w(name + ".conv2.bias")
+        if cin != cout:  # conv_shortcut(x) + conv2(h): one accumulator, two K sources (EsGemm.a2 / b2)
+            sc = self._mat(self._w(name + ".conv_shortcut.weight").reshape(cout, cin))
+            b2 = b2 + self._w(name + ".conv_shortcut.bias")
         return _Res(self._norm(name + ".norm1"), self._conv3(name + ".conv1"), self._norm(name + ".norm2"),
-                    self._conv3(name + ".conv2"), sc, cin, cout)
+                    self._conv3(name + ".conv2", b=b2), sc, cin, cout)
 
     def _attn(self, name, c) -> _Attn:
         lin = lambda p: self._w(f"{name}.{p}.weight").reshape(c, c)
@@ -342,26 +348,46 @@ class AutoencoderKL:
     def release_buffers(self):
         """Drop the activation scratch (a 512x512 image keeps ~0.5 GB of it alive between calls)."""
         self._bufs.clear()
+        self._stats_of.clear()
 
     # Scratch is keyed by role and shape, not by layer: a GroupNorm output is consumed by the very next launch, conv1's
     # output by the next GroupNorm, and the resnet outputs ping-pong between two slots (the input of a resnet is the
     # residual of its conv2, so it must outlive it).
+    def _stats_kw(self, out, n, hw, flat: bool) -> dict:
+        """GroupNorm statistics of `out` accumulated by the GEMM that produces it (EsGemm.gn_ws): the GroupNorm that
+        consumes `out` then only applies.  Needs whole 32-row groups per image and a dense 16-bit output."""
+        G = self.config.norm_num_groups
+        if not self.fuse_gn_stats or hw % 32 or out.shape[1] % G or out.stride(0) != out.shape[1]:
+            return {}
+        self._ws_next = (self._ws_next + 1) % 3
+        ws = self.buf(f"gn.ws{self._ws_next}", n, 2 * G, torch.float32)
+        ws.zero_()
+        self._stats_of[(out.data_ptr(), out.shape[0], out.shape[1])] = ws
+        kw = dict(gn_ws=ws, gn_groups=G)
+        if flat:
+            kw["rows_per_img"] = hw
+        return kw
+
     def _gn(self, x, gb, n, hw, silu):
         out = self.buf("gn", x.shape[0], x.shape[1])
-        ws = self.buf("gn.ws", n, 2 * self.config.norm_num_groups, torch.float32)
-        return ops.groupnorm(x, out, gb[0], gb[1], ws, n, hw, self.config.norm_num_groups, self.config.norm_eps, silu)
+        G, eps = self.config.norm_num_groups, self.config.norm_eps
+        ws = self._stats_of.pop((x.data_ptr(), x.shape[0], x.shape[1]), None)
+        if ws is not None:
+            return ops.groupnorm(x, out, gb[0], gb[1], ws, n, hw, G, eps, silu, stats_ready=True)
+        return ops.groupnorm(x, out, gb[0], gb[1], self.buf("gn.ws", n, 2 * G, torch.float32), n, hw, G, eps, silu)
 
-    def _conv(self, tag, x, cv: _Conv3, n, H, W, residual=None):
+    def _conv(self, tag, x, cv: _Conv3, n, H, W, residual=None, a2=None, b2=None, stats: bool = True):
         out = self.buf(f"conv.{tag}", n * H * W, cv.cout)
-        return ops.gemm(x, cv.w, cv.cout, out=out, taps=9, whn=(W, H, n), bias=cv.b, c1=cv.cin_pad, residual=residual)
+        kw = self._stats_kw(out, n, H * W, False) if stats else {}
+        return ops.gemm(x, cv.w, cv.cout, out=out, taps=9, whn=(W, H, n), bias=cv.b, c1=cv.cin_pad, residual=residual,
+                        a2=a2, b2=b2, **kw)
 
     def _resnet(self, slot: int, x, r: _Res, n, H, W):
         h = self._gn(x, r.n1, n, H * W, True)
         h = self._conv("r1", h, r.c1, n, H, W)
         h = self._gn(h, r.n2, n, H * W, True)
         if r.sc is not None:
-            sc = self.buf("sc", x.shape[0], r.cout)
-            x = ops.gemm(x, r.sc[0], r.cout, out=sc, bias=r.sc[1])
+            return self._conv(f"r2.{slot % 2}", h, r.c2, n, H, W, a2=x, b2=r.sc)
         return self._conv(f"r2.{slot % 2}", h, r.c2, n, H, W, residual=x)
 
     def _attention(self, tag, x, a: _Attn, n, hw):
@@ -379,7 +405,8 @@ class AutoencoderKL:
             ops.softmax_rows(s, p)
             ops.gemm(a.wv, hn[rows], hw, out=vt)                        # V^T = W_v X^T (bias folded into bo)
             ops.gemm(p, vt, C, out=o[rows])                             # O = P V
-        return ops.gemm(o, a.wo, C, out=self.buf(f"{tag}.out", n * hw, C), bias=a.bo, residual=x)
+        out = self.buf(f"{tag}.out", n * hw, C)
+        return ops.gemm(o, a.wo, C, out=out, bias=a.bo, residual=x, **self._stats_kw(out, n, hw, True))
 
     def _mid(self, x, mid, n, H, W):
         x = self._resnet(0, x, mid[0], n, H, W)
@@ -396,6 +423,7 @@ class AutoencoderKL:
         if cin != cfg.in_channels or H % down or W % down:
             raise ValueError(f"encode: expected [n, {cfg.in_channels}, H, W] with H, W multiples of {down}")
         t = f"e{n}x{H}x{W}"
+        self._stats_of.clear()
         a = self.buf(f"{t}.in", n * H * W, self.e_conv_in.cin_pad)
         ops.nchw_to_nhwc(x.to(device=self.dev, dtype=torch.float32).contiguous(), a)
         a = self._conv(f"{t}.in", a, self.e_conv_in, n, H, W)
@@ -407,7 +435,8 @@ class AutoencoderKL:
                 Ho, Wo = H // 2, W // 2
                 col = self.buf(f"{t}.col{i}", n * Ho * Wo, 9 * c)
                 ops.im2col3x3_pad(a, col, n, H, W, c, 2, 0, 1)
-                a = ops.gemm(col, ds[0], c, out=self.buf(f"{t}.ds{i}", n * Ho * Wo, c), bias=ds[1])
+                dso = self.buf(f"{t}.ds{i}", n * Ho * Wo, c)
+                a = ops.gemm(col, ds[0], c, out=dso, bias=ds[1], **self._stats_kw(dso, n, Ho * Wo, True))
                 H, W = Ho, Wo
         a = self._mid(a, self.e_mid, n, H, W)
         a = self._gn(a, self.e_norm_out, n, H * W, True)
@@ -425,6 +454,7 @@ class AutoencoderKL:
         if L != cfg.latent_channels:
             raise ValueError(f"decode: expected {cfg.latent_channels} latent channels, got {L}")
         t = f"d{n}x{H}x{W}"
+        self._stats_of.clear()
         zin = self.buf(f"{t}.z", n * H * W, 64)
         ops.nchw_to_nhwc(z.to(device=self.dev, dtype=torch.float32).contiguous(), zin)
         a = ops.gemm(zin, self.d_post_quant[0], 8, out=self.buf(f"{t}.pq", n * H * W, 8), bias=self.d_post_quant[1])

@@ -19,7 +19,8 @@ def _fake_ops():
     def set_gemm_workspace(nbytes=0, device="cpu"):
         return None
 
-    def gemm(a, b, n, *, out, taps=1, whn=None, bias=None, residual=None, alpha=1.0, c1=None, block_n=0, act=0, **kw):
+    def gemm(a, b, n, *, out, taps=1, whn=None, bias=None, residual=None, alpha=1.0, c1=None, block_n=0, act=0,
+             a2=None, b2=None, gn_ws=None, gn_groups=0, rows_per_img=0, **kw):
         assert not kw, kw
         c1 = c1 if c1 is not None else a.shape[1]
         assert b.is_contiguous() and b.shape[1] == taps * c1 and b.shape[0] >= n
@@ -31,27 +32,46 @@ def _fake_ops():
             x = A.view(ni, h, w, c1).permute(0, 3, 1, 2)
             wt = b[:n].float().view(n, 3, 3, c1).permute(0, 3, 1, 2)
             acc = F.conv2d(x, wt, padding=1).permute(0, 2, 3, 1).reshape(-1, n)
+            rpi = w * h
         else:
             acc = A @ b[:n].float().t()
+            rpi = rows_per_img
+        if a2 is not None:  # second K source (1x1 / centre tap): the resnet shortcut
+            assert b2.is_contiguous() and b2.shape == (n, a2.shape[1]) and a2.shape[0] == a.shape[0]
+            acc = acc + a2.float() @ b2.float().t()
         if bias is not None:
             acc = acc + bias[:n]
         acc = alpha * acc
         if residual is not None:
             acc = acc + residual[:, :n].float()
         out[:, :n] = acc.to(out.dtype)
+        if gn_ws is not None:  # (sum, sumsq) per (image, group) of the OUTPUT, accumulated into a zeroed slot
+            assert rpi > 0 and rpi % 32 == 0 and n % gn_groups == 0 and out.stride(0) == n
+            assert float(gn_ws.abs().max()) == 0.0, "statistics slot must be zeroed by the caller"
+            og = out[:, :n].float().view(-1, rpi, gn_groups, n // gn_groups)
+            gn_ws.view(-1, gn_groups, 2).copy_(torch.stack([og.sum(dim=(1, 3)), (og * og).sum(dim=(1, 3))], dim=-1))
         o.calls.append("gemm")
         return out
 
-    def groupnorm(x0, out, gamma, beta, ws, n_img, hw, groups, eps, silu, **kw):
+    def groupnorm(x0, out, gamma, beta, ws, n_img, hw, groups, eps, silu, stats_ready=False, **kw):
         assert not kw
         C = x0.shape[1]
         assert C % 8 == 0 and C % groups == 0 and ws.numel() >= n_img * groups * 2
         x = x0.float().view(n_img, hw, C).permute(0, 2, 1)
-        y = F.group_norm(x, groups, gamma, beta, eps)
+        if stats_ready:  # normalise with the statistics the producer left in ws (catches stale / mismatched slots)
+            st = ws.view(n_img, groups, 2)
+            cnt = hw * (C // groups)
+            mean = st[..., 0] / cnt
+            var = (st[..., 1] / cnt - mean * mean).clamp_min(0)
+            a = torch.rsqrt(var + eps).repeat_interleave(C // groups, dim=1) * gamma
+            sh = beta - mean.repeat_interleave(C // groups, dim=1) * a
+            y = x * a[:, :, None] + sh[:, :, None]
+        else:
+            y = F.group_norm(x, groups, gamma, beta, eps)
         if silu:
             y = F.silu(y)
         out.copy_(y.permute(0, 2, 1).reshape(n_img * hw, C).to(out.dtype))
-        o.calls.append("groupnorm")
+        o.calls.append("groupnorm_apply" if stats_ready else "groupnorm")
         return out
 
     def nchw_to_nhwc(src, dst):
@@ -146,6 +166,8 @@ def test_encode_schedule_and_packing(vae_pair):
     # a second call reuses the scratch buffers and must give the same answer (no stale state)
     again = mine.encode(x).latent_dist.mode()
     assert torch.equal(again, got.mode())
+    # every GroupNorm whose images hold whole 32-row groups took its statistics from the producing GEMM
+    assert fake.calls.count("groupnorm_apply") > 0
 
 
 def test_decode_schedule_and_packing(vae_pair):
