@@ -123,7 +123,7 @@ def vae_pair(monkeypatch):
     from edgestyle_b200 import vae as V
 
     torch.manual_seed(0)
-    cfg = OracleCfg(block_out_channels=(32, 64, 128, 128))
+    cfg = OracleCfg(block_out_channels=(32, 64, 256, 256))
     ref = OracleVAE(cfg).eval()
     with torch.no_grad():  # default init leaves the norms at identity and the biases tiny: perturb them
         for k, p in ref.named_parameters():
@@ -134,7 +134,7 @@ def vae_pair(monkeypatch):
     fake = _fake_ops()
     monkeypatch.setattr(V, "ops", fake)
     monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
-    mine = V.AutoencoderKL(V.VaeConfig(block_out_channels=(32, 64, 128, 128)), ref.state_dict(), dtype=torch.float32,
+    mine = V.AutoencoderKL(V.VaeConfig(block_out_channels=(32, 64, 256, 256)), ref.state_dict(), dtype=torch.float32,
                            device="cpu")
     return ref, mine, fake
 
