@@ -116,20 +116,6 @@ __global__ void gn_apply_kernel(const T* __restrict__ x0, int c0, long long ld0,
     src = x1 + static_cast<long long>(img) * hw * ld1 + (ch - c0);
     ld = ld1;
   }
-  const int per = (hw + gridDim.x - 1) / gridDim.x;
-  const int p0 = blockIdx.x * per;
-  const int p1 = min(hw, p0 + per);
-  const int ny = blockDim.y;
-  int p = p0 + threadIdx.y;
-  // software pipeline: the first four 16 B loads of this thread are in flight while it derives its per-channel
-  // scale / shift from the statistics (a dependent ws -> rsqrt chain), and every later group is requested before
-  // the current one is normalised and stored
-  uint4 u[4];
-  bool have = p + 3 * ny < p1;
-  if (have) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) u[q] = *reinterpret_cast<const uint4*>(src + static_cast<long long>(p + q * ny) * ld);
-  }
   float a[8], b[8];
   const float inv_n = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
 #pragma unroll
@@ -144,20 +130,18 @@ __global__ void gn_apply_kernel(const T* __restrict__ x0, int c0, long long ld0,
     b[j] = beta[ch + j] - mean * a[j];
   }
   T* dst = out + static_cast<long long>(img) * hw * ldo + ch;
-  while (have) {
-    uint4 cur[4];
+  const int per = (hw + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per;
+  const int p1 = min(hw, p0 + per);
+  const int ny = blockDim.y;
+  int p = p0 + threadIdx.y;
+  for (; p + 3 * ny < p1; p += 4 * ny) {
+    uint4 u[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) cur[q] = u[q];
-    const int pc = p;
-    p += 4 * ny;
-    have = p + 3 * ny < p1;
-    if (have) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) u[q] = *reinterpret_cast<const uint4*>(src + static_cast<long long>(p + q * ny) * ld);
-    }
+    for (int q = 0; q < 4; ++q) u[q] = *reinterpret_cast<const uint4*>(src + static_cast<long long>(p + q * ny) * ld);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const uint32_t w[4] = {cur[q].x, cur[q].y, cur[q].z, cur[q].w};
+      const uint32_t w[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
       float f[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -170,7 +154,7 @@ __global__ void gn_apply_kernel(const T* __restrict__ x0, int c0, long long ld0,
         const float y = f[j] * a[j] + b[j];
         f[j] = silu ? silu_f(y) : y;
       }
-      store8<T>(dst + static_cast<long long>(pc + q * ny) * ldo, f);
+      store8<T>(dst + static_cast<long long>(p + q * ny) * ldo, f);
     }
   }
   for (; p < p1; p += ny) {
