@@ -7,7 +7,8 @@ Reference call sites: `VAEControlNetConditioningEmbedding.forward`, /root/refere
 edgestyle_pipeline.py:552-557.  The class keeps the diffusers surface those lines use (`encode(x).latent_dist.sample()
 / .mode()`, `decode(z).sample`, `config.scaling_factor`) and takes a diffusers-layout `vae/` state dict.
 
-Everything runs channels-last on the library's kernels (no torch arithmetic):
+encode / decode / sample run channels-last on the library's kernels, with no torch arithmetic (the `logvar` / `std`
+accessors of the distribution, which the reference path never reads, are plain torch views of the moments):
   * 3x3 convolutions: es_gemm implicit GEMM (tcgen05); the stride-2 `Downsample2D(padding=0)` convs pad (0, 1, 0, 1):
     es_im2col3x3_pad + flat es_gemm; `Upsample2D`: es_upsample2x + es_gemm.
   * GroupNorm(32, eps 1e-6) + SiLU: the statistics come from the epilogue of the GEMM that produced the tensor
