@@ -12,7 +12,10 @@ fixtures for this path, and its arithmetic lives in the third-party ``diffusers=
 * the pure-torch slices of the reference that execute without diffusers (``ControlNetBlock``,
   ``interleave_tensors``; model/edgestyle_multicontrolnet.py:23-63,479-514) were run in the
   build container by ``tests/golden/make_golden.py`` and their outputs are committed under
-  ``tests/golden/`` -- ``oracle.merge`` is checked against them bit-for-bit-tolerance;
+  ``tests/golden/`` -- ``oracle.merge`` is checked against them bit-for-bit-tolerance; likewise
+  ``VAEControlNetConditioningEmbedding`` + ``_tie_weights`` (model/controllora.py:28-56, run by
+  ``tests/golden/make_golden_vae_cond.py`` around the oracle's VAE) pin ``oracle.controllora``'s embedder: zeroed
+  ``conv_vae_out`` aliasing ``conv_in``, re-tied to the UNet's conv_in, global-RNG sample x 0.18215;
 * the published parameter counts (UNet 859 520 964, ControlNet 361 279 120) and the residual
   shape table (model/edgestyle_onnx_pipeline.py:244-258);
 * algebraic identities (LoRA fuse == unfused, zero zero-convs => cond-independent UNet, DDIM

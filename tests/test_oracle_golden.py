@@ -175,3 +175,36 @@ def test_vae_oracle_published_counts_and_identities():
         folded = (p @ (t @ a.to_v.weight.t())) @ a.to_out[0].weight.t() + (a.to_out[0].bias + a.to_out[0].weight @ a.to_v.bias)
         assert torch.allclose(h + folded.transpose(1, 2).reshape(1, 64, 4, 4), a(h), atol=1e-10)
         assert m.decode(d.mode()).sample.shape == (1, 3, 32, 32)
+
+
+def test_vae_conditioning_embedder_matches_reference_golden():
+    """`VAEControlNetConditioningEmbedding` + `_tie_weights` executed from the reference's own source text
+    (tests/golden/make_golden_vae_cond.py; /root/reference/model/controllora.py:28-56) vs oracle.controllora."""
+    import os
+
+    from torch import nn
+
+    from oracle.controllora import VAEControlNetConditioningEmbedding, _tie_weights
+    from oracle.vae import AutoencoderKL, VaeConfig
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vae_cond_golden.pt"))
+    vae = AutoencoderKL(VaeConfig(block_out_channels=tuple(g["chans"]), layers_per_block=1)).eval()
+    vae.load_state_dict(g["vae"])
+    conv_in = nn.Conv2d(4, 16, 3, padding=1)
+    emb = VAEControlNetConditioningEmbedding(conv_unet=conv_in, autoencoder=vae)
+    assert float(conv_in.weight.detach().abs().max()) == 0.0  # zero_module (:36)
+    unet_conv_in = nn.Conv2d(4, 16, 3, padding=1)
+    unet_conv_in.load_state_dict(g["conv_in"])
+    _tie_weights(unet_conv_in, conv_in)
+    assert emb.conv_vae_out.weight is unet_conv_in.weight
+    torch.manual_seed(g["seed"])
+    with torch.no_grad():
+        out = emb(g["image"])
+    assert torch.allclose(out, g["out"], atol=1e-6, rtol=1e-6)
+    # and piecewise: the draw is `randn(mean.shape)` from the global RNG, scaled by 0.18215, through the tied conv
+    torch.manual_seed(g["seed"])
+    with torch.no_grad():
+        d = vae.encode(g["image"]).latent_dist
+        noise = torch.randn(d.mean.shape)
+        want = torch.nn.functional.conv2d(d.sample(noise=noise) * 0.18215, unet_conv_in.weight, unet_conv_in.bias, padding=1)
+    assert torch.allclose(want, g["out"], atol=1e-6, rtol=1e-6)
