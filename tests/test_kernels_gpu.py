@@ -517,6 +517,35 @@ def test_merge_golden_fixture():
         _close(dst, want, 1e-2, 1e-2, "merge golden")
 
 
+def test_merge_multi_forward_golden_fixture():
+    """Outputs of the reference's own `EdgeStyleMultiControlNetModel.forward` on stub nets
+    (tests/golden/make_golden_multi_forward.py): per-net conditioning scales, net pairing order and the per-level blocks
+    through the merge kernel (scales applied inside the kernel, `EsMerge.scale`)."""
+    from edgestyle_b200 import ops
+    from edgestyle_b200.engine import pack_merge_block
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "multi_forward_golden.pt"))
+    B = g["images"][0].shape[0]
+    wants = g["down"] + [g["mid"]]
+    done = 0
+    for li, (C, s) in enumerate(zip(g["ch"] + [32], g["hw"] + [1])):
+        if s * s < 4:
+            continue  # 1x1 levels only exist in this scaled-down fixture
+        prm = pack_merge_block(g["blocks"][li], C, s, s, torch.float16, DEV)
+        res16 = []
+        for k in range(6):
+            shift = g["images"][k].mean(dim=(1, 2, 3)).view(-1, 1, 1, 1)
+            r = g["bases"][k][li] + shift  # what net k returns before its conditioning_scale
+            res16.append(r.to(DEV).permute(0, 2, 3, 1).reshape(-1, C).half().contiguous())
+        stats = torch.empty(B, 4, device=DEV, dtype=torch.float64)
+        z = torch.empty(B * s * s, C, device=DEV, dtype=torch.float32)
+        dst = torch.empty(B * s * s, C, device=DEV, dtype=torch.float16)
+        ops.merge(res16, g["scales"], prm, stats, z, B, s * s, C, dst)
+        _close(dst, wants[li].to(DEV).permute(0, 2, 3, 1).reshape(-1, C), 1e-2, 1e-2, f"multi forward golden, level {li}")
+        done += 1
+    assert done == 9
+
+
 # ------------------------------------------------------------------------------------------ misc
 def test_layout_im2col_upsample_add():
     from edgestyle_b200 import ops

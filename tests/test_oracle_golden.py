@@ -208,3 +208,48 @@ def test_vae_conditioning_embedder_matches_reference_golden():
         noise = torch.randn(d.mean.shape)
         want = torch.nn.functional.conv2d(d.sample(noise=noise) * 0.18215, unet_conv_in.weight, unet_conv_in.bias, padding=1)
     assert torch.allclose(want, g["out"], atol=1e-6, rtol=1e-6)
+
+
+def test_multi_controlnet_forward_matches_reference_golden():
+    """`EdgeStyleMultiControlNetModel.forward` executed from the reference's own source text on stub nets
+    (tests/golden/make_golden_multi_forward.py; edgestyle_multicontrolnet.py:116-171) vs oracle.merge: routing of the
+    conditioning images / scales to the nets, level-wise zip, channel interleave, per-level ControlNetBlocks."""
+    import os
+
+    from torch import nn
+
+    from oracle.merge import EdgeStyleMultiControlNetModel, closed_form_block, residual_shapes
+    from oracle.sd15 import SD15Config
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "multi_forward_golden.pt"))
+    cfg = SD15Config(block_out_channels=(8, 16, 32, 32))
+    assert [(c, s, s) for c, s in zip(g["ch"] + [32], g["hw"] + [1])] == residual_shapes(cfg, 8, 8)
+
+    class StubNet(nn.Module):
+        def __init__(self, base):
+            super().__init__()
+            self.base = base
+
+        def forward(self, sample, timestep, encoder_hidden_states, controlnet_cond, conditioning_scale, guess_mode=False):
+            shift = controlnet_cond.mean(dim=(1, 2, 3)).view(-1, 1, 1, 1)
+            outs = [(b + shift) * conditioning_scale for b in self.base]
+            return outs[:-1], outs[-1]
+
+    multi = EdgeStyleMultiControlNetModel([StubNet(b) for b in g["bases"]], cfg, (8, 8))
+    for blk, sd in zip(list(multi.multi_controlnet_down_blocks) + [multi.multi_controlnet_mid_block], g["blocks"]):
+        blk.load_state_dict(sd)
+    with torch.no_grad():
+        down, mid = multi(torch.zeros(2, 4, 8, 8), torch.tensor(1), torch.zeros(2, 77, 8), g["images"], g["scales"])
+    assert len(down) == 12
+    for a, b in zip(list(down) + [mid], g["down"] + [g["mid"]]):
+        assert torch.allclose(a, b, atol=1e-5, rtol=1e-5)
+    # the closed form the CUDA merge kernel implements (no interleaved tensor), per level
+    blocks = list(multi.multi_controlnet_down_blocks) + [multi.multi_controlnet_mid_block]
+    with torch.no_grad():
+        for li, blk in enumerate(blocks):
+            res = []
+            for k in range(6):
+                shift = g["images"][k].mean(dim=(1, 2, 3)).view(-1, 1, 1, 1)
+                res.append((g["bases"][k][li] + shift) * g["scales"][k])
+            want = (g["down"] + [g["mid"]])[li]
+            assert torch.allclose(closed_form_block(blk, res), want, atol=2e-5, rtol=1e-4), li
