@@ -15,7 +15,9 @@ fixtures for this path, and its arithmetic lives in the third-party ``diffusers=
   ``tests/golden/`` -- ``oracle.merge`` is checked against them bit-for-bit-tolerance; likewise
   ``VAEControlNetConditioningEmbedding`` + ``_tie_weights`` (model/controllora.py:28-56, run by
   ``tests/golden/make_golden_vae_cond.py`` around the oracle's VAE) pin ``oracle.controllora``'s embedder: zeroed
-  ``conv_vae_out`` aliasing ``conv_in``, re-tied to the UNet's conv_in, global-RNG sample x 0.18215;
+  ``conv_vae_out`` aliasing ``conv_in``, re-tied to the UNet's conv_in, global-RNG sample x 0.18215; and
+  ``EdgeStyleMultiControlNetModel.forward`` (model/edgestyle_multicontrolnet.py:116-171) was run on stub nets by
+  ``tests/golden/make_golden_multi_forward.py`` and pins ``oracle.merge.EdgeStyleMultiControlNetModel.forward``;
 * the published parameter counts (UNet 859 520 964, ControlNet 361 279 120) and the residual
   shape table (model/edgestyle_onnx_pipeline.py:244-258);
 * algebraic identities (LoRA fuse == unfused, zero zero-convs => cond-independent UNet, DDIM
