@@ -18,6 +18,8 @@ fixtures for this path, and its arithmetic lives in the third-party ``diffusers=
   ``conv_vae_out`` aliasing ``conv_in``, re-tied to the UNet's conv_in, global-RNG sample x 0.18215; and
   ``EdgeStyleMultiControlNetModel.forward`` (model/edgestyle_multicontrolnet.py:116-171) was run on stub nets by
   ``tests/golden/make_golden_multi_forward.py`` and pins ``oracle.merge.EdgeStyleMultiControlNetModel.forward``;
+  ``CachedControlNetModel.forward`` (model/controllora.py:59-287) was run over the oracle's sub-modules by
+  ``tests/golden/make_golden_controlnet_forward.py`` and pins ``oracle.sd15.ControlNetModel.forward``;
 * the published parameter counts (UNet 859 520 964, ControlNet 361 279 120) and the residual
   shape table (model/edgestyle_onnx_pipeline.py:244-258);
 * algebraic identities (LoRA fuse == unfused, zero zero-convs => cond-independent UNet, DDIM

@@ -253,3 +253,32 @@ def test_multi_controlnet_forward_matches_reference_golden():
                 res.append((g["bases"][k][li] + shift) * g["scales"][k])
             want = (g["down"] + [g["mid"]])[li]
             assert torch.allclose(closed_form_block(blk, res), want, atol=2e-5, rtol=1e-4), li
+
+
+def test_controlnet_forward_matches_reference_golden():
+    """`CachedControlNetModel.forward` executed from the reference's own source text over the oracle's sub-modules
+    (tests/golden/make_golden_controlnet_forward.py; controllora.py:59-287) vs oracle.sd15.ControlNetModel.forward:
+    timestep forms, embedder skipping, skip order, zero-convs, conditioning_scale, guess_mode gains."""
+    import importlib.util
+    import os
+
+    from oracle.sd15 import ControlNetModel
+
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_controlnet_forward",
+                                                  os.path.join(here, "make_golden_controlnet_forward.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    g = torch.load(os.path.join(here, "controlnet_forward_golden.pt"))
+    net = ControlNetModel(SD15Config(**g["cfg"])).eval()
+    gen.seeded_fill(net, g["weight_seed"])
+    cs = gen.cases()
+    assert len(cs) == len(g["outs"]) == 4
+    with torch.no_grad():
+        for c, want in zip(cs, g["outs"]):
+            down, mid = net(c["sample"], c["timestep"], c["ehs"], c["cond"], c["scale"], guess_mode=c["guess_mode"])
+            assert len(down) == 12
+            for a, b in zip(list(down) + [mid], want["down"] + [want["mid"]]):
+                assert a.shape == b.shape and torch.allclose(a, b, atol=1e-6, rtol=1e-5)
+    assert float(g["outs"][0]["mid"].abs().max()) > 1e-3          # the fixture is not trivially zero
+    assert float(g["outs"][3]["mid"].abs().max()) == 0.0          # conditioning_scale 0
