@@ -222,3 +222,47 @@ def test_fuse_matches_oracle_fuse_lora(models, tmp_path):
     multi = EdgeStyleMultiControlNetModel([agn, pose, clo, pose, clo, pose], models.controlnet.merge_state_dict(), (8, 8))
     multi.fuse()
     assert multi._fused and multi.nets[0] is agn  # nets stay ControlLoRA objects: conditioning stays cacheable
+
+
+def test_checkpoint_directory_matches_reference_save_pretrained(models, tmp_path):
+    """N1 against the reference's own `save_pretrained` / `state_dict` (edgestyle_multicontrolnet.py:173-282, executed
+    from its source text on stub nets by tests/golden/make_golden_checkpoint_dir.py): the mirror reads the file the
+    reference wrote, and writes the same file name, keys, tensors and `controlnet_{idx}` sub-directories."""
+    import json
+    import os
+    import shutil
+
+    from safetensors.torch import load_file
+
+    from edgestyle_b200.model import (CachedControlNetModel, ControlLoRAModel, EdgeStyleMultiControlNetModel,
+                                      UNet2DConditionModel)
+
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    meta = json.load(open(os.path.join(here, "checkpoint_dir_golden.json")))
+    golden = load_file(os.path.join(here, "checkpoint_dir_golden.safetensors"))
+    assert sorted(golden) == meta["keys"] and meta["listing"] == ["diffusion_pytorch_model.safetensors"]
+    cfg = C.UNetConfig.from_any(TINY)
+    assert set(C.merge_spec(cfg, 8, 8)) == set(golden)
+    assert all(tuple(golden[k].shape) == tuple(s) for k, s in C.merge_spec(cfg, 8, 8).items())
+    unet = UNet2DConditionModel(cfg, models.unet.state_dict())
+    agn = ControlLoRAModel(cfg, models.lora_agnostic.state_dict(), 4, unet=unet)
+    clo = ControlLoRAModel(cfg, models.lora_clothes.state_dict(), 4, unet=unet)
+    pose = CachedControlNetModel(cfg, models.openpose.state_dict())
+    # a directory as the reference leaves it: its top-level file + one sub-directory per distinct pattern index
+    d = tmp_path / "ref_written"
+    d.mkdir()
+    shutil.copy(os.path.join(here, "checkpoint_dir_golden.safetensors"), d / "diffusion_pytorch_model.safetensors")
+    saved = [c for c in meta["calls"] if c[0] == "save_pretrained"]
+    assert [c[2] for c in saved] == ["controlnet_0", "controlnet_1"] and all(c[3] is None for c in saved)  # VAE detached
+    agn.save_pretrained(str(d / "controlnet_0"))
+    clo.save_pretrained(str(d / "controlnet_1"))
+    multi = EdgeStyleMultiControlNetModel.from_pretrained(str(d), load_pattern=meta["pattern"],
+                                                          controlnet_class=ControlLoRAModel,
+                                                          static_controlnets=[None, pose, None, pose, None, pose],
+                                                          latent_hw=(8, 8))
+    assert all(torch.equal(multi.state_dict()[k], v) for k, v in golden.items())
+    out = tmp_path / "mirror_written"
+    multi.save_pretrained(str(out), save_pattern=meta["pattern"])
+    assert sorted(os.listdir(out)) == sorted(meta["listing"] + [c[2] for c in saved])
+    mine = load_file(str(out / "diffusion_pytorch_model.safetensors"))
+    assert set(mine) == set(golden) and all(torch.equal(mine[k], golden[k]) for k in golden)
