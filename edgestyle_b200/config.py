@@ -184,13 +184,27 @@ def lora_linear_names(cfg: UNetConfig) -> List[str]:
     return [k[: -len(".weight")] for k, s in encoder_spec(cfg).items() if k.endswith(".weight") and len(s) == 2]
 
 
-def lora_spec(cfg: UNetConfig, rank: int) -> Dict[str, Tuple[int, ...]]:
+def lora_conv_names(cfg: UNetConfig) -> List[str]:
+    """Every nn.Conv2d under ControlLoRAModel._skip_layers: conv_in, resnet conv1 / conv2 / conv_shortcut, the
+    down-samplers and the transformers' 1x1 proj_in / proj_out (/root/reference/model/controllora.py:538-575)."""
+    return [k[: -len(".weight")] for k, s in encoder_spec(cfg).items() if k.endswith(".weight") and len(s) == 4]
+
+
+def lora_spec(cfg: UNetConfig, rank: int, conv_rank: int = 0) -> Dict[str, Tuple[int, ...]]:
+    """LoRA tensors a ControlLoRAModel owns.  conv_rank > 0 adds a LoRAConv2dLayer on every convolution -- whose
+    rank is `rank` (lora_linear_rank), not conv_rank: the reference passes rank=lora_linear_rank at controllora.py:569
+    and lora_conv2d_rank only switches the branch on."""
     enc = encoder_spec(cfg)
     d = {}
     for n in lora_linear_names(cfg):
         out_f, in_f = enc[n + ".weight"]
         d[f"{n}.lora_layer.down.weight"] = (rank, in_f)
         d[f"{n}.lora_layer.up.weight"] = (out_f, rank)
+    if conv_rank > 0:
+        for n in lora_conv_names(cfg):
+            cout, cin, kh, kw = enc[n + ".weight"]
+            d[f"{n}.lora_layer.down.weight"] = (rank, cin, kh, kw)
+            d[f"{n}.lora_layer.up.weight"] = (cout, rank, 1, 1)
     return d
 
 

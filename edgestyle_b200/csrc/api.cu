@@ -74,4 +74,4 @@ extern "C" int es_set_pdl(int enabled) {
   return old;
 }
 extern "C" const char* es_last_error(void) { return es::g_err; }
-extern "C" int es_abi_version(void) { return 1; }
+extern "C" int es_abi_version(void) { return 2; }

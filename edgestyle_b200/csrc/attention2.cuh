@@ -1,0 +1,463 @@
+// es_attention, second generation: QT query tiles (128 rows each) per CTA, one softmax warpgroup per tile, one TMA
+// warp and one MMA warp per CTA.  What changed against attention_kernel (attention.cu) and why:
+//
+//   * the MUFU pipe was 50 % busy with 2 softmax warps per SM sub-partition (one warpgroup per CTA, two CTAs per SM):
+//     every warp sat half of its time in the tcgen05.ld -> ex2 -> pack -> st.shared -> fence -> mbarrier chain.  Two
+//     query tiles per CTA (K/V tiles shared, loaded once) and still two CTAs per SM give FOUR softmax warps per
+//     sub-partition to hide that chain.
+//   * S is single-buffered per tile (64 fp32 columns) and released EARLY: as soon as a thread has pulled its row into
+//     registers (already shifted and packed to 16-bit pairs) the warpgroup arrives on s_free and the MMA warp issues
+//     Q K^T of the next key tile into the same columns, while the exponentials of the current one run.
+//   * fp16: the exponent argument x = s * scale*log2e - m is formed in fp32, packed to f16x2 and exponentiated with
+//     ex2.approx.ftz.f16x2 -- TWO exponentials per MUFU operation, and the result is already the packed P operand of
+//     the P V MMA (no separate conversion).  Row sums: HADD2 tree over 16 pairs, then fp32.  (bf16 keeps fp32 ex2:
+//     an 8-bit-mantissa argument would cost ~1 % per probability.)
+//   * P is single-buffered per tile: the write of P(j+1) waits for the commit of P(j) V (pv_done), which also is the
+//     "O is stable" condition the rare rescale path needs.
+//
+//   TMEM columns: [t * 64, +64) = S of tile t, [QT * 64 + t * dN, +dN) = O of tile t  (d = 40: 224 -> 256 columns,
+//   two CTAs per SM).
+#pragma once
+
+namespace es {
+
+constexpr int kAtt2KV = 64;  // keys per K/V tile
+
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.ftz.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t hadd2_u(uint32_t a, uint32_t b) {
+  uint32_t y;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b));
+  return y;
+}
+__device__ __forceinline__ uint32_t hmax2_u(uint32_t a, uint32_t b) {
+  uint32_t y;
+  asm("max.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b));
+  return y;
+}
+// pack two fp32 into f16x2 (lo = a, hi = b)
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  uint32_t y;
+  asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(y) : "f"(a), "f"(b));
+  return y;
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
+
+template <typename T>
+struct AttPacked {
+  static constexpr bool value = false;
+};
+template <>
+struct AttPacked<__half> {
+  static constexpr bool value = true;
+};
+
+template <typename T, int NA, int QT>
+__global__ void __launch_bounds__(64 + 128 * QT, (NA == 1) ? 2 : 1)
+attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const AttParams p) {
+  constexpr int kKV = kAtt2KV;
+  constexpr int kKVAtom = kKV * 128;  // bytes of one 64-column atom of a K / V tile
+  constexpr bool kPacked = AttPacked<T>::value;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;                              // QT tiles x NA atoms x [128 rows x 128 B]
+  uint8_t* sK = sQ + QT * NA * kAtomBytes;         // 2 stages x NA atoms x [64 rows x 128 B]
+  uint8_t* sV = sK + 2 * NA * kKVAtom;             // 2 stages x NA atoms x [64 rows x 128 B]
+  uint8_t* sP = sV + 2 * NA * kKVAtom;             // QT x [128 rows x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + QT * kAtomBytes);
+  uint64_t& q_full = bars[0];
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [QT] MMA -> softmax: S(j) complete
+  uint64_t* s_free = bars + 11;   // [QT] softmax -> MMA: S(j) is in registers (128 arrivals)
+  uint64_t* p_full = bars + 13;   // [QT] softmax -> MMA: P(j) in smem (128 arrivals)
+  uint64_t* pv_done = bars + 15;  // [QT] MMA -> softmax: P(j) V retired (P buffer free, O stable)
+  uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 17);
+
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (128 * QT);
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_tiles = (p.nkv + kKV - 1) / kKV;
+  const uint32_t tmem_cols = p.tmem_cols;
+  const int o_col0 = QT * kKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(&q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int t = 0; t < QT; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&s_free[t], 128);
+      mbar_init(&p_full[t], 128);
+      mbar_init(&pv_done[t], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();  // PDL: everything above overlaps the previous kernel's tail
+
+  if (warp == 0) {
+    // ================================ TMA producer ==============================================================
+    if (lane == 0) {
+      mbar_expect_tx(&q_full, QT * NA * kAtomBytes);
+#pragma unroll
+      for (int t = 0; t < QT; ++t)
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+          tma_load_4d(sQ + (t * NA + a) * kAtomBytes, &tmQ, &q_full, a * 64, head, q0 + t * 128, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_expect_tx(&k_full[s], NA * kKVAtom);
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+          tma_load_4d(sK + (s * NA + a) * kKVAtom, &tmK, &k_full[s], a * 64, head, j * kKV, b);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_expect_tx(&v_full[s], NA * kKVAtom);
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+          tma_load_4d(sV + (s * NA + a) * kKVAtom, &tmV, &v_full[s], a * 64, head, j * kKV, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================================================
+    if (lane == 0) {
+      const uint32_t idesc_qk = make_idesc_f16(128, kKV, Cvt<T>::kFmt, 0, 0);
+      const uint32_t idesc_pv = make_idesc_f16(128, p.dN, Cvt<T>::kFmt, 0, 1);
+      const int kq = (p.d + 15) / 16;  // MMAs along the head dim
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+      // a second tile that lies entirely beyond nq still runs (its rows are never stored): uniform control flow
+      auto issue_qk = [&](int t, int j) {
+        const int s = j & 1;
+        for (int k = 0; k < kq; ++k) {
+          const uint64_t ad = smem_desc_sw128(aQ + (t * NA + (k >> 2)) * kAtomBytes, 16, 1024) + 2 * (k & 3);
+          const uint64_t bd = smem_desc_sw128(aK + (s * NA + (k >> 2)) * kKVAtom, 16, 1024) + 2 * (k & 3);
+          umma_f16(tmem_base + t * kKV, ad, bd, idesc_qk, k != 0);
+        }
+        umma_commit(&s_full[t]);
+      };
+      mbar_wait(&q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+#pragma unroll
+      for (int t = 0; t < QT; ++t) issue_qk(t, 0);
+      umma_commit(&k_empty[0]);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        if (j + 1 < n_tiles) {  // S(j+1) = Q K(j+1)^T as soon as S(j) has been pulled into registers
+          mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+#pragma unroll
+          for (int t = 0; t < QT; ++t) {
+            mbar_wait(&s_free[t], j & 1);
+            tc_fence_after();
+            issue_qk(t, j + 1);
+          }
+          umma_commit(&k_empty[(j + 1) & 1]);
+        }
+        mbar_wait(&v_full[s], ph);
+#pragma unroll
+        for (int t = 0; t < QT; ++t) {
+          mbar_wait(&p_full[t], j & 1);  // P(j) of tile t in smem
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kKV / 16; ++k) {
+            const uint64_t ad = smem_desc_sw128(aP + t * kAtomBytes, 16, 1024) + 2 * k;
+            // V: MN-major, 16 keys = 2048 B along K; N atoms (64 of d) kKVAtom apart
+            const uint64_t bd = smem_desc_sw128(aV + s * NA * kKVAtom + k * 2048, kKVAtom, 1024);
+            umma_f16(tmem_base + o_col0 + t * p.dN, ad, bd, idesc_pv, (j | k) != 0);
+          }
+          umma_commit(&pv_done[t]);
+        }
+        umma_commit(&v_empty[s]);
+      }
+    }
+  } else {
+    // ================================ softmax: warpgroup t owns query tile t, thread r its row r ===============
+    const int t = (warp - 2) >> 2;
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+    const uint32_t t_s = t_row + t * kKV;
+    const uint32_t t_o = t_row + o_col0 + t * p.dN;
+    float m_run = -INFINITY;  // shift of the exponent (scaled, log2 units): within 2^kSlack of the running row max
+    float l_run = 0.f;        // running row sum of P (fp32)
+    const float sl2 = p.scale_log2;
+    constexpr float kSlack = 8.0f;
+    uint8_t* prow = sP + t * kAtomBytes + r * 128;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int kv_valid = min(kKV, p.nkv - j * kKV);
+      const bool full_tile = kv_valid == kKV;
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t va[32], vb[32];
+      if (j == 0) {  // first tile: a max pass to establish the shift
+        float mx = -INFINITY;
+        tmem_ld_x32(t_s, va);
+        tmem_ld_wait();
+        tmem_ld_x32(t_s + 32, vb);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (full_tile || i < kv_valid) mx = fmaxf(mx, __uint_as_float(va[i]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (full_tile || 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(vb[i]));
+        m_run = mx * sl2;
+      } else {
+        tmem_ld_x32(t_s, va);
+        tmem_ld_wait();
+        tmem_ld_x32(t_s + 32, vb);
+      }
+      uint32_t pk[32];  // packed 16-bit pairs: exponent arguments (fp16 path) or probabilities
+      float sum = 0.f;
+      bool pv_waited = false;
+      if (kPacked) {
+        // ---- fp16: x = s * scale - m in fp32 -> f16x2; the tile max is taken on the packed values -------------
+        auto pack_x = [&](const uint32_t (&v)[32], int c, float neg_m, uint32_t* out) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float a0 = fmaf(__uint_as_float(v[i]), sl2, neg_m), a1 = fmaf(__uint_as_float(v[i + 1]), sl2, neg_m);
+            if (!full_tile) {
+              if (c + i >= kv_valid) a0 = -60000.f;
+              if (c + i + 1 >= kv_valid) a1 = -60000.f;
+            }
+            out[i >> 1] = pack_h2(a0, a1);
+          }
+        };
+        float neg_m = -m_run;
+        if (j > 0) tmem_ld_wait();  // va complete (vb in flight)
+        pack_x(va, 0, neg_m, pk);
+        tmem_ld_wait();
+        pack_x(vb, 32, neg_m, pk + 16);
+        if (j > 0) {
+          uint32_t mx2 = pk[0];
+#pragma unroll
+          for (int i = 1; i < 32; ++i) mx2 = hmax2_u(mx2, pk[i]);
+          const float2 mf = unpack_h2(mx2);
+          const float rel = fmaxf(mf.x, mf.y);  // tile max relative to the current shift
+          if (__any_sync(0xffffffffu, rel > kSlack)) {
+            // rare path: raise the shift of the rows that need it, rescale their O, redo the arguments from TMEM
+            mbar_wait(&pv_done[t], (j - 1) & 1);  // P(j-1) V retired: O is stable, P is free
+            pv_waited = true;
+            tc_fence_after();
+            const float m_new = rel > 0.f ? m_run + rel : m_run;
+            const float alpha = ex2_approx(m_run - m_new);
+#pragma unroll 1
+            for (int c = 0; c < p.dN; c += 16) {
+              uint32_t o[16];
+              tmem_ld_x16(t_o + c, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_x16(t_o + c, o);
+            }
+            tmem_st_wait();
+            l_run *= alpha;
+            m_run = m_new;
+            neg_m = -m_run;
+            tmem_ld_x32(t_s, va);
+            tmem_ld_wait();
+            tmem_ld_x32(t_s + 32, vb);
+            pack_x(va, 0, neg_m, pk);
+            tmem_ld_wait();
+            pack_x(vb, 32, neg_m, pk + 16);
+          }
+        }
+        // S(j) is in registers: the MMA warp may overwrite it with S(j+1)
+        tc_fence_before();
+        mbar_arrive(&s_free[t]);
+        // ---- P = 2^x, two per MUFU op; row sum through an HADD2 tree per 16 pairs, then fp32 ----------------
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pk[i] = ex2_f16x2(pk[i]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t s8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s8[i] = hadd2_u(pk[h * 16 + 2 * i], pk[h * 16 + 2 * i + 1]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) s8[i] = hadd2_u(s8[2 * i], s8[2 * i + 1]);
+          const float2 f0 = unpack_h2(hadd2_u(s8[0], s8[1])), f1 = unpack_h2(hadd2_u(s8[2], s8[3]));
+          sum += (f0.x + f0.y) + (f1.x + f1.y);
+        }
+      } else {
+        // ---- bf16 (and any other storage type): fp32 exponentials, one per score -------------------------------
+        auto tile_max = [&](const uint32_t (&v)[32], int c, float mx) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            if (full_tile) {
+              mx = fmax3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+            } else {
+              if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+              if (c + i + 1 < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i + 1]));
+            }
+          }
+          return mx;
+        };
+        float mx = -INFINITY;
+        if (j > 0) {
+          tmem_ld_wait();
+          mx = tile_max(va, 0, mx);
+        }
+        tmem_ld_wait();
+        if (j > 0) {
+          mx = tile_max(vb, 32, mx);
+          const float m_tile = mx * sl2;
+          if (__any_sync(0xffffffffu, m_tile > m_run + kSlack)) {
+            mbar_wait(&pv_done[t], (j - 1) & 1);
+            pv_waited = true;
+            tc_fence_after();
+            const float m_new = fmaxf(m_run, m_tile);
+            const float alpha = ex2_approx(m_run - m_new);
+#pragma unroll 1
+            for (int c = 0; c < p.dN; c += 16) {
+              uint32_t o[16];
+              tmem_ld_x16(t_o + c, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_x16(t_o + c, o);
+            }
+            tmem_st_wait();
+            l_run *= alpha;
+            m_run = m_new;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&s_free[t]);
+        const float neg_m = -m_run;
+        float s0 = 0.f, s1 = 0.f;
+        auto emit = [&](const uint32_t (&v)[32], int c, uint32_t* out) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, neg_m));
+            float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, neg_m));
+            if (!full_tile) {
+              if (c + i >= kv_valid) p0 = 0.f;
+              if (c + i + 1 >= kv_valid) p1 = 0.f;
+            }
+            s0 += p0;
+            s1 += p1;
+            out[i >> 1] = Cvt<T>::pack2(p0, p1);
+          }
+        };
+        emit(va, 0, pk);
+        emit(vb, 32, pk + 16);
+        sum = s0 + s1;
+      }
+      l_run += sum;
+      // ---- P(j) -> smem (canonical K-major SWIZZLE_128B: row r at r * 128 B, 16 B chunk index XOR (r & 7)) ----------
+      if (j > 0 && !pv_waited) mbar_wait(&pv_done[t], (j - 1) & 1);  // the MMAs reading P(j-1) have retired
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const int chunk = q4 ^ (r & 7);
+        *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+      }
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      mbar_arrive(&p_full[t]);
+    }
+    // ---- epilogue: O / l ---------------------------------------------------------------------------------------
+    mbar_wait(&pv_done[t], (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int qrow = q0 + t * 128 + r;
+    const bool row_ok = qrow < p.nq;
+    T* optr = reinterpret_cast<T*>(p.out) + static_cast<long long>(b) * p.bso + static_cast<long long>(qrow) * p.ldo +
+              head * p.d;
+#pragma unroll 1
+    for (int c = 0; c < p.dN; c += 16) {
+      uint32_t o[16];
+      tmem_ld_x16(t_o + c, o);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (c + h * 8 < p.d) {
+            uint4 u;
+            u.x = Cvt<T>::pack2(__uint_as_float(o[h * 8 + 0]) * inv_l, __uint_as_float(o[h * 8 + 1]) * inv_l);
+            u.y = Cvt<T>::pack2(__uint_as_float(o[h * 8 + 2]) * inv_l, __uint_as_float(o[h * 8 + 3]) * inv_l);
+            u.z = Cvt<T>::pack2(__uint_as_float(o[h * 8 + 4]) * inv_l, __uint_as_float(o[h * 8 + 5]) * inv_l);
+            u.w = Cvt<T>::pack2(__uint_as_float(o[h * 8 + 6]) * inv_l, __uint_as_float(o[h * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(optr + c + h * 8) = u;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+template <typename T, int NA, int QT>
+static int launch_attention2(const EsAttention* a, cudaStream_t stream) {
+  CUtensorMap tmQ, tmK, tmV;
+  const uint32_t box[4] = {64u, 1u, 128u, 1u};
+  {
+    uint64_t dims[4] = {(uint64_t)a->d, (uint64_t)a->heads, (uint64_t)a->nq, (uint64_t)a->batch};
+    uint64_t str[4] = {0, (uint64_t)a->d * 2, (uint64_t)a->ldq * 2, (uint64_t)a->bsq * 2};
+    if (encode_tmap_16b(&tmQ, a->q, 4, dims, str, box)) return -3;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)a->d, (uint64_t)a->heads, (uint64_t)a->nkv, (uint64_t)a->batch};
+    uint64_t str[4] = {0, (uint64_t)a->d * 2, (uint64_t)a->ldk * 2, (uint64_t)a->bsk * 2};
+    const uint32_t boxkv[4] = {64u, 1u, static_cast<uint32_t>(kAtt2KV), 1u};
+    if (encode_tmap_16b(&tmK, a->k, 4, dims, str, boxkv)) return -3;
+    uint64_t strv[4] = {0, (uint64_t)a->d * 2, (uint64_t)a->ldv * 2, (uint64_t)a->bsv * 2};
+    if (encode_tmap_16b(&tmV, a->v, 4, dims, strv, boxkv)) return -3;
+  }
+  AttParams p;
+  p.d = a->d;
+  p.dN = ((a->d + 15) / 16) * 16;
+  p.nq = a->nq;
+  p.nkv = a->nkv;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.out = a->out;
+  p.ldo = a->ldo;
+  p.bso = a->bso;
+  const int need = QT * (kAtt2KV + p.dN);
+  p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+  ES_CHECK(need <= 512, "es_attention: TMEM budget exceeded (d %d, %d query tiles)", a->d, QT);
+  // Q + P per tile, 2 stages of K and V, barriers
+  const size_t smem = static_cast<size_t>(QT) * (NA + 1) * kAtomBytes + 4 * NA * kAtt2KV * 128 + 256;
+  auto kern = attention2_kernel<T, NA, QT>;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    ES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_smem = smem;
+  }
+  dim3 grid((a->nq + 128 * QT - 1) / (128 * QT), a->heads, a->batch);
+  ES_CUDA(launch_kernel(kern, dim3(grid), dim3(64 + 128 * QT), smem, stream, tmQ, tmK, tmV, p));
+  ES_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace es

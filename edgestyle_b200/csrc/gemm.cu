@@ -134,8 +134,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     y0 = ty * p.bh;
     i0 = tn * p.bn;
     x_end = p.W;
-    b_noff = p.seg_b_noff[0];
-    b2_noff = p.seg_b2_noff[0];
+    // implicit conv: segments are IMAGE ranges (conv LoRA: one fused weight copy / one `up` matrix per image segment)
+    int g = 0;
+#pragma unroll
+    for (int s = 1; s < ES_MAX_SEG; ++s)
+      if (s < p.nseg && i0 >= p.seg_row_start[s]) g = s;
+    b_noff = p.seg_b_noff[g];
+    b2_noff = p.seg_b2_noff[g];
   }
   const int kb1 = p.taps * p.kblocks1;
   const int kb_total = kb1 + ((p.kblocks2 > 0 && b2_noff >= 0) ? p.kblocks2 : 0);
@@ -1035,9 +1040,18 @@ static int gemm_dispatch(const EsGemm* g, cudaStream_t stream) {
     kp.tiles_x = ceil_div(W, bw);
     kp.tiles_y = ceil_div(H, bh);
     m_tiles = kp.tiles_x * kp.tiles_y * ceil_div(NI, bn);
-    kp.nseg = 1;
-    kp.seg_b_noff[0] = g->nseg > 0 ? g->seg_b_noff[0] : 0;
-    kp.seg_b2_noff[0] = g->a2 ? (g->nseg > 0 ? g->seg_b2_noff[0] : 0) : -1;
+    kp.nseg = g->nseg > 0 ? g->nseg : 1;
+    ES_CHECK(kp.nseg <= ES_MAX_SEG, "es_gemm: too many segments");
+    for (int s = 0; s < kp.nseg; ++s) {  // image segments: every boundary must fall on a tile boundary
+      const int i0s = g->nseg > 0 ? g->seg_row_start[s] : 0;
+      const int i1s = g->nseg > 0 ? g->seg_row_start[s + 1] : NI;
+      ES_CHECK(i1s >= i0s && i1s <= NI && (i0s % bn == 0 || i0s == i1s),
+               "es_gemm: image segment [%d, %d) does not fall on tiles of %d image(s)", i0s, i1s, bn);
+      kp.seg_row_start[s] = i0s;
+      kp.seg_row_start[s + 1] = i1s;
+      kp.seg_b_noff[s] = g->nseg > 0 ? g->seg_b_noff[s] : 0;
+      kp.seg_b2_noff[s] = g->a2 ? (g->nseg > 0 ? g->seg_b2_noff[s] : 0) : -1;
+    }
   }
   kp.W = W;
   kp.H = H;

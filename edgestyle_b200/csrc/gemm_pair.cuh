@@ -77,8 +77,12 @@ __device__ __forceinline__ PairUnit pair_decode(const GemmKParams& p, int u, int
     d.y0 = ty * p.bh;
     d.i0 = tnn * p.bn;
     d.x_end = p.W;
-    d.b_noff = p.seg_b_noff[0];
-    d.b2_noff = p.seg_b2_noff[0];
+    int g = 0;  // image segments (conv LoRA)
+#pragma unroll
+    for (int s = 1; s < ES_MAX_SEG; ++s)
+      if (s < p.nseg && d.i0 >= p.seg_row_start[s]) g = s;
+    d.b_noff = p.seg_b_noff[g];
+    d.b2_noff = p.seg_b2_noff[g];
   }
   const int kb1 = p.taps * p.kblocks1;
   const int kb_total = kb1 + ((p.kblocks2 > 0 && d.b2_noff >= 0) ? p.kblocks2 : 0);
@@ -670,6 +674,13 @@ static bool gemm_pair_eligible(const EsGemm* g, const GemmKParams& kp, int m_til
     if (g->rowvec && !(g->rows_per_img > 0 && g->rows_per_img % 32 == 0)) return false;
   } else {
     if (g->rowvec && (kp.bw * kp.bh) % 32 != 0) return false;
+    // the two CTAs of a pair share one weight tile: both of their M tiles must lie in the same image segment
+    const int tiles_per_img_group = kp.tiles_x * kp.tiles_y;
+    for (int s = 0; s < kp.nseg && kp.nseg > 1; ++s) {
+      const int t0 = kp.seg_row_start[s] / kp.bn * tiles_per_img_group;
+      const int t1 = ceil_div(kp.seg_row_start[s + 1], kp.bn) * tiles_per_img_group;
+      if (t1 > t0 && (t0 % 2 != 0 || (t1 % 2 != 0 && s != kp.nseg - 1))) return false;
+    }
   }
   (void)m_tiles;
   return true;

@@ -43,11 +43,11 @@ def pack_merge_block(sd: Dict[str, torch.Tensor], Cc: int, h: int, w: int, dtype
     hw = h * w
     dd = dict(device=device, dtype=dtype)
     return {
-        "w1": sd["first_conv.weight"].reshape(Cc, 3, 2).to(**f32).contiguous(),
-        "b1": sd["first_conv.bias"].reshape(Cc, 3).to(**f32).contiguous(),
+        "w1": sd["first_conv.weight"].reshape(Cc, 3, 2).permute(1, 2, 0).to(**f32).contiguous(),   # [3 pairs][2 nets][C]
+        "b1": sd["first_conv.bias"].reshape(Cc, 3).permute(1, 0).to(**f32).contiguous(),            # [3][C]
         "g1": sd["first_normalization.weight"].reshape(Cc, 3, hw).permute(2, 1, 0).to(**dd).contiguous(),
         "be1": sd["first_normalization.bias"].reshape(Cc, 3, hw).permute(2, 1, 0).to(**dd).contiguous(),
-        "w2": sd["second_conv.weight"].reshape(Cc, 3).to(**f32).contiguous(),
+        "w2": sd["second_conv.weight"].reshape(Cc, 3).permute(1, 0).to(**f32).contiguous(),         # [3][C]
         "b2": sd["second_conv.bias"].reshape(Cc).to(**f32).contiguous(),
         "g2": sd["second_normalization.weight"].reshape(Cc, hw).permute(1, 0).to(**dd).contiguous(),
         "be2": sd["second_normalization.bias"].reshape(Cc, hw).permute(1, 0).to(**dd).contiguous(),
@@ -98,6 +98,25 @@ class Res:
     cin: int
     cout: int
     temb_off: int = 0
+    # conv LoRA (lora_conv2d_rank > 0, controllora.py:561-575).  Fused mode: w1 / w2 / wsc / b1 / b2 hold `groups`
+    # copies stacked along N ([W; W + up_1 down_1; ...]) and an image segment selects its copy.  Unfused mode: the
+    # rank-r update stays a K-extension: lora[k] = (down [G * rp, taps * cin], up [G * cout, rp], rp) for
+    # k in ("conv1", "conv2", "conv_shortcut")
+    groups: int = 1
+    lora: Optional[Dict[str, Tuple[torch.Tensor, torch.Tensor, int]]] = None
+    bsc: Optional[torch.Tensor] = None  # shortcut bias on its own (only used when the shortcut runs as its own GEMM)
+
+
+@dataclass
+class ConvW:
+    """A packed stand-alone convolution (conv_in as im2col GEMM, down-sampler): w [groups * cout, K], bias fp32
+    [groups * cout]; unfused conv LoRA as (down [G * rp, K], up [G * cout, rp], rp)."""
+
+    w: torch.Tensor
+    bias: torch.Tensor
+    cout: int
+    groups: int = 1
+    lora: Optional[Tuple[torch.Tensor, torch.Tensor, int]] = None
 
 
 @dataclass
@@ -145,6 +164,7 @@ class _Packer:
             if dk not in sd:
                 return None
             d, u = sd[dk].float(), sd[uk].float()
+            d, u = d.reshape(d.shape[0], -1), u.reshape(u.shape[0], -1)  # 1x1 conv LoRA (proj_in / proj_out) -> 2-D
             r = d.shape[0]
             rp = _pad8(r)
             dp = torch.zeros(rp, k_in)
@@ -228,21 +248,76 @@ class _Packer:
         return Lin(torch.cat(w_f, 0).to(self.device).contiguous(), torch.cat(b_f).to(self.device).contiguous(), n_tot,
                    None, None, 0, block_n, len(ws_g), torch.cat(cs).to(self.device).contiguous())
 
+    def _conv_lora(self, name: str, k_cols: Optional[int] = None):
+        """LoRAConv2dLayer of conv `name` per LoRA group: [(down [rp, taps * cin] tap-major like `conv3`, up [cout, rp])]
+        with the rank zero-padded to a multiple of 8 (and the K columns to `k_cols`); None when the conv has no LoRA."""
+        parts = []
+        for sd in self.loras:
+            dk, uk = f"{name}.lora_layer.down.weight", f"{name}.lora_layer.up.weight"
+            if dk not in sd:
+                return None
+            d, u = sd[dk].float().cpu(), sd[uk].float().cpu()  # [r, cin, kh, kw], [cout, r, 1, 1]
+            r = d.shape[0]
+            rp = _pad8(r)
+            d2 = d.permute(0, 2, 3, 1).reshape(r, -1)
+            dp = torch.zeros(rp, k_cols or d2.shape[1])
+            dp[:r, :d2.shape[1]] = d2
+            up = torch.zeros(u.shape[0], rp)
+            up[:, :r] = u.reshape(u.shape[0], r)
+            parts.append((dp, up))
+        return parts if parts else None
+
+    def conv(self, name: str, k_cols: Optional[int] = None, n_pad: Optional[int] = None):
+        """Conv weight `name` as a GEMM operand [cout, taps * cin] (tap-major) with its conv LoRA.  Returns
+        (w, groups, lora): fused mode stacks [W; W + up_g down_g ...] along N (`_fuse_lora` of LoRACompatibleConv:
+        W += (up.flatten(1) @ down.flatten(1)).reshape(W.shape)), unfused keeps (down, up, rp) for the K-extension."""
+        w = self.sd[name + ".weight"].float().cpu()
+        cout = w.shape[0]
+        w2 = w.permute(0, 2, 3, 1).reshape(cout, -1)
+        if k_cols is not None and k_cols != w2.shape[1]:
+            wp = torch.zeros(cout, k_cols)
+            wp[:, :w2.shape[1]] = w2
+            w2 = wp
+        parts = self._conv_lora(name, k_cols)
+        if parts is None:
+            return self.mat(w2), 1, None
+        if self.fuse_lora:
+            return self.mat(torch.cat([w2] + [w2 + u @ d for d, u in parts], 0)), 1 + len(parts), None
+        rp = parts[0][0].shape[0]
+        return self.mat(w2), 1, (self.mat(torch.cat([d for d, _ in parts], 0)), self.mat(torch.cat([u for _, u in parts], 0)), rp)
+
     def res(self, p: str) -> Res:
         sd = self.sd
         cout, cin = sd[f"{p}.conv1.weight"].shape[:2]
-        for n in (f"{p}.conv1", f"{p}.conv2", f"{p}.conv_shortcut"):
-            for l in self.loras:
-                if f"{n}.lora_layer.down.weight" in l:
-                    raise NotImplementedError("conv LoRA (lora_conv2d_rank > 0) is not supported by the engine yet")
-        wsc = None
+        w1, g1, l1 = self.conv(f"{p}.conv1")
+        w2, g2, l2 = self.conv(f"{p}.conv2")
+        groups = max(g1, g2)
+        assert g1 == g2, "conv LoRA must cover conv1 and conv2 alike"
+        lora = {}
+        if l1 is not None:
+            lora["conv1"], lora["conv2"] = l1, l2
+        wsc = bsc = None
+        b1 = self.f32(f"{p}.conv1.bias")
         b2 = self.f32(f"{p}.conv2.bias")
         if f"{p}.conv_shortcut.weight" in sd:
-            wsc = self.mat(sd[f"{p}.conv_shortcut.weight"].reshape(cout, cin))
-            b2 = b2 + self.f32(f"{p}.conv_shortcut.bias")
-        return Res(self.f32(f"{p}.norm1.weight"), self.f32(f"{p}.norm1.bias"), self.conv3(f"{p}.conv1.weight"),
-                   self.f32(f"{p}.conv1.bias"), self.f32(f"{p}.norm2.weight"), self.f32(f"{p}.norm2.bias"),
-                   self.conv3(f"{p}.conv2.weight"), b2, wsc, cin, cout)
+            wsc, gsc, lsc = self.conv(f"{p}.conv_shortcut")
+            assert gsc == groups
+            bsc = self.f32(f"{p}.conv_shortcut.bias")
+            if lsc is not None:
+                lora["conv_shortcut"] = lsc
+            else:
+                b2 = b2 + bsc  # the shortcut rides in conv2's accumulator (K-extension): one bias
+        if groups > 1:  # the bias is indexed with the weight-row offset of the segment: one copy per group
+            b1, b2 = b1.repeat(groups), b2.repeat(groups)
+        return Res(self.f32(f"{p}.norm1.weight"), self.f32(f"{p}.norm1.bias"), w1, b1,
+                   self.f32(f"{p}.norm2.weight"), self.f32(f"{p}.norm2.bias"), w2, b2, wsc, cin, cout,
+                   groups=groups, lora=lora or None, bsc=bsc)
+
+    def convw(self, name: str, k_cols: Optional[int] = None) -> ConvW:
+        w, groups, lora = self.conv(name, k_cols)
+        bias = self.f32(name + ".bias")
+        cout = bias.shape[0]
+        return ConvW(w, bias.repeat(groups) if groups > 1 else bias, cout, groups, lora)
 
     def tfm(self, p: str) -> Tfm:
         t = f"{p}.transformer_blocks.0"
@@ -276,13 +351,21 @@ class _Packer:
         )
 
 
+@dataclass(frozen=True)
+class StepGeometry:
+    base_nets: Tuple[Optional[int], ...]  # net index per image block of the base pass (None = the UNet's own rows)
+    pose_nets: Tuple[int, ...]            # net index per image block of the pose pass
+    seg: Tuple[int, int, int]             # images of (UNet | agnostic | clothes) rows in the base pass
+    btag: str
+    ptag: str
+
+
 @dataclass
 class EncoderW:
-    conv_in: torch.Tensor  # [c0, 64] (im2col of 4 channels x 9 taps, zero padded)
-    conv_in_b: torch.Tensor
+    conv_in: ConvW  # w [groups * c0, 64] (im2col of 4 channels x 9 taps, zero padded)
     down_res: List[List[Res]]
     down_tfm: List[List[Optional[Tfm]]]
-    down_conv: List[Optional[Tuple[torch.Tensor, torch.Tensor]]]
+    down_conv: List[Optional[ConvW]]
     mid_res: List[Res]
     mid_tfm: Tfm
     # time path: per weight-set group (LoRA folded into these tiny-M linears at pack time)
@@ -316,6 +399,7 @@ class DenoiseEngine:
         self.use_graph = use_graph
         self._bufs: Dict[str, torch.Tensor] = {}
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self._graph_launches: Dict[tuple, int] = {}
         self.fuse_gn_stats = os.environ.get("ES_FUSE_GN", "1") != "0"
         # ControlLoRA update: "fused" = one fused weight copy per LoRA group (default), "unfused" = rank-r update as
         # extra K-blocks of the accumulator (t = x down^T, then [x | t] [W | up]^T)
@@ -328,8 +412,11 @@ class DenoiseEngine:
         # kernel and no normalised copy of the hidden state in memory.  Needs whole 128-row tiles per row segment.
         self.fold_ln = (os.environ.get("ES_FOLD_LN", "1") != "0" and self.fuse_lora
                         and (rows * self.levels[-1][0] * self.levels[-1][1]) % 128 == 0)
-        self.merge_mode = int(os.environ.get("ES_MERGE_EARLY", "0"))
-        self.merge_early = self.merge_mode != 0
+        # merge levels >= merge_split form the first group (one launch per phase, deep levels: the decoder starts on
+        # them), levels < merge_split the second (the heavy 64x64-level merges, under the decoder's deep levels);
+        # 0 = a single group
+        self.merge_split = int(os.environ.get("ES_MERGE_SPLIT", "3"))
+        self.merge_z16 = os.environ.get("ES_MERGE_Z16", "1") != "0"  # fp16 engines keep the merge's z tensor in fp16
         self._stats_of = {}
         self._cat_slot = {}
         self._kv_recompute = False  # True: redo the text K/V projections inside every step (reference behaviour)
@@ -339,17 +426,9 @@ class DenoiseEngine:
             if c % 8 or c % cfg.norm_num_groups or (c // cfg.num_heads) % 8:
                 raise ValueError(f"channel count {c} unsupported (needs %8, %groups, head_dim %8)")
         ops.set_gemm_workspace(256 << 20, self.dev)  # split-K scratch of the main stream
-        # encoder chains (see _run_step): ES_CHAINS = "b0123;p012" style spec, default below
-        spec = os.environ.get("ES_CHAINS", "b0123;p012")
-        self.chains = []
-        for part in spec.split(";"):
-            self.chains.append(("base" if part[0] == "b" else "pose", [int(ch) for ch in part[1:]]))
-        assert sorted(b for k, bl in self.chains if k == "base" for b in bl) == [0, 1, 2, 3], spec
-        assert sorted(b for k, bl in self.chains if k == "pose" for b in bl) == [0, 1, 2], spec
-        assert self.chains[0][0] == "base" and 0 in self.chains[0][1], "the first chain (main stream) must hold the UNet rows"
         # stream priorities (ES_PRIO = "<chains>,<merge>", lower number = higher priority, 0 = default)
         prio = [int(v) for v in os.environ.get("ES_PRIO", "0,0").split(",")]
-        self._chain_streams = [torch.cuda.Stream(device=self.dev, priority=prio[0]) for _ in range(len(self.chains) - 1)]
+        self._chain_streams = [torch.cuda.Stream(device=self.dev, priority=prio[0])]  # the pose pass
         self._merge_stream = torch.cuda.Stream(device=self.dev, priority=prio[1])
         self._side_ws = []
         for st in self._chain_streams + [self._merge_stream]:  # concurrent launches must not share split-K scratch
@@ -365,26 +444,27 @@ class DenoiseEngine:
             if os.environ.get("ES_RETUNE", "0") == "0":
                 ops.TUNER.load(self._tuned_path)
             ops.TUNER.enabled = True
+        self._tune = os.environ.get("ES_AUTOTUNE", "1") != "0"
         self._tuning_done = False
+        self._kv_masks = set()      # active-net masks whose text K/V projections exist for the current prompt
+        self._scale_host = None
 
     # ------------------------------------------------------------------------------------ packing
     def _pack_encoder(self, sd, loras) -> EncoderW:
         cfg = self.cfg
         P = _Packer(sd, loras, self.dtype, self.dev, self.fuse_lora, self.fold_ln)
         c0 = cfg.block_out_channels[0]
-        wci = torch.zeros(c0, 64)
-        wci[:, :9 * cfg.in_channels] = sd["conv_in.weight"].float().cpu().permute(0, 2, 3, 1).reshape(c0, -1)
         down_res, down_tfm, down_conv = [], [], []
         for i in range(len(cfg.block_out_channels)):
             down_res.append([P.res(f"down_blocks.{i}.resnets.{j}") for j in range(cfg.layers_per_block)])
             down_tfm.append([P.tfm(f"down_blocks.{i}.attentions.{j}") if cfg.down_has_attn[i] else None
                              for j in range(cfg.layers_per_block)])
             k = f"down_blocks.{i}.downsamplers.0.conv"
-            down_conv.append((P.conv3(k + ".weight"), P.f32(k + ".bias")) if k + ".weight" in sd else None)
+            down_conv.append(P.convw(k) if k + ".weight" in sd else None)
         mid_res = [P.res("mid_block.resnets.0"), P.res("mid_block.resnets.1")]
         mid_tfm = P.tfm("mid_block.attentions.0")
         all_res = [r for lvl in down_res for r in lvl] + mid_res
-        return self._finish_time_path(EncoderW(P.mat(wci), P.f32("conv_in.bias"), down_res, down_tfm, down_conv,
+        return self._finish_time_path(EncoderW(P.convw("conv_in", 64), down_res, down_tfm, down_conv,
                                                mid_res, mid_tfm, [], [], [], []), sd, loras, all_res,
                                       [f"down_blocks.{i}.resnets.{j}" for i in range(len(cfg.block_out_channels))
                                        for j in range(cfg.layers_per_block)] + ["mid_block.resnets.0",
@@ -541,6 +621,7 @@ class DenoiseEngine:
         self._merge_next = 0
         self._ln_next = 0
         self.coef = torch.zeros(4, device=self.dev, dtype=torch.float32)
+        self.cond_scale_dev = torch.ones(6, device=self.dev, dtype=torch.float32)  # read by the merge kernels
         self.guidance = torch.ones(max(B // 2, 1), device=self.dev, dtype=torch.float32)
 
     # ------------------------------------------------------------------------------------ inputs
@@ -551,39 +632,60 @@ class DenoiseEngine:
         pe = prompt_embeds.to(device=self.dev, dtype=self.dtype).reshape(B * nt, -1)
         for g in range(4):
             self.ctx_base[g * B * nt:(g + 1) * B * nt].copy_(pe)
-        self._precompute_text_kv()
+        masks = self._kv_masks or {(True,) * 6}
+        self._kv_masks = set()
+        for T in (t for lvl in self.up_tfm for t in lvl if t is not None):
+            kv = self.buf(f"kv.dec.{T.uid}", B * nt, 2 * T.c)
+            self._lin(T.kv2, self.ctx_dec, kv, nt, None, "dec.kv")
+        for m in sorted(masks, reverse=True):
+            self._ensure_text_kv(m)
 
-    def _chain_geometry(self):
-        """(tag, EncoderW, first image block, n blocks, LoRA segment image counts) per encoder chain."""
+    def _geometry(self, active: Sequence[bool]) -> "StepGeometry":
+        """Image blocks of the two batched encoder passes for the set of contributing nets: the base (UNet weights)
+        pass carries the UNet rows plus one block per active ControlLoRA net (agnostic = net 0, clothes = nets 2, 4),
+        the pose pass one block per active openpose net (1, 3, 5)."""
         B = self.B
-        lora_of_block = (0, 1, 2, 2)
-        out = []
-        for kind, blocks in self.chains:
-            b0, nb = blocks[0], len(blocks)
-            if kind == "base":
-                cnt = [0, 0, 0]
-                for blk in blocks:
-                    cnt[lora_of_block[blk]] += B
-                out.append((f"{kind}{b0}", self.enc_base, b0, nb, tuple(cnt)))
-            else:
-                out.append((f"{kind}{b0}", self.enc_pose, b0, nb, None))
-        return out
+        base = [None] + [k for k in (0, 2, 4) if active[k]]
+        pose = [k for k in (1, 3, 5) if active[k]]
+        seg = (B, B if active[0] else 0, B * (int(active[2]) + int(active[4])))
+        m = "".join("1" if a else "0" for a in active)
+        return StepGeometry(tuple(base), tuple(pose), seg, "b" + m[0::2], "p" + m[1::2])
 
-    def _precompute_text_kv(self):
-        """attn2.to_k / to_v of every transformer on the (step-invariant) prompt embeddings, LoRA included."""
+    def _ensure_text_kv(self, active):
+        """attn2.to_k / to_v of every encoder transformer on the (step-invariant) prompt embeddings, LoRA included, for
+        the image blocks of this set of active nets.  Computed once per (prompt, set): never inside a captured step."""
+        active = tuple(bool(a) for a in active)
+        if active in self._kv_masks:
+            return
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("text K/V projections must exist before a step is captured")
         B, nt = self.B, self.n_text
-        for tag, E, b0, nb, seg in self._chain_geometry():
-            ctx_all = self.ctx_base if E is self.enc_base else self.ctx_pose
-            ctx = ctx_all[b0 * B * nt:(b0 + nb) * B * nt]
+        geo = self._geometry(active)
+        for tag, E, nb, seg in ((geo.btag, self.enc_base, len(geo.base_nets), geo.seg),
+                                (geo.ptag, self.enc_pose, len(geo.pose_nets), None)):
+            if nb == 0:
+                continue
+            ctx = (self.ctx_base if E is self.enc_base else self.ctx_pose)[: nb * B * nt]
             tf = [t for lvl in E.down_tfm for t in lvl if t is not None] + [E.mid_tfm]
             for T in tf:
                 kv = self.buf(f"kv.{tag}.{T.uid}", nb * B * nt, 2 * T.c)
                 self._lin(T.kv2, ctx, kv, nt, seg, tag + ".kv")
-        for lvl in self.up_tfm:
-            for T in lvl:
-                if T is not None:
-                    kv = self.buf(f"kv.dec.{T.uid}", B * nt, 2 * T.c)
-                    self._lin(T.kv2, self.ctx_dec, kv, nt, None, "dec.kv")
+        self._kv_masks.add(active)
+
+    def _convw_block(self, Cw: ConvW, col, out, grp: int, tag: str, residual=None):
+        """conv_in of ONE image block (flat GEMM on the im2col of the sample) with the weights of LoRA group `grp`
+        (0 = plain UNet weights, 1 = agnostic, 2 = clothes): fused copy, or the rank-r K-extension."""
+        co = Cw.cout
+        if Cw.groups > 1:
+            return ops.gemm(col, Cw.w, co, out=out, bias=Cw.bias, residual=residual,
+                            segs=([0, col.shape[0]], [grp * co], None))
+        if Cw.lora is not None and grp > 0:
+            down, up, rp = Cw.lora
+            t = self.buf(f"{tag}.lora_t", col.shape[0], rp)
+            ops.gemm(col, down, rp, out=t, segs=([0, col.shape[0]], [(grp - 1) * rp], None))
+            return ops.gemm(col, Cw.w, co, out=out, bias=Cw.bias, residual=residual, a2=t, b2=up,
+                            segs=([0, col.shape[0]], [0], [(grp - 1) * co]))
+        return ops.gemm(col, Cw.w, co, out=out, bias=Cw.bias, residual=residual)
 
     def set_conditioning(self, conds: Sequence[torch.Tensor]):
         """Six cached conditioning embeddings [B, c0, h, w] (prepare_image, edgestyle_pipeline.py:629-664)."""
@@ -695,7 +797,91 @@ class DenoiseEngine:
             ops.gemm(a, L.w, L.n, out=out, bias=L.bias, block_n=L.block_n, **ep)
         return out
 
-    def _resnet(self, R: Res, x, imgs, H, W, temb, out, tag):
+    @staticmethod
+    def _imgs_per_tile(H: int, W: int) -> int:
+        """Images one 128-row conv tile of es_gemm covers (gemm.cu: bw x bh x bn boxes): > 1 only on tiny levels."""
+        bw = W if W < 128 else 128
+        bh = max(128 // bw, 1)
+        if bh <= H:
+            return 1
+        hh = 1
+        while hh < H:
+            hh <<= 1
+        return max(bh // hh, 1)
+
+    def _conv_seg(self, a, w, n, *, out, H, W, imgs, taps, seg, noff, noff2=None, a2=None, b2=None, rowvec=None,
+                  residual=None, gn_ws=None, **kw):
+        """One convolution (taps 9: implicit GEMM over [imgs, H, W]; taps 1: flat) whose weight rows depend on the
+        image segment: seg = image counts of (UNet | agnostic | clothes) rows, noff / noff2 = weight-row offset of
+        each segment in `w` / `b2` (-1 in noff2: no second source for that segment).  One launch when the segment
+        boundaries fall on tile boundaries, else one launch per segment over its image range."""
+        hw = H * W
+        if seg is None:
+            seg, noff, noff2 = (imgs, 0, 0), (noff[0], 0, 0), None if noff2 is None else (noff2[0], 0, 0)
+        starts = [0, seg[0], seg[0] + seg[1], seg[0] + seg[1] + seg[2]]
+        assert starts[-1] == imgs, (seg, imgs)
+        common = dict(taps=taps, a2=a2, b2=b2, rowvec=rowvec, residual=residual, gn_ws=gn_ws, **kw)
+        unit = 1 if taps == 9 else hw  # segment starts: images (implicit conv) or rows (flat)
+        per_tile = self._imgs_per_tile(H, W) if taps == 9 else 1  # flat GEMMs clip segment tails themselves
+        if all(b % per_tile == 0 for b in starts[1:3]):
+            segs = ([b * unit for b in starts], list(noff), None if noff2 is None else list(noff2))
+            if taps == 9:
+                common["whn"] = (W, H, imgs)
+            elif gn_ws is not None or rowvec is not None:
+                common["rows_per_img"] = hw
+            return ops.gemm(a, w, n, out=out, segs=segs, **common)
+        for i in range(3):  # ragged segments (e.g. one image per segment on a level whose tile holds two)
+            i0, i1 = starts[i], starts[i + 1]
+            if i1 == i0:
+                continue
+            sub = dict(common)
+            for key in ("a2", "residual"):
+                if sub[key] is not None:
+                    sub[key] = sub[key][i0 * hw:i1 * hw]
+            for key in ("rowvec", "gn_ws"):
+                if sub[key] is not None:
+                    sub[key] = sub[key][i0:i1]
+            if noff2 is not None and noff2[i] < 0:
+                sub["a2"] = sub["b2"] = None
+            if taps == 9:
+                sub["whn"] = (W, H, i1 - i0)
+            elif gn_ws is not None or rowvec is not None:
+                sub["rows_per_img"] = hw
+            ops.gemm(a[i0 * hw:i1 * hw], w, n, out=out[i0 * hw:i1 * hw],
+                     segs=([0, (i1 - i0) * unit], [noff[i]], None if sub["a2"] is None else [max(noff2[i], 0) if noff2 else 0]),
+                     **sub)
+        return out
+
+    def _lora_t(self, x, lora, seg, H, W, imgs, taps, tag, c1):
+        """Unfused conv LoRA: t = conv_down_g(x) over the LoRA rows only ([imgs * hw, rp]; the UNet rows are skipped)."""
+        down, up, rp = lora
+        hw = H * W
+        n0 = seg[0]
+        t = self.buf(f"{tag}.lora_t", imgs * hw, rp)
+        if imgs - n0 > 0:
+            self._conv_seg(x[n0 * hw:], down, rp, out=t[n0 * hw:], H=H, W=W, imgs=imgs - n0, taps=taps,
+                           seg=(0, seg[1], seg[2]), noff=(0, 0, rp), c1=c1)
+        return t
+
+    def _convw(self, Cw: ConvW, col, out, H, W, imgs, seg, tag, **kw):
+        """A stand-alone convolution run as a flat GEMM on an im2col matrix (conv_in, stride-2 down-sampler) with its
+        conv LoRA: fused weight copy per image segment, or the K-extension t = col @ down^T, [col | t] [W | up]^T."""
+        co = Cw.cout
+        if seg is None or (Cw.groups == 1 and Cw.lora is None):
+            if kw.get("gn_ws") is not None:
+                kw["rows_per_img"] = H * W
+            return ops.gemm(col, Cw.w, co, out=out, bias=Cw.bias, **kw)
+        if Cw.groups > 1:
+            return self._conv_seg(col, Cw.w, co, out=out, H=H, W=W, imgs=imgs, taps=1, seg=seg, noff=(0, co, 2 * co),
+                                  bias=Cw.bias, **kw)
+        t = self._lora_t(col, Cw.lora, seg, H, W, imgs, 1, tag, col.shape[1])
+        return self._conv_seg(col, Cw.w, co, out=out, H=H, W=W, imgs=imgs, taps=1, seg=seg, noff=(0, 0, 0),
+                              noff2=(-1, 0, co), bias=Cw.bias, a2=t, b2=Cw.lora[1], **kw)
+
+    def _resnet(self, R: Res, x, imgs, H, W, temb, out, tag, seg=None):
+        """ResnetBlock2D.  seg = image counts of (UNet | agnostic | clothes) rows when the convolutions carry a conv
+        LoRA (lora_conv2d_rank > 0, /root/reference/model/controllora.py:561-575): fused weight copies are selected
+        per image segment, the unfused update rides as a K-extension (source 2 = down-conv output, B2 = up)."""
         M = imgs * H * W
         g1 = self.buf(f"{tag}.gn1", M, R.cin)
         self._gn(x, g1, R.n1g, R.n1b, imgs, H * W, True)
@@ -706,16 +892,51 @@ class DenoiseEngine:
             if st.cuda_stream not in self._temb_waited:  # time path of the base pass (enqueued on the side stream)
                 st.wait_event(self._temb_ready)
                 self._temb_waited.add(st.cuda_stream)
-        ops.gemm(g1, R.w1, R.cout, out=hbuf, taps=9, whn=(W, H, imgs), bias=R.b1,
-                 rowvec=temb[:, R.temb_off:R.temb_off + R.cout], c1=R.cin,
-                 gn_ws=self._stats_for(hbuf, imgs, H * W), gn_groups=G)
-        g2 = self.buf(f"{tag}.gn2", M, R.cout)
+        rowvec = temb[:, R.temb_off:R.temb_off + R.cout]
+        co = R.cout
+        if (R.groups == 1 and R.lora is None) or seg is None:
+            ops.gemm(g1, R.w1, co, out=hbuf, taps=9, whn=(W, H, imgs), bias=R.b1, rowvec=rowvec, c1=R.cin,
+                     gn_ws=self._stats_for(hbuf, imgs, H * W), gn_groups=G)
+            g2 = self.buf(f"{tag}.gn2", M, co)
+            self._gn(hbuf, g2, R.n2g, R.n2b, imgs, H * W, True)
+            okw = self._gn_kw(out, imgs, H * W)
+            if R.wsc is not None:
+                ops.gemm(g2, R.w2, co, out=out, taps=9, whn=(W, H, imgs), bias=R.b2, a2=x, b2=R.wsc, c1=co, **okw)
+            else:
+                ops.gemm(g2, R.w2, co, out=out, taps=9, whn=(W, H, imgs), bias=R.b2, residual=x, c1=co, **okw)
+            return out
+        if R.groups > 1:  # fused copies [W; W + up_1 down_1; W + up_2 down_2] stacked along N
+            noff = (0, co, 2 * co)
+            self._conv_seg(g1, R.w1, co, out=hbuf, H=H, W=W, imgs=imgs, taps=9, seg=seg, noff=noff, bias=R.b1,
+                           rowvec=rowvec, c1=R.cin, gn_ws=self._stats_for(hbuf, imgs, H * W), gn_groups=G)
+            g2 = self.buf(f"{tag}.gn2", M, co)
+            self._gn(hbuf, g2, R.n2g, R.n2b, imgs, H * W, True)
+            okw = self._gn_kw(out, imgs, H * W)
+            if R.wsc is not None:
+                self._conv_seg(g2, R.w2, co, out=out, H=H, W=W, imgs=imgs, taps=9, seg=seg, noff=noff, noff2=noff,
+                               bias=R.b2, a2=x, b2=R.wsc, c1=co, **okw)
+            else:
+                self._conv_seg(g2, R.w2, co, out=out, H=H, W=W, imgs=imgs, taps=9, seg=seg, noff=noff, bias=R.b2,
+                               residual=x, c1=co, **okw)
+            return out
+        # unfused: t = down-conv(x) as source 2, `up` as B2 (the UNet rows take no second source)
+        zero, lo2 = (0, 0, 0), (-1, 0, co)
+        t1 = self._lora_t(g1, R.lora["conv1"], seg, H, W, imgs, 9, tag + ".c1", R.cin)
+        self._conv_seg(g1, R.w1, co, out=hbuf, H=H, W=W, imgs=imgs, taps=9, seg=seg, noff=zero, noff2=lo2, bias=R.b1,
+                       rowvec=rowvec, c1=R.cin, a2=t1, b2=R.lora["conv1"][1],
+                       gn_ws=self._stats_for(hbuf, imgs, H * W), gn_groups=G)
+        g2 = self.buf(f"{tag}.gn2", M, co)
         self._gn(hbuf, g2, R.n2g, R.n2b, imgs, H * W, True)
+        res = x
+        if R.wsc is not None:  # the second source is taken by the LoRA: the 1x1 shortcut runs as its own GEMM
+            res = self.buf(f"{tag}.sc", M, co)
+            tsc = self._lora_t(x, R.lora["conv_shortcut"], seg, H, W, imgs, 1, tag + ".sc", R.cin)
+            self._conv_seg(x, R.wsc, co, out=res, H=H, W=W, imgs=imgs, taps=1, seg=seg, noff=zero, noff2=lo2,
+                           bias=R.bsc, a2=tsc, b2=R.lora["conv_shortcut"][1])
+        t2 = self._lora_t(g2, R.lora["conv2"], seg, H, W, imgs, 9, tag + ".c2", co)
         okw = self._gn_kw(out, imgs, H * W)
-        if R.wsc is not None:
-            ops.gemm(g2, R.w2, R.cout, out=out, taps=9, whn=(W, H, imgs), bias=R.b2, a2=x, b2=R.wsc, c1=R.cout, **okw)
-        else:
-            ops.gemm(g2, R.w2, R.cout, out=out, taps=9, whn=(W, H, imgs), bias=R.b2, residual=x, c1=R.cout, **okw)
+        self._conv_seg(g2, R.w2, co, out=out, H=H, W=W, imgs=imgs, taps=9, seg=seg, noff=zero, noff2=lo2, bias=R.b2,
+                       residual=res, c1=co, a2=t2, b2=R.lora["conv2"][1], **okw)
         return out
 
     def _transformer(self, T: Tfm, x, imgs, H, W, ctx, out, tag, seg):
@@ -727,7 +948,7 @@ class DenoiseEngine:
         hcur = self.buf(f"{tag}.th", M, c)
         fold = self.fold_ln
         st = [self._ln_slot(M) for _ in range(3)] if fold else [None] * 3
-        self._lin(T.proj_in, g, hcur, hw, None, tag, rowstat_out=st[0])
+        self._lin(T.proj_in, g, hcur, hw, seg, tag + ".pin", rowstat_out=st[0])
         ln = hcur if fold else self.buf(f"{tag}.ln", M, c)  # folded: the projections read the raw hidden state
         att = self.buf(f"{tag}.att", M, c)
         # self-attention
@@ -754,7 +975,7 @@ class DenoiseEngine:
         u = self.buf(f"{tag}.ff", M, 4 * c)
         self._lin(T.ff1, ln, u, hw, seg, tag + ".o", ln_stat=st[2], act=ACT_GEGLU)
         self._lin(T.ff2, u, hcur, hw, seg, tag + ".ff2", residual=hcur)
-        self._lin(T.proj_out, hcur, out, hw, None, tag, residual=x, **self._gn_kw(out, imgs, hw))
+        self._lin(T.proj_out, hcur, out, hw, seg, tag + ".pout", residual=x, **self._gn_kw(out, imgs, hw))
         return out
 
     def _time_path(self, E: EncoderW, groups: Sequence[Tuple[int, int]], tag: str, ncols: Sequence[int], out=None):
@@ -793,10 +1014,10 @@ class DenoiseEngine:
                 M = imgs * H * W
                 if T is None:
                     out = self.buf(f"{tag}.skip{len(skips)}", M, c)
-                    self._resnet(R, x, imgs, H, W, temb, out, f"{tag}.L{i}")
+                    self._resnet(R, x, imgs, H, W, temb, out, f"{tag}.L{i}", seg)
                 else:
                     r_out = self.buf(f"{tag}.L{i}.rout", M, c)
-                    self._resnet(R, x, imgs, H, W, temb, r_out, f"{tag}.L{i}")
+                    self._resnet(R, x, imgs, H, W, temb, r_out, f"{tag}.L{i}", seg)
                     out = self.buf(f"{tag}.skip{len(skips)}", M, c)
                     self._transformer(T, r_out, imgs, H, W, ctx, out, f"{tag}.L{i}", seg)
                 x = out
@@ -807,8 +1028,8 @@ class DenoiseEngine:
                 col = self.buf(f"{tag}.L{i}.col", imgs * Hn * Wn, 9 * c)
                 ops.im2col3x3(x, col, imgs, H, W, c, 2)
                 out = self.buf(f"{tag}.skip{len(skips)}", imgs * Hn * Wn, c)
-                ops.gemm(col, E.down_conv[i][0], c, out=out, bias=E.down_conv[i][1], rows_per_img=Hn * Wn,
-                         gn_ws=self._stats_for(out, imgs, Hn * Wn), gn_groups=cfg.norm_num_groups)
+                self._convw(E.down_conv[i], col, out, Hn, Wn, imgs, seg, f"{tag}.L{i}.down",
+                            gn_ws=self._stats_for(out, imgs, Hn * Wn), gn_groups=cfg.norm_num_groups)
                 x = out
                 skips.append(x)
                 notify(len(skips) - 1, x)
@@ -816,19 +1037,24 @@ class DenoiseEngine:
         c = cfg.block_out_channels[-1]
         M = imgs * H * W
         m0 = self.buf(f"{tag}.mid0", M, c)
-        self._resnet(E.mid_res[0], x, imgs, H, W, temb, m0, f"{tag}.mid")
+        self._resnet(E.mid_res[0], x, imgs, H, W, temb, m0, f"{tag}.mid", seg)
         m1 = self.buf(f"{tag}.mid1", M, c)
         self._transformer(E.mid_tfm, m0, imgs, H, W, ctx, m1, f"{tag}.mid", seg)
         mid = self.buf(f"{tag}.mid2", M, c)
-        self._resnet(E.mid_res[1], m1, imgs, H, W, temb, mid, f"{tag}.mid")
+        self._resnet(E.mid_res[1], m1, imgs, H, W, temb, mid, f"{tag}.mid", seg)
         notify(len(skips), mid)
         return skips, mid
 
     # ------------------------------------------------------------------------------------ the step
-    def _run_step(self, cond_scale: Sequence[float], mode: str = "step", guess_mode: bool = False,
+    def _run_step(self, active: Sequence[bool] = (True,) * 6, mode: str = "step", guess_mode: bool = False,
                   zero_uncond: bool = False):
         """mode 'step': full fused step -> eps_out.  mode 'residuals': stop after the merge and leave the 13
         merged residuals (what EdgeStyleMultiControlNetModel.forward returns) in self.res_out.
+
+        The conditioning scales are read by the merge kernels from `self.cond_scale_dev` (a device vector), so one
+        captured graph serves every scale.  `active[k]` = net k contributes (its scale is non-zero): the image blocks
+        of inactive nets are dropped from the two batched encoder passes (control_guidance_start / end gating,
+        /root/reference/model/edgestyle_pipeline.py:418-427, without spending the gated branch's FLOPs).
 
         guess_mode: every ControlNet scales its 13 outputs by logspace(-1, 0, 13) * conditioning_scale
         (controllora.py:257-265) instead of a uniform scale.  zero_uncond: the pipeline's guess mode under CFG
@@ -840,6 +1066,9 @@ class DenoiseEngine:
         boc = cfg.block_out_channels
         c0 = boc[0]
         nt = self.n_text
+        active = tuple(bool(a) for a in active)
+        geo = self._geometry(active)
+        self._ensure_text_kv(active)
         self._begin_step_scratch()
         # -- sample: NCHW fp32 -> NHWC, im2col (K = 36 padded to 64)
         s16 = self.buf("sample16", B * hw, 8)
@@ -849,7 +1078,7 @@ class DenoiseEngine:
         ops.timestep_embedding(self.t_in, c0, self.buf("t_sin", B, c0, torch.float32))
         Eb, Ep = self.enc_base, self.enc_pose
         enc_cols = Eb.temb_cols
-        # fork here: the other chains only need the sinusoidal embedding and the im2col of the sample.  The base
+        # fork here: the pose chain only needs the sinusoidal embedding and the im2col of the sample.  The base
         # chain's time path (a dozen weight-streaming GEMVs) runs on the otherwise idle merge stream while the main
         # stream does conv_in and the first GroupNorm; the first resnet waits for it just before its conv1.
         main = torch.cuda.current_stream()
@@ -857,75 +1086,43 @@ class DenoiseEngine:
         fork.record(main)
         self._merge_stream.wait_event(fork)
         with torch.cuda.stream(self._merge_stream):
-            temb_base = self._time_path(Eb, [(0, B), (1, B), (2, 2 * B)], "base",
-                                        [enc_cols + self.dec_temb_cols, enc_cols, enc_cols])
+            groups = [(0, B)] + ([(1, B)] if geo.seg[1] else []) + ([(2, geo.seg[2])] if geo.seg[2] else [])
+            temb_base = self._time_path(Eb, groups, geo.btag,
+                                        [enc_cols + self.dec_temb_cols] + [enc_cols] * (len(groups) - 1))
             self._temb_ready = torch.cuda.Event()
             self._temb_ready.record(self._merge_stream)
             self._temb_waited = set()
         cond = lambda k: self.conds[k * B * hw:(k + 1) * B * hw]
-        # -- encoder chains.  Image order of the base weight set: unet (B) | agn (B) | clo cond2 (B) | clo cond4 (B);
-        #    of the pose set: cond1 | cond3 | cond5 (B each).  `self.chains` groups consecutive image blocks into
-        #    independent traversals, each on its own stream: most layers at CFG batch 2 are latency / occupancy
-        #    bound, so concurrent chains fill the SMs that one chain's partial waves leave idle.
-        xb = self.buf("base.x0", 4 * B * hw, c0)
-        xp = self.buf("pose.x0", 3 * B * hw, c0)
-        base_cond = (None, 0, 2, 4)   # conditioning net index of base image block 0..3
-        pose_cond = (1, 3, 5)
-        lora_of_block = (0, 1, 2, 2)  # segment class of base block: 0 = UNet rows (no LoRA), 1 = agn, 2 = clo
-        results = {}                  # ("base"|"pose", block) -> (chain skips+mid list, first image of block in chain)
+        # -- encoder passes.  Image order of the base weight set: unet (B) | agn (B) | clo cond2 (B) | clo cond4 (B)
+        #    (inactive nets dropped); of the pose set: cond1 | cond3 | cond5.  The two passes run on two streams: most
+        #    layers at CFG batch 2 are latency / occupancy bound, so the concurrent pass fills the SMs that one chain's
+        #    partial waves leave idle.
+        nb_b, nb_p = len(geo.base_nets), len(geo.pose_nets)
+        xb = self.buf(f"{geo.btag}.x0", nb_b * B * hw, c0)
         done_events = []
-        level_events = []             # per chain: residual level -> event recorded once that level has been enqueued
-        temb_pose = None
-        for ci, (kind, blocks) in enumerate(self.chains):
-            st = main if ci == 0 else self._chain_streams[ci - 1]
-            if st is not main:
-                st.wait_event(fork)
+        # conv_in (+ cached conditioning embedding as the residual, controllora.py:203): one GEMM per image block
+        ci = Eb.conv_in
+        for pos, k in enumerate(geo.base_nets):
+            grp = 0 if k is None else (1 if k == 0 else 2)
+            self._convw_block(ci, col, xb[pos * B * hw:(pos + 1) * B * hw], grp, f"{geo.btag}.ci{pos}",
+                              residual=None if k is None else cond(k))
+        outs_b = self._encoder(Eb, xb, nb_b * B, temb_base, self.ctx_base[: nb_b * B * nt], geo.seg, geo.btag)
+        outs_b = outs_b[0] + [outs_b[1]]
+        outs_p = None
+        if nb_p:
+            st = self._chain_streams[0]
+            st.wait_event(fork)
             with torch.cuda.stream(st):
-                b0, nb = blocks[0], len(blocks)
-                tag = f"{kind}{b0}"
-                if kind == "base":
-                    E, x_all, ctx_all, temb_all = Eb, xb, self.ctx_base, temb_base
-                    for blk in blocks:
-                        k = base_cond[blk]
-                        ops.gemm(col, E.conv_in, c0, out=xb[blk * B * hw:(blk + 1) * B * hw], bias=E.conv_in_b,
-                                 residual=None if k is None else cond(k))
-                    cnt = [0, 0, 0]
-                    for blk in blocks:
-                        cnt[lora_of_block[blk]] += B
-                    seg = tuple(cnt)
-                else:
-                    E, x_all, ctx_all = Ep, xp, self.ctx_pose
-                    if temb_pose is None:
-                        temb_pose = self.buf("pose.temb", 3 * B, Ep.temb_cols, torch.float32)
-                    self._time_path(Ep, [(0, nb * B)], tag, [Ep.temb_cols], out=temb_pose[b0 * B:(b0 + nb) * B])
-                    temb_all = temb_pose
-                    for blk in blocks:
-                        ops.gemm(col, E.conv_in, c0, out=xp[blk * B * hw:(blk + 1) * B * hw], bias=E.conv_in_b,
-                                 residual=cond(pose_cond[blk]))
-                    seg = None
-                imgs = nb * B
-                lev = {}
-
-                def on_level(li, _t, lev=lev, st=st):
-                    lev[li] = torch.cuda.Event()
-                    lev[li].record(st)
-
-                level_events.append(lev)
-                sk, md = self._encoder(E, x_all[b0 * B * hw:(b0 + nb) * B * hw], imgs, temb_all[b0 * B:(b0 + nb) * B],
-                                       ctx_all[b0 * B * nt:(b0 + nb) * B * nt], seg, tag,
-                                       on_level if self.merge_early else None)
-                outs_chain = sk + [md]  # one list per chain: block_span() recognises blocks of the same traversal by it
-                for i, blk in enumerate(blocks):
-                    results[(kind, blk)] = (outs_chain, i * B)
+                xp = self.buf(f"{geo.ptag}.x0", nb_p * B * hw, c0)
+                temb_pose = self._time_path(Ep, [(0, nb_p * B)], geo.ptag, [Ep.temb_cols])
+                for pos, k in enumerate(geo.pose_nets):
+                    ops.gemm(col, Ep.conv_in.w, c0, out=xp[pos * B * hw:(pos + 1) * B * hw], bias=Ep.conv_in.bias,
+                             residual=cond(k))
+                sk, md = self._encoder(Ep, xp, nb_p * B, temb_pose, self.ctx_pose[: nb_p * B * nt], None, geo.ptag)
+                outs_p = sk + [md]
                 ev = torch.cuda.Event()
                 ev.record(st)
                 done_events.append(ev)
-
-        def block_rows(kind, blk, li):
-            """rows of image block `blk` at residual level li: [B*H*W, C] view into its chain's buffer"""
-            outs, first = results[(kind, blk)]
-            c, H, W = self.res_shapes[li]
-            return outs[li][first * H * W:(first + B) * H * W]
         # -- decoder concat buffers (x | skip) and their geometry
         rev = list(reversed(boc))
         rev_attn = list(reversed(cfg.down_has_attn))
@@ -947,90 +1144,77 @@ class DenoiseEngine:
                 H, W = self.levels[len(boc) - 1 - i]
                 if self._register_cat(cbuf, B, H * W):
                     cat_gn[sidx_ij] = (self._cat_slot[cbuf.data_ptr()], xc)
-        # -- zero convs (controllora.py:240-254) + EdgeStyle merge (edgestyle_multicontrolnet.py:160-169), on the side
-        #    stream in the order the decoder consumes them (mid, then skips 11..0): the large 64x64-level merges
-        #    overlap the decoder's deep levels; the decoder waits on one event per level
-        scale = [float(s) for s in cond_scale]
+        # -- zero convs (controllora.py:240-254) + EdgeStyle merge (edgestyle_multicontrolnet.py:160-169) on the side
+        #    stream, in the order the decoder consumes them (mid, then skips 11..0).  All levels of a group go through
+        #    ONE launch per merge phase; the decoder waits on one event per group.  Default: the deep levels first (the
+        #    decoder starts on them), the three heavy 64x64-level merges under the decoder's latency-bound deep levels.
         level_gain = torch.logspace(-1, 0, len(self.res_shapes)).tolist() if guess_mode else [1.0] * len(self.res_shapes)
+        nlev = len(self.res_shapes)
         merged = {}
         side = self._merge_stream
-        if not self.merge_early:
-            for ev in done_events:
-                side.wait_event(ev)
-
-        def block_span(kind, blks, li):
-            """rows of consecutive image blocks `blks` at level li when they sit back to back in ONE chain buffer"""
-            outs0, first0 = results[(kind, blks[0])]
-            for j, blk in enumerate(blks):
-                outs, first = results[(kind, blk)]
-                if outs is not outs0 or first != first0 + j * B:
-                    return None
-            c, H, W = self.res_shapes[li]
-            return outs0[li][first0 * H * W:(first0 + len(blks) * B) * H * W]
-
-        # early: level by level as the encoders produce them (only the mid level is left on the critical path between
-        # the encoders and the decoder); late: after both encoders, in the order the decoder consumes them
-        nlev = len(self.res_shapes)
-        if self.merge_mode == 2:
-            order = list(range(3, nlev)) + [2, 1, 0]
-        elif self.merge_early:
-            order = list(range(nlev))
-        else:
-            order = list(reversed(range(nlev)))
+        ev_main = torch.cuda.Event()
+        ev_main.record(main)
+        side.wait_event(ev_main)
+        for ev in done_events:
+            side.wait_event(ev)
+        split = min(self.merge_split, nlev) if mode == "step" else 0
+        level_groups = [list(reversed(range(split, nlev)))] + ([list(reversed(range(split)))] if split > 0 else [])
+        n_lora = len(geo.base_nets) - 1
+        z_dtype = torch.float32 if (self.dtype == torch.bfloat16 or not self.merge_z16) else self.dtype
         with torch.cuda.stream(side):
-            for li in order:
-                if self.merge_early:
-                    for lev in level_events:
-                        side.wait_event(lev[li])
-                c, H, W = self.res_shapes[li]
-                n = B * H * W
-                rb = self.buf(f"zres_b{li}", 3 * n, c)
-                rp = self.buf(f"zres_p{li}", 3 * n, c)
-                zw, zb = self.zero_base[li]
-                # zero convs (controllora.py:240-254): the three ControlLoRA image blocks (agn | clo | clo) are one GEMM
-                # with the weight set selected per row segment, the three openpose blocks one GEMM
-                span = block_span("base", (1, 2, 3), li)
-                if span is not None:
-                    ops.gemm(span, zw, c, out=rb, bias=zb, segs=([0, n, 3 * n], [0, c], None))
-                else:
-                    for slot, (blk, noff) in enumerate(((1, 0), (2, c), (3, c))):  # agn | clo(cond 2) | clo(cond 4)
-                        ops.gemm(block_rows("base", blk, li), zw, c, out=rb[slot * n:(slot + 1) * n], bias=zb,
-                                 segs=([0, n], [noff], None))
-                span = block_span("pose", (0, 1, 2), li)
-                if span is not None:
-                    ops.gemm(span, self.zero_pose[li][0], c, out=rp, bias=self.zero_pose[li][1])
-                else:
-                    for blk in range(3):
-                        ops.gemm(block_rows("pose", blk, li), self.zero_pose[li][0], c, out=rp[blk * n:(blk + 1) * n],
-                                 bias=self.zero_pose[li][1])
-                res = [rb[:n], rp[:n], rb[n:2 * n], rp[n:2 * n], rb[2 * n:], rp[2 * n:]]
-                z = self.buf(f"merge_z{li}", n, c, torch.float32)
-                unet_rows = block_rows("base", 0, li)
-                if mode == "residuals":
-                    dst, skip = self.buf(f"res_out{li}", n, c), None
-                elif li < len(self.res_shapes) - 1:
-                    cbuf, xc = cat_of_skip[li]
-                    dst, skip = cbuf[:, xc:], unet_rows
-                else:  # mid: becomes the x half of the first decoder concat
-                    dst, skip = cats[(0, 0)][0][:, :c], unet_rows
-                gn = None
-                G = cfg.norm_num_groups
-                if mode == "step" and li < len(self.res_shapes) - 1 and li in cat_gn:
-                    (ws_c, cpg_c), xc_c = cat_gn[li]          # skip half of the concat that consumes level li
-                    gn = (ws_c, G, cpg_c, xc_c)
-                elif mode == "step" and li == len(self.res_shapes) - 1 and cats[(0, 0)][0].data_ptr() in self._cat_slot:
-                    ws_c, cpg_c = self._cat_slot[cats[(0, 0)][0].data_ptr()]  # merged mid = x half of the first concat
-                    gn = (ws_c, G, cpg_c, 0)
-                ops.merge(res, [sc * level_gain[li] for sc in scale], self.merge[li], self._merge_slot(), z, B, H * W, c,
-                          dst, skip=skip, zero_stats=False, gn=gn)
+            for lg in level_groups:
+                table = []
+                for li in lg:
+                    c, H, W = self.res_shapes[li]
+                    n = B * H * W
+                    zw, zb = self.zero_base[li]
+                    res = [None] * 6
+                    # zero convs (controllora.py:240-254): the ControlLoRA image blocks (agn | clo | clo) are one GEMM
+                    # with the weight set selected per row segment, the openpose blocks one GEMM
+                    if n_lora:
+                        rb = self.buf(f"zres_b{li}.{n_lora}", n_lora * n, c)
+                        n_agn = n if geo.seg[1] else 0
+                        ops.gemm(outs_b[li][n:], zw, c, out=rb, bias=zb, segs=([0, n_agn, n_lora * n], [0, c], None))
+                        for pos, k in enumerate(geo.base_nets[1:]):
+                            res[k] = rb[pos * n:(pos + 1) * n]
+                    if nb_p:
+                        rp = self.buf(f"zres_p{li}.{nb_p}", nb_p * n, c)
+                        ops.gemm(outs_p[li], self.zero_pose[li][0], c, out=rp, bias=self.zero_pose[li][1])
+                        for pos, k in enumerate(geo.pose_nets):
+                            res[k] = rp[pos * n:(pos + 1) * n]
+                    unet_rows = outs_b[li][:n]
+                    res = [r if r is not None else unet_rows for r in res]  # never read: their scale is 0
+                    z = self.buf(f"merge_z{li}", n, c, z_dtype)
+                    if mode == "residuals":
+                        dst, skip = self.buf(f"res_out{li}", n, c), None
+                    elif li < nlev - 1:
+                        cbuf, xc = cat_of_skip[li]
+                        dst, skip = cbuf[:, xc:], unet_rows
+                    else:  # mid: becomes the x half of the first decoder concat
+                        dst, skip = cats[(0, 0)][0][:, :c], unet_rows
+                    gn = None
+                    G = cfg.norm_num_groups
+                    if mode == "step" and li < nlev - 1 and li in cat_gn:
+                        (ws_c, cpg_c), xc_c = cat_gn[li]          # skip half of the concat that consumes level li
+                        gn = (ws_c, G, cpg_c, xc_c)
+                    elif mode == "step" and li == nlev - 1 and cats[(0, 0)][0].data_ptr() in self._cat_slot:
+                        ws_c, cpg_c = self._cat_slot[cats[(0, 0)][0].data_ptr()]  # merged mid = x half of the first concat
+                        gn = (ws_c, G, cpg_c, 0)
+                    table.append(dict(res=res, prm=self.merge[li], stats=self._merge_slot(), z=z, hw=H * W, C=c, dst=dst,
+                                      skip=skip, gn=gn, gain=level_gain[li]))
+                ops.merge_levels(table, self.cond_scale_dev, B)
                 if zero_uncond:
-                    nu = (B // 2) * H * W  # rows of the unconditional images (negative prompt rows come first)
-                    if skip is not None:
-                        dst[:nu].copy_(skip[:nu])
-                    else:
-                        dst[:nu].zero_()
-                merged[li] = torch.cuda.Event()
-                merged[li].record(side)
+                    for lv in table:
+                        nu = (B // 2) * lv["hw"]  # rows of the unconditional images (negative prompt rows come first)
+                        if lv["skip"] is not None:
+                            lv["dst"][:nu].copy_(lv["skip"][:nu])
+                        else:
+                            lv["dst"][:nu].zero_()
+                ev = torch.cuda.Event()
+                ev.record(side)
+                for li in lg:
+                    merged[li] = ev
+        order = [li for lg in level_groups for li in lg]
         self._temb_ready = None
         if mode == "residuals":
             # the side stream is in order: the last event covers all levels
@@ -1088,7 +1272,7 @@ class DenoiseEngine:
         """noise_pred = UNet(sample, t, ehs, residuals(6 ControlNets + merge)) -- the fused single-step form the
         reference defines at /root/reference/export_onnx.py:43-74.  Returns a view of the static output buffer."""
         self._load_sample_t(sample, timestep)
-        key = tuple(float(s) for s in cond_scale)
+        key = self._set_cond_scale(cond_scale)
         if guess_mode or zero_uncond:  # the rare path: eager (no graph per flag combination)
             n0 = ops.LAUNCHES
             self._run_step(key, guess_mode=guess_mode, zero_uncond=zero_uncond)
@@ -1102,6 +1286,10 @@ class DenoiseEngine:
             return self.eps_out
         gph = self._graphs.get(key)
         if gph is None:
+            # one graph per SET of contributing nets (not per scale value: the scales are a device vector)
+            if self._tune:
+                ops.TUNER.enabled = True
+                self._tuning_done = False
             self._run_step(key)  # eager warm-up: allocates every buffer, sets kernel attributes, tunes GEMM tiles
             torch.cuda.synchronize()
             self._finish_tuning()
@@ -1121,10 +1309,24 @@ class DenoiseEngine:
                     self._run_step(key)
             finally:
                 ops.PREFETCH.end()
-            self.launches_per_step = ops.LAUNCHES - n0
+            self._graph_launches[key] = ops.LAUNCHES - n0
             self._graphs[key] = gph
+        self.launches_per_step = self._graph_launches[key]
         gph.replay()
         return self.eps_out
+
+    def _set_cond_scale(self, cond_scale: Sequence[float]) -> Tuple[bool, ...]:
+        """Upload the six conditioning scales (only when they changed) and return the set of contributing nets: the
+        key of the step's schedule / CUDA graph.  ES_SKIP_GATED=0 keeps gated nets in the batched passes (their
+        residuals are then multiplied by 0 inside the merge, as in the reference)."""
+        sc = tuple(float(x) for x in cond_scale)
+        assert len(sc) == 6
+        if sc != self._scale_host:
+            self.cond_scale_dev.copy_(torch.tensor(sc, dtype=torch.float32), non_blocking=False)
+            self._scale_host = sc
+        if os.environ.get("ES_SKIP_GATED", "1") == "0":
+            return (True,) * 6
+        return tuple(x != 0.0 for x in sc)
 
     def _finish_tuning(self):
         """Called after the first full eager step: freeze the tuner (lookups stay active) and dump the table."""
@@ -1148,7 +1350,7 @@ class DenoiseEngine:
         """EdgeStyleMultiControlNetModel.forward (edgestyle_multicontrolnet.py:116-171): 12 merged down residuals +
         mid as fresh NCHW fp32 tensors."""
         self._load_sample_t(sample, timestep)
-        self._run_step(tuple(float(s) for s in cond_scale), mode="residuals", guess_mode=guess_mode)
+        self._run_step(self._set_cond_scale(cond_scale), mode="residuals", guess_mode=guess_mode)
         outs = []
         for li, (c, H, W) in enumerate(self.res_shapes):
             dst = torch.empty(self.B, c, H, W, device=self.dev, dtype=torch.float32)
@@ -1176,7 +1378,7 @@ class DenoiseEngine:
         cond16 = self.buf("single.cond", B * hw, c0)
         ops.nchw_to_nhwc(cond.to(device=self.dev, dtype=torch.float32).contiguous(), cond16)
         x0 = self.buf("single.x0", B * hw, c0)
-        ops.gemm(col, E.conv_in, c0, out=x0, bias=E.conv_in_b, residual=cond16)
+        self._convw_block(E.conv_in, col, x0, 0 if group is None else group + 1, "single.ci", residual=cond16)
         ctx = self.buf("single.ctx", B * nt, cfg.cross_attention_dim)
         ctx.copy_(prompt_embeds.to(device=self.dev, dtype=self.dtype).reshape(B * nt, -1))
         seg = None if group is None else ((0, B, 0) if group == 0 else (0, 0, B))
@@ -1233,7 +1435,7 @@ class DenoiseEngine:
         return dst
 
     @torch.no_grad()
-    def embed_vae_latent(self, z: torch.Tensor) -> torch.Tensor:
+    def embed_vae_latent(self, z: torch.Tensor, group: Optional[int] = None) -> torch.Tensor:
         """Tail of VAEControlNetConditioningEmbedding.forward (controllora.py:40-41): `conv_vae_out(z)` where z is the
         scaled VAE latent [n, 4, h, w] fp32 NCHW.  `conv_vae_out` IS the net's `conv_in` module (:36), whose parameters
         `tie_weights` points at the UNet's conv_in (:624), so this runs the UNet conv_in weights (SURVEY.md appendix,
@@ -1247,7 +1449,9 @@ class DenoiseEngine:
         col = self.buf(f"vemb.col.{n}x{h}x{w}", n * h * w, 64)
         ops.im2col3x3(s16, col, n, h, w, cfg.in_channels, 1)
         out = self.buf(f"vemb.out.{n}x{h}x{w}", n * h * w, c0)
-        ops.gemm(col, self.enc_base.conv_in, c0, out=out, bias=self.enc_base.conv_in_b)
+        # `group`: the ControlLoRA net the embedder belongs to -- with a conv LoRA (lora_conv2d_rank > 0) its conv_in
+        # carries that net's low-rank update, and conv_vae_out is that very module
+        self._convw_block(self.enc_base.conv_in, col, out, 0 if group is None else group + 1, "vemb.ci")
         dst = torch.empty(n, c0, h, w, device=self.dev, dtype=torch.float32)
         ops.nhwc_to_nchw(out, dst)
         return dst

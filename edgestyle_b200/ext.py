@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ES_LIB", os.path.join(HERE, "libedgestyle_b200.so"))
 
 ES_MAX_SEG = 4
+ABI_VERSION = 2  # 2: es_merge_levels (level table, device-side scales) replaced es_merge_phase
 DTYPE_F16, DTYPE_BF16 = 0, 1
 ACT_NONE, ACT_GEGLU, ACT_SILU = 0, 1, 2
 
@@ -49,12 +50,22 @@ class EsGroupNorm(C.Structure):
     ]
 
 
-class EsMerge(C.Structure):
+ES_MERGE_MAX_LEVELS = 16
+
+
+class EsMergeLevel(C.Structure):
     _fields_ = [
-        ("dtype", C.c_int), ("res", vp * 6), ("scale", C.c_float * 6), ("B", C.c_int), ("hw", C.c_int),
-        ("C", C.c_int), ("w1", vp), ("b1", vp), ("w2", vp), ("b2", vp), ("w3", vp), ("b3", vp), ("g1", vp),
-        ("be1", vp), ("g2", vp), ("be2", vp), ("stats", vp), ("z", vp), ("skip", vp), ("lds", ll), ("dst", vp),
-        ("ldd", ll), ("gn_ws", vp), ("gn_groups", C.c_int), ("gn_cpg", C.c_int), ("gn_col0", C.c_int),
+        ("res", vp * 6), ("w1", vp), ("b1", vp), ("w2", vp), ("b2", vp), ("w3", vp), ("b3", vp), ("g1", vp),
+        ("be1", vp), ("g2", vp), ("be2", vp), ("stats", vp), ("z", vp), ("skip", vp), ("dst", vp), ("gn_ws", vp),
+        ("lds", ll), ("ldd", ll), ("hw", C.c_int), ("C", C.c_int), ("gn_groups", C.c_int), ("gn_cpg", C.c_int),
+        ("gn_col0", C.c_int), ("z_f32", C.c_int), ("gain", C.c_float),
+    ]
+
+
+class EsMergeBatch(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int), ("B", C.c_int), ("n_levels", C.c_int), ("scale", vp),
+        ("levels", EsMergeLevel * ES_MERGE_MAX_LEVELS),
     ]
 
 
@@ -68,7 +79,7 @@ EXPORTS = {
     "es_groupnorm_apply": (C.c_int, [C.POINTER(EsGroupNorm), vp]),
     "es_groupnorm_fused": (C.c_int, [C.POINTER(EsGroupNorm), vp]),
     "es_layernorm": (C.c_int, [C.c_int, vp, ll, vp, ll, vp, vp, C.c_int, C.c_int, C.c_float, vp]),
-    "es_merge_phase": (C.c_int, [C.POINTER(EsMerge), C.c_int, vp]),
+    "es_merge_levels": (C.c_int, [C.POINTER(EsMergeBatch), C.c_int, vp]),
     "es_timestep_embedding": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
     "es_small_linear": (C.c_int, [C.c_int, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, vp]),
@@ -107,7 +118,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.es_abi_version() != 1:
+    if lib.es_abi_version() != ABI_VERSION:
         raise EdgeStyleNativeError("ABI version mismatch between ext.py and libedgestyle_b200.so")
     _lib = lib
     return lib

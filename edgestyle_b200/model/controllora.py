@@ -67,6 +67,12 @@ def _config_from_dict(d: dict) -> C.UNetConfig:
     kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in d.items() if k in names}
     if "num_heads" not in kw and "attention_head_dim" in d and isinstance(d["attention_head_dim"], int):
         kw["num_heads"] = d["attention_head_dim"]
+    if "down_has_attn" not in kw and "down_block_types" in d:  # diffusers' own config.json names the block classes
+        known = {"CrossAttnDownBlock2D": True, "DownBlock2D": False}
+        bad = [t for t in d["down_block_types"] if t not in known]
+        if bad:
+            raise NotImplementedError(f"down_block_types {bad}: the engine implements CrossAttnDownBlock2D / DownBlock2D")
+        kw["down_has_attn"] = tuple(known[t] for t in d["down_block_types"])
     return C.UNetConfig(**kw)
 
 
@@ -121,6 +127,22 @@ class CachedControlNetModel:
     def state_dict(self):
         return self._sd
 
+    def _weights_changed(self):
+        """The owning multi-ControlNet caches engines that hold packed device copies of these weights (and captured
+        CUDA graphs): drop them, so the next forward runs the new weights -- in the reference the modules are live."""
+        if self._owner is not None:
+            self._owner._invalidate_engines()
+
+    def load_state_dict(self, state_dict: Mapping[str, Any], strict: bool = True):
+        for k, v in state_dict.items():
+            if k in self._sd:
+                if tuple(v.shape) != tuple(self._sd[k].shape):
+                    raise ValueError(f"{k}: shape {tuple(v.shape)} != {tuple(self._sd[k].shape)}")
+                self._sd[k] = v
+            elif strict:
+                raise KeyError(k)
+        self._weights_changed()
+
     # -- reference surface -------------------------------------------------------------------
     def forward(self, sample, timestep, encoder_hidden_states, controlnet_cond, conditioning_scale: float = 1.0,
                 class_labels=None, timestep_cond=None, attention_mask=None, added_cond_kwargs=None,
@@ -173,11 +195,13 @@ class CachedControlNetModel:
         if repeats > 1:
             dist = dist.repeat(repeats)
         z = dist.sample(generator=generator, noise=noise, scale=vae.config.scaling_factor)  # :39-40
-        return self._owner.embed_engine(z.shape[0], H // 8, W // 8).embed_vae_latent(z)       # :41
+        # :41 -- conv_vae_out IS this net's conv_in (with its conv LoRA, if any)
+        return self._owner.embed_engine(z.shape[0], H // 8, W // 8).embed_vae_latent(z, self._owner.lora_group(self))
 
     # -- checkpoint format (diffusers layout: <dir>/config.json + <dir>/diffusion_pytorch_model.safetensors) ------
     def _extra_config(self) -> dict:
-        return {"_class_name": "ControlNetModel"}
+        return {"_class_name": "ControlNetModel",
+                "controlnet_conditioning_channel_order": self.controlnet_conditioning_channel_order}
 
     def save_pretrained(self, directory, **_):
         _save_dir(directory, self.state_dict(), _config_dict(self.config, **self._extra_config()))
@@ -185,7 +209,9 @@ class CachedControlNetModel:
     @classmethod
     def from_pretrained(cls, directory, **_):
         sd, cfg = _load_dir(directory)
-        return cls(_config_from_dict(cfg), sd)
+        net = cls(_config_from_dict(cfg), sd)
+        net.controlnet_conditioning_channel_order = cfg.get("controlnet_conditioning_channel_order", "rgb")
+        return net
 
 
 class ControlLoRAModel(CachedControlNetModel):
@@ -200,10 +226,9 @@ class ControlLoRAModel(CachedControlNetModel):
     def __init__(self, config: C.UNetConfig, state_dict: Mapping[str, torch.Tensor], lora_linear_rank: int = 4,
                  lora_conv2d_rank: int = 0, unet: Optional[UNet2DConditionModel] = None):
         self.config = C.UNetConfig.from_any(config)
-        if lora_conv2d_rank > 0:
-            raise NotImplementedError("lora_conv2d_rank > 0 (conv LoRA, controllora.py:561-575) is not implemented")
         self.lora_linear_rank, self.lora_conv2d_rank = lora_linear_rank, lora_conv2d_rank
-        spec = dict(C.lora_spec(self.config, lora_linear_rank))
+        # lora_conv2d_rank > 0: a LoRAConv2dLayer on every convolution too -- of rank lora_linear_rank (controllora.py:569)
+        spec = dict(C.lora_spec(self.config, lora_linear_rank, lora_conv2d_rank))
         spec.update(C.controlnet_extra_spec(self.config, with_embedder=False))
         filtered = OrderedDict((k, v) for k, v in state_dict.items()
                                if k.split(".")[0] not in self._skip_layers or ".lora_layer." in k)
@@ -213,6 +238,11 @@ class ControlLoRAModel(CachedControlNetModel):
         self._owner = None
         self._slots = []
         self.controlnet_conditioning_channel_order = "rgb"
+        self.autoencoder = None
+
+    @property
+    def uses_vae(self) -> bool:
+        return self.autoencoder is not None
 
     @classmethod
     def from_unet(cls, unet: UNet2DConditionModel, conditioning_channels: int = 3,
@@ -221,8 +251,12 @@ class ControlLoRAModel(CachedControlNetModel):
                   lora_conv2d_rank: int = 0, autoencoder=None, generator: Optional[torch.Generator] = None):
         """Fresh LoRA (down ~ N(0, 1/r^2), up = 0) and zero zero-convs, tied to `unet` (controllora.py:644-725)."""
         cfg = unet.config
+        if conditioning_channels != cfg.conditioning_channels or \
+                tuple(conditioning_embedding_out_channels) != tuple(cfg.conditioning_embedding_out_channels):
+            raise NotImplementedError("a ControlLoRA net embeds its control image with the VAE (controllora.py:596-598): "
+                                      "non-default conditioning_channels / conditioning_embedding_out_channels are unused")
         sd = OrderedDict()
-        for k, shape in C.lora_spec(cfg, lora_linear_rank).items():
+        for k, shape in C.lora_spec(cfg, lora_linear_rank, lora_conv2d_rank).items():
             if k.endswith("down.weight"):
                 sd[k] = torch.randn(shape, generator=generator) / lora_linear_rank
             else:
@@ -231,10 +265,15 @@ class ControlLoRAModel(CachedControlNetModel):
             sd[k] = torch.zeros(shape)
         net = cls(cfg, sd, lora_linear_rank, lora_conv2d_rank, unet)
         net.controlnet_conditioning_channel_order = controlnet_conditioning_channel_order
+        if autoencoder is not None:  # controllora.py:718-722
+            net.set_autoencoder(autoencoder)
         return net
 
     def tie_weights(self, unet: UNet2DConditionModel):
+        changed = unet is not self._unet
         self._unet = unet
+        if changed:
+            self._weights_changed()
 
     def set_autoencoder(self, autoencoder):
         self.autoencoder = autoencoder
@@ -242,20 +281,26 @@ class ControlLoRAModel(CachedControlNetModel):
     def load_state_dict(self, state_dict: Mapping[str, Any], strict: bool = True):
         for k, v in state_dict.items():
             if k in self._sd:
+                if tuple(v.shape) != tuple(self._sd[k].shape):
+                    raise ValueError(f"{k}: shape {tuple(v.shape)} != {tuple(self._sd[k].shape)}")
                 self._sd[k] = v
             elif strict and (k.split(".")[0] not in self._skip_layers) and not k.startswith("controlnet_cond_embedding."):
                 raise KeyError(k)
+        self._weights_changed()
 
     def _extra_config(self) -> dict:
         return {"_class_name": "ControlLoRAModel", "lora_linear_rank": self.lora_linear_rank,
-                "lora_conv2d_rank": self.lora_conv2d_rank, "uses_vae": True}
+                "lora_conv2d_rank": self.lora_conv2d_rank, "uses_vae": self.uses_vae,
+                "controlnet_conditioning_channel_order": self.controlnet_conditioning_channel_order}
 
     @classmethod
     def from_pretrained(cls, directory, unet: Optional[UNet2DConditionModel] = None, **_):
         """Loads only LoRA + non-tied tensors (what :600-606 saves); call tie_weights(unet) afterwards (app.py:95-97)."""
         sd, cfg = _load_dir(directory)
-        return cls(_config_from_dict(cfg), sd, lora_linear_rank=cfg.get("lora_linear_rank", 4),
-                   lora_conv2d_rank=cfg.get("lora_conv2d_rank", 0), unet=unet)
+        net = cls(_config_from_dict(cfg), sd, lora_linear_rank=cfg.get("lora_linear_rank", 4),
+                  lora_conv2d_rank=cfg.get("lora_conv2d_rank", 0), unet=unet)
+        net.controlnet_conditioning_channel_order = cfg.get("controlnet_conditioning_channel_order", "rgb")
+        return net
 
     def fused_state_dict(self, lora_scale: float = 1.0) -> "OrderedDict[str, torch.Tensor]":
         """Full diffusers-layout ControlNet state dict of this net with the LoRA folded in: every tied base tensor of the
@@ -271,8 +316,9 @@ class ControlLoRAModel(CachedControlNetModel):
             if k.endswith(".weight"):
                 base = k[:-len(".weight")]
                 dn, up = self._sd.get(f"{base}.lora_layer.down.weight"), self._sd.get(f"{base}.lora_layer.up.weight")
-                if dn is not None and up is not None:
-                    w = (w.float() + lora_scale * (up.float() @ dn.float())).to(w.dtype)
+                if dn is not None and up is not None:  # Linear, or LoRACompatibleConv._fuse_lora (flatten(1) on both)
+                    upd = (up.float().flatten(1) @ dn.float().flatten(1)).reshape(w.shape)
+                    w = (w.float() + lora_scale * upd).to(w.dtype)
             out[k] = w
         for k, v in self._sd.items():  # conv_vae_out is an alias of the (tied) conv_in module (controllora.py:36)
             if ".lora_layer." not in k and k not in out and not k.startswith("controlnet_cond_embedding.conv_vae_out."):
@@ -285,7 +331,7 @@ class ControlLoRAModel(CachedControlNetModel):
         the UNet (and stacks both nets' updates when two ControlLoRAs share it) -- the UNet is left untouched."""
         net = FusedControlLoRAModel(self.config, self.fused_state_dict(1.0))
         net.controlnet_conditioning_channel_order = self.controlnet_conditioning_channel_order
-        if getattr(self, "autoencoder", None) is not None:
+        if self.autoencoder is not None:
             net.autoencoder = self.autoencoder
         return net
 

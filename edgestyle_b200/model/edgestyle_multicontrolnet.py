@@ -57,6 +57,27 @@ class EdgeStyleMultiControlNetModel:
     def state_dict(self):
         return self._merge_sd
 
+    def load_state_dict(self, state_dict: Mapping, strict: bool = True):
+        """Merge-block tensors (edgestyle_multicontrolnet.py:173-193); cached engines are rebuilt on the next call."""
+        spec = C.merge_spec(self.config, *self.latent_hw)
+        if strict:
+            _check_spec(state_dict, spec, "EdgeStyleMultiControlNetModel")
+        for k, v in state_dict.items():
+            if k in spec:
+                self._merge_sd[k] = v
+        self._invalidate_engines()
+
+    def _invalidate_engines(self):
+        """Engines hold packed device copies of the nets' weights and captured CUDA graphs: a weight reload / re-tie of
+        any net (ControlLoRAModel.load_state_dict / tie_weights) must drop them (the reference's modules are live)."""
+        self._engines.clear()
+
+    def lora_group(self, net) -> Optional[int]:
+        """LoRA weight group of a registered net inside the engine: 0 = agnostic set, 1 = clothes set, None = plain."""
+        if not net.uses_lora:
+            return None
+        return 0 if net is self.nets[0] else 1
+
     def unet(self) -> UNet2DConditionModel:
         u = self.nets[0]._unet
         if u is None or self.nets[2]._unet is not u:
@@ -122,10 +143,9 @@ class EdgeStyleMultiControlNetModel:
     def _single_forward(self, net, sample, timestep, ehs, cond, scale, guess_mode):
         B, _, h, w = sample.shape
         eng = self.engine(B, h, w)
-        group = None if not net.uses_lora else (0 if net is self.nets[0] else 1)
-        return eng.single_controlnet(group, sample, timestep, ehs, cond, scale, guess_mode)
+        return eng.single_controlnet(self.lora_group(net), sample, timestep, ehs, cond, scale, guess_mode)
 
-    def fuse(self):
+    def fuse(self):  # noqa: D401
         """edgestyle_multicontrolnet.py:284-287 replaces every ControlLoRA net by `net.fuse()`.  Here the nets stay
         (so their conditioning embeddings remain cacheable, which the reference loses after fusing: SURVEY.md appendix,
         quirk 11) and the engine is pinned to one fused weight copy `W + up @ down` per LoRA group -- the same
@@ -158,7 +178,8 @@ class EdgeStyleMultiControlNetModel:
 
     @classmethod
     def from_pretrained(cls, pretrained_model_path, *, load_pattern=None, static_controlnets=None,
-                        controlnet_class=ControlLoRAModel, vae=None, torch_dtype=None, latent_hw=(64, 64), **kwargs):
+                        controlnet_class=ControlLoRAModel, vae=None, torch_dtype=None, latent_hw=(64, 64),
+                        variant: Optional[str] = None, **kwargs):
         import os
 
         from safetensors.torch import load_file
@@ -167,6 +188,9 @@ class EdgeStyleMultiControlNetModel:
 
         if not os.path.isdir(pretrained_model_path):
             raise ValueError(f"Provided path ({pretrained_model_path}) should be a directory")
+        if variant is not None:
+            raise NotImplementedError("weight-file variants (e.g. 'fp16') are not implemented: the mirrors read "
+                                      "diffusion_pytorch_model.safetensors")
         if load_pattern is None:
             raise ValueError("load_pattern must be provided")
         static_controlnets = static_controlnets or [None] * len(load_pattern)

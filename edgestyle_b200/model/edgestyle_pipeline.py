@@ -171,9 +171,21 @@ class EdgeStyleStableDiffusionControlNetPipeline:
                 a_t, a_prev = sch.coefficients(int(t))
                 eng.cfg_ddim_update(latents, a_t, a_prev)
             self.h2d_bytes += 4 + 16  # timestep + 4 scheduler coefficients
-            if callback_on_step_end is not None:
-                out = callback_on_step_end(self, i, t, {k: locals()[k] for k in callback_on_step_end_tensor_inputs})
-                latents = out.pop("latents", latents) if out else latents
+            if callback_on_step_end is not None:  # :523-533
+                avail = {"latents": latents, "prompt_embeds": pe[n_img:] if cfg_on else pe,
+                         "negative_prompt_embeds": pe[:n_img] if cfg_on else None}
+                callback_kwargs = {}
+                for k in callback_on_step_end_tensor_inputs:
+                    if k not in avail:
+                        raise KeyError(f"callback_on_step_end_tensor_inputs: {k!r} is not available (have {sorted(avail)})")
+                    callback_kwargs[k] = avail[k]
+                out = callback_on_step_end(self, i, t, callback_kwargs) or {}
+                latents = out.pop("latents", latents)
+                if "prompt_embeds" in out or "negative_prompt_embeds" in out:
+                    p_new = out.pop("prompt_embeds", avail["prompt_embeds"])
+                    n_new = out.pop("negative_prompt_embeds", avail["negative_prompt_embeds"])
+                    pe = torch.cat([self._to_dev(n_new, dev), self._to_dev(p_new, dev)]) if cfg_on else self._to_dev(p_new, dev)
+                    eng.set_prompt(pe)
         images = latents
         if output_type != "latent":  # :552-572 (no safety checker: has_nsfw_concept is None, every image denormalised)
             images = self.vae.decode(latents / self.vae.config.scaling_factor, return_dict=False, generator=generator)[0]

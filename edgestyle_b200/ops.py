@@ -11,7 +11,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import ext
-from .ext import ACT_GEGLU, ACT_NONE, EsAttention, EsGemm, EsGroupNorm, EsMerge, check, load
+from .ext import ACT_GEGLU, ACT_NONE, EsAttention, EsGemm, EsGroupNorm, EsMergeBatch, check, load
 
 
 GEMM_WORKSPACE: Optional[torch.Tensor] = None  # default split-K scratch (zero-initialised uint8 tensor), see EsGemm
@@ -202,7 +202,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, out: torch.Tensor, taps: i
     ln = (rowstat [M, 2] of the rows of `a`, colsum fp32 [n_total], features, eps): LayerNorm folded into this GEMM
     (b must be W * gamma and bias = bias + W beta, see include/edgestyle_b200.h).
 
-    whn=(w, h, n_img) for taps == 9.  segs = list of (row_start, b_noff, b2_noff) + final row end via segs_end.
+    whn=(w, h, n_img) for taps == 9.  segs = (starts [nseg + 1], b_noff [nseg], b2_noff [nseg] or None): segment
+    boundaries in rows (taps == 1) or images (taps == 9), weight-row offset of each segment in b / bias and in b2.
     """
     _need_cuda(a, b, out)
     g = EsGemm()
@@ -365,33 +366,53 @@ def layernorm(x, out, gamma, beta, eps: float = 1e-5):
     return out
 
 
-def merge(res: Sequence[torch.Tensor], scale: Sequence[float], prm: dict, stats, z, B: int, hw: int, Cc: int, dst,
-          skip=None, zero_stats: bool = True, gn=None):
-    """EdgeStyle ControlNetBlock over six [B*hw, C] residual slabs; dst = skip + block(res).
+def merge_levels(levels: Sequence[dict], scale_dev: torch.Tensor, B: int):
+    """EdgeStyle ControlNetBlock for several residual levels at once: three launches (one per phase) whatever the
+    number of levels.  Every level is a dict(res=[6 x [B*hw, C]], prm=pack_merge_block(...), stats=fp64 [B, 4] (zero),
+    z=[B*hw, C] scratch (fp32 or the activation dtype), hw, C, dst, skip=None, gn=None, gain=1.0); dst = skip + block(res).
 
+    scale_dev: fp32 CUDA tensor [6] with the conditioning scales (read by the kernels, so a captured graph follows it).
     gn = (ws [B, groups, 2] fp32, groups, channels per group, first channel): also accumulate the GroupNorm statistics
     of the rows written to dst, which is a column slice of the tensor the consumer normalises."""
-    m = EsMerge()
-    m.dtype = _dt(res[0])
-    for i in range(6):
-        m.res[i] = res[i].data_ptr()
-        m.scale[i] = float(scale[i])
-    m.B, m.hw, m.C = B, hw, Cc
-    for k in ("w1", "b1", "w2", "b2", "w3", "b3", "g1", "be1", "g2", "be2"):
-        setattr(m, k, prm[k].data_ptr())
-    m.stats, m.z = stats.data_ptr(), z.data_ptr()
-    if skip is not None:
-        m.skip, m.lds = skip.data_ptr(), skip.stride(0)
-    m.dst, m.ldd = dst.data_ptr(), dst.stride(0)
-    if gn is not None:
-        gws, m.gn_groups, m.gn_cpg, m.gn_col0 = gn
-        m.gn_ws = gws.data_ptr()
+    assert 1 <= len(levels) <= ext.ES_MERGE_MAX_LEVELS
+    _need_cuda(scale_dev)
+    assert scale_dev.dtype == torch.float32 and scale_dev.numel() >= 6
+    m = EsMergeBatch()
+    m.dtype = _dt(levels[0]["res"][0])
+    m.B, m.n_levels, m.scale = B, len(levels), scale_dev.data_ptr()
+    for i, lv in enumerate(levels):
+        L = m.levels[i]
+        _need_cuda(lv["dst"], lv["z"], lv["stats"])
+        for k in range(6):
+            L.res[k] = lv["res"][k].data_ptr()
+        prm = lv["prm"]
+        for k in ("w1", "b1", "w2", "b2", "w3", "b3", "g1", "be1", "g2", "be2"):
+            setattr(L, k, prm[k].data_ptr())
+        L.hw, L.C = lv["hw"], lv["C"]
+        L.stats, L.z = lv["stats"].data_ptr(), lv["z"].data_ptr()
+        L.z_f32 = 1 if lv["z"].dtype == torch.float32 else 0
+        skip = lv.get("skip")
+        if skip is not None:
+            L.skip, L.lds = skip.data_ptr(), skip.stride(0)
+        L.dst, L.ldd = lv["dst"].data_ptr(), lv["dst"].stride(0)
+        gn = lv.get("gn")
+        if gn is not None:
+            gws, L.gn_groups, L.gn_cpg, L.gn_col0 = gn
+            L.gn_ws = gws.data_ptr()
+        L.gain = float(lv.get("gain", 1.0))
+    lib = load()
+    _count(3)  # three phases, all levels in each
+    for ph in (1, 2, 3):
+        check(lib.es_merge_levels(C.byref(m), ph, _stream()), f"es_merge_levels({ph})")
+
+
+def merge(res: Sequence[torch.Tensor], scale: Sequence[float], prm: dict, stats, z, B: int, hw: int, Cc: int, dst,
+          skip=None, zero_stats: bool = True, gn=None):
+    """One ControlNetBlock over six [B*hw, C] residual slabs (a one-level `merge_levels`); host-side scales."""
     if zero_stats:
         stats.zero_()
-    lib = load()
-    _count(3)  # three phases (the stats memset is torch's)
-    for ph in (1, 2, 3):
-        check(lib.es_merge_phase(C.byref(m), ph, _stream()), f"es_merge_phase({ph})")
+    sc = torch.tensor([float(x) for x in scale], dtype=torch.float32, device=dst.device)
+    merge_levels([dict(res=res, prm=prm, stats=stats, z=z, hw=hw, C=Cc, dst=dst, skip=skip, gn=gn)], sc, B)
     return dst
 
 

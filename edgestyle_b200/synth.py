@@ -36,13 +36,14 @@ def _fill(spec: Dict[str, Tuple[int, ...]], gen: torch.Generator, device) -> Dic
     return out
 
 
-def synth_state_dicts(cfg: C.UNetConfig, h: int, w: int, rank: int = 32, seed: int = 0, device="cpu"):
+def synth_state_dicts(cfg: C.UNetConfig, h: int, w: int, rank: int = 32, seed: int = 0, device="cpu",
+                      conv_rank: int = 0):
     """Returns dict(unet=..., lora=[agn, clo], pose=..., merge=...) of fp32 tensors."""
     gen = torch.Generator(device=device).manual_seed(seed)
     unet = _fill(C.unet_spec(cfg), gen, device)
     loras = []
     for _ in range(2):
-        spec = dict(C.lora_spec(cfg, rank))
+        spec = dict(C.lora_spec(cfg, rank, conv_rank))
         spec.update(C.controlnet_extra_spec(cfg, with_embedder=False))
         loras.append(_fill(spec, gen, device))
     pose_spec = dict(C.encoder_spec(cfg))

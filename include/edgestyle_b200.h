@@ -48,8 +48,11 @@ int es_set_pdl(int enabled);
  *               + residual[m, n]
  *
  *   A is [n_img, h, w, c1] with pixel pitch `lda` elements (flat GEMM: w = M, h = n_img = 1).
- *   Row segments (flat only): rows [seg_row_start[g], seg_row_start[g+1]) use weight-row offset
- *   seg_b_noff[g] in B/bias and seg_b2_noff[g] in B2 (-1: no source 2 for that segment).
+ *   Segments: rows (flat GEMM) or IMAGES (taps == 9; boundaries on tile boundaries) [seg_row_start[g],
+ *   seg_row_start[g+1]) use weight-row offset seg_b_noff[g] in B/bias and seg_b2_noff[g] in B2 (-1: no source 2
+ *   for that segment).  This is how one batched pass serves the UNet rows and the ControlLoRA rows: a fused weight
+ *   copy W + up_g down_g per LoRA group (Linear: controllora.py:578-593; conv: :561-575), or -- unfused -- the
+ *   rank-r update as source 2 (A2 = x (*) down_g, B2 = up_g).
  * ------------------------------------------------------------------------------------------ */
 typedef struct EsGemm {
   int dtype;
@@ -168,34 +171,44 @@ int es_layernorm(int dtype, const void* x, long long ldx, void* out, long long l
 
 /* ------------------------------------------------------------------------------------------
  * EdgeStyle merge (ControlNetBlock, /root/reference/model/edgestyle_multicontrolnet.py:23-63 with
- * the interleave of :160-164,479-514 folded into indexing; closed form in SURVEY.md A.9).
+ * the interleave of :160-164,479-514 folded into indexing; closed form in SURVEY.md A.9), for up to
+ * ES_MERGE_MAX_LEVELS residual levels per launch (the 13 blocks of :104-114 run as ONE grid per phase).
  *   res[k]  : residual of net k, [B, hw, C] (zero-conv outputs, NOT yet scaled); k = 0..5
- *   scale[k]: conditioning_scale (controllora.py:267-270)
- *   params (repacked channels-last by the host): w1 [C][3][2], b1 [C][3], g1/be1 [hw][3][C] (dtype),
- *           w2 [C][3], b2 [C], g2/be2 [hw][C] (dtype), w3 [C], b3 [C]
- *   phase 1: sums of u  -> stats[b][0..1];  phase 2: z (fp32, [B,hw,C]) + sums of z -> stats[b][2..3];
+ *   scale   : DEVICE vector [6] of conditioning_scale (controllora.py:267-270); a level multiplies it by
+ *             `gain` (guess_mode: logspace(-1, 0, 13)[level], controllora.py:257-265).  Nets whose scale is 0
+ *             are not read (control_guidance gating, edgestyle_pipeline.py:418-427).
+ *   params (repacked channels-last by the host): w1 [3][2][C], b1 [3][C], g1/be1 [hw][3][C] (dtype),
+ *           w2 [3][C], b2 [C], g2/be2 [hw][C] (dtype), w3 [C], b3 [C]
+ *   phase 1: sums of u  -> stats[b][0..1];  phase 2: z ([B,hw,C], fp32 or dtype) + sums of z -> stats[b][2..3];
  *   phase 3: dst[b,p,c] = skip[b,p,c] + w3*SiLU(LN(z))+b3   (skip may be NULL; dst pitch ldd)
  * ------------------------------------------------------------------------------------------ */
-typedef struct EsMerge {
-  int dtype;
+#define ES_MERGE_MAX_LEVELS 16
+typedef struct EsMergeLevel {
   const void* res[6];
-  float scale[6];
-  int B, hw, C;
   const float *w1, *b1, *w2, *b2, *w3, *b3;
   const void *g1, *be1, *g2, *be2;
   double* stats; /* [B][4], zeroed by the caller */
-  float* z;      /* [B][hw][C] */
+  void* z;       /* [B][hw][C], fp32 when z_f32 else `dtype` */
   const void* skip;
-  long long lds;
   void* dst;
-  long long ldd;
   /* optional (phase 3): accumulate GroupNorm statistics of what is written to dst, for a consumer that normalises the
    * tensor dst is a column slice of: ws [B][gn_groups][2] (sum, sumsq; zeroed by the caller), channels per group of the
    * whole tensor, channel of that tensor column 0 of dst lands on */
   float* gn_ws;
+  long long lds, ldd;
+  int hw, C;
   int gn_groups, gn_cpg, gn_col0;
-} EsMerge;
-int es_merge_phase(const EsMerge* m, int phase, void* stream);
+  int z_f32;
+  float gain;
+} EsMergeLevel;
+typedef struct EsMergeBatch {
+  int dtype;
+  int B;
+  int n_levels;
+  const float* scale; /* DEVICE pointer, 6 floats */
+  EsMergeLevel levels[ES_MERGE_MAX_LEVELS];
+} EsMergeBatch;
+int es_merge_levels(const EsMergeBatch* m, int phase, void* stream);
 
 /* ------------------------------------------------------------------------------------------ misc */
 /* sinusoidal timestep embedding (flip_sin_to_cos, freq_shift 0): out fp32 [n][dim]; controllora.py:150 */

@@ -28,7 +28,7 @@ def test_header_symbols_exported(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
         assert name in ext.EXPORTS, f"{name} has no ctypes signature in ext.py"
-    assert lib.es_abi_version() == 1
+    assert lib.es_abi_version() == ext.ABI_VERSION == 2
 
 
 def test_struct_sizes_match_c(tmp_path, lib):
@@ -38,12 +38,12 @@ def test_struct_sizes_match_c(tmp_path, lib):
     prog = tmp_path / "sz.c"
     prog.write_text(
         '#include <stdio.h>\n#include "edgestyle_b200.h"\n'
-        'int main(){printf("%zu %zu %zu %zu\\n", sizeof(EsGemm), sizeof(EsAttention), sizeof(EsGroupNorm), sizeof(EsMerge));return 0;}\n')
+        'int main(){printf("%zu %zu %zu %zu\\n", sizeof(EsGemm), sizeof(EsAttention), sizeof(EsGroupNorm), sizeof(EsMergeBatch));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     want = [ctypes.sizeof(ext.EsGemm), ctypes.sizeof(ext.EsAttention), ctypes.sizeof(ext.EsGroupNorm),
-            ctypes.sizeof(ext.EsMerge)]
+            ctypes.sizeof(ext.EsMergeBatch)]
     assert [int(x) for x in out] == want
 
 

@@ -9,17 +9,17 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _mk(cfg, h, w, rank, images=1, dtype=torch.float16, use_graph=False):
+def _mk(cfg, h, w, rank, images=1, dtype=torch.float16, use_graph=False, lora_conv2d_rank=0, fuse_lora=None):
     from edgestyle_b200.engine import DenoiseEngine
     from oracle.step import build_models, synthetic_inputs
 
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    m = build_models(cfg, (h, w), rank=rank)
+    m = build_models(cfg, (h, w), rank=rank, lora_conv2d_rank=lora_conv2d_rank)
     inp = synthetic_inputs(cfg, images, h, w)
     eng = DenoiseEngine(cfg, m.unet.state_dict(), [m.lora_agnostic.state_dict(), m.lora_clothes.state_dict()],
                         m.openpose.state_dict(), m.controlnet.merge_state_dict(), rows=2 * images, h=h, w=w,
-                        dtype=dtype, use_graph=use_graph)
+                        dtype=dtype, use_graph=use_graph, fuse_lora=fuse_lora)
     m.unet.to(DEV)
     m.controlnet.to(DEV)
     inp.latents = inp.latents.to(DEV)
@@ -55,6 +55,134 @@ def test_step_parity_small(h, w, images, scale):
     got = eng.step(x, t, scale)
     cos, mx = _metrics(got, want)
     assert cos >= 0.999 and mx <= 2e-2, (cos, mx)
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+@pytest.mark.parametrize("h,w,images", [(16, 16, 1), (16, 32, 2)])
+def test_conv_lora_parity(fuse, h, w, images):
+    """lora_conv2d_rank > 0 (/root/reference/model/controllora.py:561-575): a LoRAConv2dLayer of rank
+    lora_linear_rank (sic, :569) on conv_in, every resnet conv / shortcut, the down-samplers and proj_in / proj_out.
+    fuse=True: one fused weight copy per LoRA group selected per image segment (the reference's own `fuse_lora`);
+    fuse=False: the rank-r update as a K-extension of the conv GEMM (source 2 = down-conv output, B2 = up).  The
+    16x16 latent covers single-launch image segments (16x16 / 8x8 levels) and ragged ones (4x4 / 2x2: many images
+    per tile -> one launch per segment)."""
+    from oracle.sd15 import SD15Config
+    from oracle.step import fused_step
+
+    cfg = SD15Config(block_out_channels=(64, 128, 256, 256), cross_attention_dim=96)
+    m, inp, eng = _mk(cfg, h, w, rank=4, images=images, lora_conv2d_rank=4, fuse_lora=fuse)
+    assert any(".conv1.lora_layer.down.weight" in k for k in m.lora_agnostic.state_dict())
+    x = torch.cat([inp.latents] * 2)
+    t = torch.tensor(651, device=DEV)
+    scale = [1.0, 0.5, 2.0, 1.0, 1.0, 1.5]
+    want = fused_step(m, x, t, inp.prompt_embeds, scale, inp.conds)
+    got = eng.step(x, t, scale)
+    cos, mx = _metrics(got, want)
+    assert cos >= 0.999 and mx <= 2e-2, (cos, mx)
+
+
+def test_conv_lora_single_net_and_embedder():
+    """CachedControlNetModel.forward of ONE conv-LoRA net through the mirrors (conv_in carries the net's LoRA too)."""
+    from edgestyle_b200 import config as C
+    from edgestyle_b200.model import (CachedControlNetModel, ControlLoRAModel, EdgeStyleMultiControlNetModel,
+                                      UNet2DConditionModel)
+    from oracle.sd15 import SD15Config
+    from oracle.step import build_models, synthetic_inputs
+
+    ocfg = SD15Config(block_out_channels=(64, 128, 256, 256), cross_attention_dim=96)
+    h = w = 16
+    m = build_models(ocfg, (h, w), rank=4, lora_conv2d_rank=2)
+    inp = synthetic_inputs(ocfg, 1, h, w)
+    cfg = C.UNetConfig.from_any(ocfg)
+    unet = UNet2DConditionModel(cfg, m.unet.state_dict())
+    agn = ControlLoRAModel(cfg, m.lora_agnostic.state_dict(), 4, lora_conv2d_rank=2, unet=unet)
+    clo = ControlLoRAModel(cfg, m.lora_clothes.state_dict(), 4, lora_conv2d_rank=2, unet=unet)
+    pose = CachedControlNetModel(cfg, m.openpose.state_dict())
+    multi = EdgeStyleMultiControlNetModel([agn, pose, clo, pose, clo, pose], m.controlnet.merge_state_dict(), (h, w))
+    m.unet.to(DEV)
+    m.controlnet.to(DEV)
+    x = torch.cat([inp.latents] * 2).to(DEV)
+    pe = inp.prompt_embeds.to(DEV)
+    conds = [c.to(DEV) for c in inp.conds]
+    t = torch.tensor(401, device=DEV)
+    for net, onet, cond in ((agn, m.lora_agnostic, conds[0]), (clo, m.lora_clothes, conds[2])):
+        wd, wm = onet(x, t, pe, cond, 1.25)
+        out = net(x, t, pe, cond, conditioning_scale=1.25)
+        for a, b in zip(list(out.down_block_res_samples) + [out.mid_block_res_sample], wd + [wm]):
+            assert (a - b).abs().max().item() <= 1e-2 * max(1.0, b.abs().max().item())
+    # fuse(): W + up @ down for Linear AND conv weights equals the oracle's fuse_lora
+    fused = agn.fused_state_dict()
+    m.lora_agnostic.fuse_lora()
+    for k, v in m.lora_agnostic.full_state_dict().items():
+        if k in fused and v.dim() == 4 and "controlnet" not in k:
+            assert torch.allclose(fused[k].float().cpu(), v.float().cpu(), atol=1e-5), k
+
+
+def test_gated_nets_are_skipped_and_match(monkeypatch):
+    """control_guidance gating (/root/reference/model/edgestyle_pipeline.py:418-427) sets a net's scale to 0: the
+    engine drops that net's image block from the batched passes (fewer launches' worth of rows) and the result is the
+    one the reference computes by multiplying the residuals with 0.  One graph per SET of active nets; changing the
+    VALUE of a scale re-uses the graph (the scales are a device vector)."""
+    from oracle.sd15 import SD15Config
+    from oracle.step import fused_step
+
+    cfg = SD15Config(block_out_channels=(64, 128, 256, 256), cross_attention_dim=96)
+    m, inp, eng = _mk(cfg, 16, 16, rank=4, use_graph=True)
+    x = torch.cat([inp.latents] * 2)
+    t = torch.tensor(751, device=DEV)
+    for scale in ([1.0, 0.0, 1.0, 1.0, 0.0, 1.0], [0.0, 1.0, 0.0, 0.0, 0.5, 0.0], [0.0] * 6, [1.0, 0.0, 0.0, 2.0, 0.0, 0.0],
+                  [0.7, 0.0, 1.3, 1.0, 0.0, 0.4]):
+        want = fused_step(m, x, t, inp.prompt_embeds, scale, inp.conds)
+        got = eng.step(x, t, scale)
+        cos, mx = _metrics(got, want)
+        assert cos >= 0.999 and mx <= 2e-2, (scale, cos, mx)
+    assert len(eng._graphs) == 4, list(eng._graphs)  # the first and last scale lists share one set of active nets
+    # without skipping (ES_SKIP_GATED=0: gated nets stay in the batched passes, the merge multiplies them by 0, as the
+    # reference does): same numbers from the full schedule
+    got_skip = eng.step(x, t, [1.0, 0.0, 1.0, 1.0, 0.0, 1.0]).clone()
+    monkeypatch.setenv("ES_SKIP_GATED", "0")
+    got_full = eng.step(x, t, [1.0, 0.0, 1.0, 1.0, 0.0, 1.0]).clone()
+    assert (got_skip - got_full).abs().max().item() <= 5e-3
+
+
+def test_weight_reload_takes_effect():
+    """ControlLoRAModel.load_state_dict / tie_weights must invalidate the multi-model's cached engines
+    (packed device weights + captured graphs): in the reference the modules are live."""
+    from edgestyle_b200 import config as C
+    from edgestyle_b200.model import (CachedControlNetModel, ControlLoRAModel, EdgeStyleMultiControlNetModel,
+                                      UNet2DConditionModel)
+    from oracle.sd15 import SD15Config
+    from oracle.step import build_models, synthetic_inputs
+
+    ocfg = SD15Config(block_out_channels=(64, 128, 256, 256), cross_attention_dim=96)
+    h = w = 16
+    m = build_models(ocfg, (h, w), rank=4)
+    m2 = build_models(ocfg, (h, w), rank=4, seed=5)
+    inp = synthetic_inputs(ocfg, 1, h, w)
+    cfg = C.UNetConfig.from_any(ocfg)
+    unet = UNet2DConditionModel(cfg, m.unet.state_dict())
+    agn = ControlLoRAModel(cfg, m.lora_agnostic.state_dict(), 4, unet=unet)
+    clo = ControlLoRAModel(cfg, m.lora_clothes.state_dict(), 4, unet=unet)
+    pose = CachedControlNetModel(cfg, m.openpose.state_dict())
+    multi = EdgeStyleMultiControlNetModel([agn, pose, clo, pose, clo, pose], m.controlnet.merge_state_dict(), (h, w))
+    x = torch.cat([inp.latents] * 2).to(DEV)
+    pe = inp.prompt_embeds.to(DEV)
+    conds = [c.to(DEV) for c in inp.conds]
+    t = torch.tensor(651, device=DEV)
+    d0, m0 = multi(x, t, pe, conds, [1.0] * 6)
+    d0 = [d.clone() for d in d0]
+    # (without the conv_vae_out alias of conv_in: loading it into the oracle would overwrite the TIED UNet conv_in)
+    new_sd = {k: v for k, v in m2.lora_agnostic.state_dict().items() if not k.startswith("controlnet_cond_embedding.")}
+    agn.load_state_dict(new_sd)
+    d1, m1 = multi(x, t, pe, conds, [1.0] * 6)
+    assert max((a - b).abs().max().item() for a, b in zip(d0, d1)) > 1e-3, "reloaded LoRA weights were ignored"
+    # and the reloaded model matches the oracle built from the new weights
+    m.lora_agnostic.load_state_dict(new_sd, strict=False)
+    m.unet.to(DEV)
+    m.controlnet.to(DEV)
+    wd, wm = m.controlnet(x, t, pe, conds, [1.0] * 6, return_dict=False)
+    for a, b in zip(d1 + [m1], wd + [wm]):
+        assert (a - b).abs().max().item() <= 2e-2 * max(1.0, b.abs().max().item())
 
 
 def test_step_parity_full_size_and_graph():
@@ -292,22 +420,46 @@ def test_pipeline_without_cfg_matches_oracle():
     assert _psnr(out.images, lat) >= 40.0
 
 
-def test_step_parity_768x1024_bf16(monkeypatch):
-    """BASELINE config 5: 96 x 128 latent (768 x 1024 image), bf16 storage, full SD1.5 widths -- long-sequence
-    self-attention (12288 tokens), 12 x 16 deepest level with masked conv tiles, merge blocks sized from the latent."""
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_step_parity_768x1024(dtype, monkeypatch):
+    """BASELINE config 5: 96 x 128 latent (768 x 1024 image), full SD1.5 widths -- long-sequence self-attention
+    (12288 tokens), 12 x 16 deepest level with masked conv tiles, merge blocks sized from the latent.  BOTH storage
+    dtypes meet the stated gate (cosine >= 0.999, max-abs <= 2e-2) at t = 701; measured on B200 (profiles/
+    r2a_config5_parity.json): fp16 max-abs 1.9e-3, 20-step PSNR 78.0 dB; bf16 max-abs 1.4e-2, PSNR 59.8 dB."""
     from oracle.sd15 import SD15Config
     from oracle.step import fused_step
 
-    monkeypatch.setenv("ES_AUTOTUNE", "0")  # heuristic tiles: tuning ~150 new shapes would dominate the test time
+    monkeypatch.setenv("ES_AUTOTUNE", "0")  # heuristic tiles: the tile choice does not change the arithmetic
     cfg = SD15Config()
-    m, inp, eng = _mk(cfg, 96, 128, rank=32, images=1, dtype=torch.bfloat16, use_graph=False)
+    m, inp, eng = _mk(cfg, 96, 128, rank=32, images=1, dtype=dtype, use_graph=False)
     x = torch.cat([inp.latents] * 2)
     t = torch.tensor(701, device=DEV)
     want = fused_step(m, x, t, inp.prompt_embeds, inp.conditioning_scale, inp.conds)
     got = eng.step(x, t, inp.conditioning_scale)
     cos, mx = _metrics(got, want)
-    print(f"768x1024 bf16: cos={cos:.6f} max_abs={mx:.4g}")
-    assert cos >= 0.999 and mx <= 8e-2, (cos, mx)
+    print(f"768x1024 {dtype}: cos={cos:.6f} max_abs={mx:.4g}")
+    assert cos >= 0.999 and mx <= 2e-2, (dtype, cos, mx)
+
+
+def test_ddim20_psnr_768x1024_bf16(monkeypatch):
+    """BASELINE config 5 end to end: 20 DDIM steps at 96 x 128 in bf16 against the fp32 oracle loop, PSNR >= 40 dB."""
+    from oracle.schedulers import DDIMScheduler
+    from oracle.sd15 import SD15Config
+    from oracle.step import denoise
+
+    monkeypatch.setenv("ES_AUTOTUNE", "0")
+    cfg = SD15Config()
+    m, inp, eng = _mk(cfg, 96, 128, rank=32, dtype=torch.bfloat16, use_graph=True)
+    want = denoise(m, inp, 20, 4.5)
+    sch = DDIMScheduler()
+    lat = inp.latents.clone().float()
+    for t in sch.set_timesteps(20):
+        eng.step(torch.cat([lat] * 2), torch.tensor(float(t), device=DEV), inp.conditioning_scale)
+        a_t, a_p = sch.coefficients(int(t))
+        eng.cfg_ddim_update(lat, float(a_t), float(a_p), 4.5)
+    psnr = _psnr(lat, want)
+    print(f"768x1024 bf16 20-step DDIM latent PSNR = {psnr:.2f} dB")
+    assert psnr >= 40.0, psnr
 
 
 def test_guess_mode_multi_and_pipeline():

@@ -69,7 +69,8 @@ def test_merge_block_repack_is_a_pure_permutation(models):
     p = pack_merge_block(sd, c, h, w, torch.float32, "cpu")
     g1 = sd["first_normalization.weight"]  # [3C, H, W], channel index c*3 + pair
     assert torch.equal(p["g1"][5, 2, 7], g1[7 * 3 + 2].reshape(-1)[5])
-    assert torch.equal(p["w1"][3, 1], sd["first_conv.weight"][3 * 3 + 1, :, 0, 0])
+    assert torch.equal(p["w1"][1, :, 3], sd["first_conv.weight"][3 * 3 + 1, :, 0, 0])  # [pair][net][channel]
+    assert torch.equal(p["w2"][2, 3], sd["second_conv.weight"][3, 2, 0, 0])
     assert torch.equal(p["g2"][6, 9], sd["second_normalization.weight"][9].reshape(-1)[6])
 
 
@@ -92,7 +93,7 @@ def test_model_mirrors_reference_surface(models):
     agn.tie_weights(unet)
     clo.tie_weights(unet)
     assert multi.unet() is unet
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(KeyError):  # a conv-LoRA net needs the LoRAConv2dLayer tensors of every convolution
         ControlLoRAModel(cfg, models.lora_agnostic.state_dict(), lora_linear_rank=4, lora_conv2d_rank=4)
     fresh = ControlLoRAModel.from_unet(unet, lora_linear_rank=4)
     assert all(v.abs().max() == 0 for k, v in fresh.state_dict().items() if k.endswith("up.weight"))

@@ -282,3 +282,62 @@ def test_controlnet_forward_matches_reference_golden():
                 assert a.shape == b.shape and torch.allclose(a, b, atol=1e-6, rtol=1e-5)
     assert float(g["outs"][0]["mid"].abs().max()) > 1e-3          # the fixture is not trivially zero
     assert float(g["outs"][3]["mid"].abs().max()) == 0.0          # conditioning_scale 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Cross-check of the oracle's diffusers internals against an independent port of the same diffusers modules: TVM's
+# relax frontend (get_timestep_embedding / Timesteps / TimestepEmbedding / Attention), executed from its source text by
+# tests/golden/make_golden_tvm_port.py (the only other implementation of these modules on the box).
+# ------------------------------------------------------------------------------------------------------------------
+TVM_GOLD = os.path.join(os.path.dirname(__file__), "golden", "tvm_port_golden.pt")
+
+
+def test_tvm_port_timestep_embedding():
+    from oracle.sd15 import TimestepEmbedding, timestep_sinusoid
+
+    g = torch.load(TVM_GOLD)
+    ts = g["timesteps"]
+    emb = timestep_sinusoid(ts["t"], ts["dim"])  # flip_sin_to_cos=True, freq_shift=0 (SD1.5 config)
+    assert emb.shape == ts["emb"].shape
+    assert torch.allclose(emb, ts["emb"], rtol=0, atol=2e-5)
+    te = g["time_embedding"]
+    mod = TimestepEmbedding(te["w1"].shape[1], te["w1"].shape[0])
+    mod.load_state_dict({"linear_1.weight": te["w1"], "linear_1.bias": te["b1"], "linear_2.weight": te["w2"],
+                         "linear_2.bias": te["b2"]})
+    with torch.no_grad():
+        y = mod(te["x"])
+    assert torch.allclose(y, te["y"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["self_attention", "cross_attention"])
+def test_tvm_port_attention(name):
+    """Bias-free to_q/k/v, to_out[0] with bias, scale = dim_head ** -0.5, heads split as [B, N, heads, head_dim]."""
+    from oracle.sd15 import Attention
+
+    a = torch.load(TVM_GOLD)[name]
+    assert a["qkv_bias"] is False and abs(a["scale"] - 20 ** -0.5) < 1e-12
+    ctx = a["encoder_hidden_states"]
+    att = Attention(a["to_q"].shape[1], 8, None if ctx is None else ctx.shape[-1])
+    sd = {"to_q.weight": a["to_q"], "to_k.weight": a["to_k"], "to_v.weight": a["to_v"],
+          "to_out.0.weight": a["to_out_w"], "to_out.0.bias": a["to_out_b"]}
+    assert set(att.state_dict()) == set(sd)  # in particular: no q/k/v bias parameters in the oracle either
+    att.load_state_dict(sd)
+    with torch.no_grad():
+        y = att(a["hidden_states"], ctx)
+    assert torch.allclose(y, a["y"], rtol=1e-4, atol=1e-5)
+
+
+def test_tvm_port_golden_is_reproducible():
+    """When TVM's sources are on the box, regenerating the vectors from their text gives the committed fixture."""
+    import importlib.util
+
+    path = os.path.join(os.path.dirname(__file__), "golden", "make_golden_tvm_port.py")
+    spec = importlib.util.spec_from_file_location("make_golden_tvm_port", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    if not os.path.exists(os.path.join(mod.NN, "op.py")):
+        pytest.skip("TVM sources not present on this box")
+    _, menv = mod._make_env()
+    g = torch.load(TVM_GOLD)
+    ts = menv["Timesteps"](320, flip_sin_to_cos=True, downscale_freq_shift=0)
+    assert torch.equal(ts(mod.Tensor(g["timesteps"]["t"]))._expr, g["timesteps"]["emb"])

@@ -64,9 +64,15 @@ def d_ln(x, out, *a, **k):
     return f"layernorm M={x.shape[0]} C={x.shape[1]}", 0.0, 4.0 * x.numel()
 
 
-def d_merge(res, scale, prm, stats, z, B, hw, Cc, dst, skip=None, **kw):
-    n = B * hw * Cc
-    return f"merge B={B} hw={hw} C={Cc}", 0.0, n * (3 * 12 + 4 + 4 + 2 + 2) + hw * Cc * 16
+def d_merge(levels, scale_dev, B):
+    # bytes: phase 1 reads 6 residual slabs, phase 2 reads them again + g1/be1 and writes z, phase 3 reads z, g2/be2, skip
+    # and writes dst (16-bit everything except an fp32 z)
+    tot = 0.0
+    for lv in levels:
+        n = B * lv["hw"] * lv["C"]
+        zb = lv["z"].element_size()
+        tot += n * (12 + 12 + zb + zb + 2 + 2) + lv["hw"] * lv["C"] * (12 + 4)
+    return f"merge B={B} levels={len(levels)}", 0.0, tot
 
 
 def d_other(*a, **k):
@@ -77,7 +83,7 @@ ops.gemm = wrap("gemm", ops.gemm, d_gemm)
 ops.attention = wrap("attention", ops.attention, d_att)
 ops.groupnorm = wrap("groupnorm", ops.groupnorm, d_gn)
 ops.layernorm = wrap("layernorm", ops.layernorm, d_ln)
-ops.merge = wrap("merge", ops.merge, d_merge)
+ops.merge_levels = wrap("merge", ops.merge_levels, d_merge)
 for nm in ("small_linear", "im2col3x3", "upsample2x", "nchw_to_nhwc", "timestep_embedding"):
     setattr(ops, nm, wrap(nm, getattr(ops, nm), d_other))
 

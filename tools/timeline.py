@@ -70,7 +70,7 @@ ops.gemm = wrap("gemm", ops.gemm, d_gemm)
 ops.attention = wrap("attention", ops.attention, d_att)
 ops.groupnorm = wrap("groupnorm", ops.groupnorm, lambda x0, out, *a, **k: (f"M={x0.shape[0]} C={out.shape[1]} {'apply' if k.get('stats_ready') else 'stats+apply'}", 0.0))
 ops.layernorm = wrap("layernorm", ops.layernorm, lambda x, out, *a, **k: (f"M={x.shape[0]} C={x.shape[1]}", 0.0))
-ops.merge = wrap("merge", ops.merge, lambda res, scale, prm, stats, z, B, hw, Cc, dst, **k: (f"B={B} hw={hw} C={Cc}", 0.0))
+ops.merge_levels = wrap("merge", ops.merge_levels, lambda levels, scale_dev, B: (f"B={B} levels={len(levels)} (3 launches)", 0.0))
 for nm in ("small_linear", "im2col3x3", "upsample2x", "nchw_to_nhwc", "timestep_embedding"):
     setattr(ops, nm, wrap(nm, getattr(ops, nm), lambda *a, **k: ("", 0.0)))
 
