@@ -11,6 +11,8 @@
 //                P written to smem as 16-bit in the canonical K-major SWIZZLE_128B layout, O rescaled in TMEM
 //                only when some row's max moved, final O / l stored with 16 B vectors.
 // Replaces F.scaled_dot_product_attention in diffusers' AttnProcessor2_0 (see include/edgestyle_b200.h).
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -73,6 +75,8 @@ struct AttParams {
   float scale_log2;
   void* out;
   long long ldo, bso;
+  uint32_t tmem_cols;  // attention2_kernel: TMEM columns to allocate
+  int o_stride;        // attention2_kernel: TMEM columns between the O accumulators of two query tiles
 };
 
 template <typename T, int NA>
@@ -406,6 +410,30 @@ static int launch_attention(const EsAttention* a, cudaStream_t stream) {
   return 0;
 }
 
+}  // namespace es
+#include "attention2.cuh"
+namespace es {
+
+// 0 = second-generation kernel (attention2.cuh), 1 = the first one (kept for A/B measurements: ES_ATT_V1=1)
+static int att_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ES_ATT_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+
+template <typename T>
+static int attention2_dispatch(const EsAttention* a, cudaStream_t s) {
+  // two query tiles per CTA when that still gives every SM work (K/V tiles are then loaded once for both)
+  const long long ctas2 = static_cast<long long>((a->nq + 255) / 256) * a->heads * a->batch;
+  const bool two = a->nq > 128 && ctas2 >= 148;
+  if (a->d <= 64) return two ? launch_attention2<T, 1, 2>(a, s) : launch_attention2<T, 1, 1>(a, s);
+  if (a->d <= 128) return two ? launch_attention2<T, 2, 2>(a, s) : launch_attention2<T, 2, 1>(a, s);
+  return two ? launch_attention2<T, 3, 2>(a, s) : launch_attention2<T, 3, 1>(a, s);
+}
+
 template <typename T>
 static int attention_dispatch(const EsAttention* a, cudaStream_t s) {
   ES_CHECK(a->d % 8 == 0 && a->d >= 8 && a->d <= 192, "es_attention: head dim %d unsupported (multiple of 8, <= 192)", a->d);
@@ -413,6 +441,7 @@ static int attention_dispatch(const EsAttention* a, cudaStream_t s) {
                a->bsk % 8 == 0 && a->bsv % 8 == 0 && a->bso % 8 == 0,
            "es_attention: pitches must be multiples of 8 elements");
   ES_CHECK(a->nq > 0 && a->nkv > 0 && a->batch > 0 && a->heads > 0, "es_attention: empty problem");
+  if (!att_v1()) return attention2_dispatch<T>(a, s);
   if (a->d <= 64) return launch_attention<T, 1>(a, s);
   if (a->d <= 128) return launch_attention<T, 2>(a, s);
   return launch_attention<T, 3>(a, s);

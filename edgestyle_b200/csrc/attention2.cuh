@@ -6,54 +6,25 @@
 //     query tiles per CTA (K/V tiles shared, loaded once) and still two CTAs per SM give FOUR softmax warps per
 //     sub-partition to hide that chain.
 //   * S is single-buffered per tile (64 fp32 columns) and released EARLY: as soon as a thread has pulled its row into
-//     registers (already shifted and packed to 16-bit pairs) the warpgroup arrives on s_free and the MMA warp issues
-//     Q K^T of the next key tile into the same columns, while the exponentials of the current one run.
-//   * fp16: the exponent argument x = s * scale*log2e - m is formed in fp32, packed to f16x2 and exponentiated with
-//     ex2.approx.ftz.f16x2 -- TWO exponentials per MUFU operation, and the result is already the packed P operand of
-//     the P V MMA (no separate conversion).  Row sums: HADD2 tree over 16 pairs, then fp32.  (bf16 keeps fp32 ex2:
-//     an 8-bit-mantissa argument would cost ~1 % per probability.)
+//     registers (and checked the row max against the current shift) the warpgroup arrives on s_free and the MMA warp
+//     issues Q K^T of the next key tile into the same columns, while the exponentials of the current one run.
+//     (Consuming the row in four 16-column chunks with the release after the last load measured slower: 491 vs 440 us.)
+//   * one exponential per score on the MUFU pipe in fp32 (ex2.approx.ftz.f32).  Measured on B200
+//     (tools/ubench_softmax.cu, profiles/r2d_ubench_softmax.txt): ex2.approx.f16x2 is NOT faster -- 16 packed
+//     instructions take the 256 cycles of 32 scalar ones (it is two MUFU operations plus pack/unpack moves) -- and
+//     tcgen05.ld 32x32b.x32 delivers 4 KB per warp in ~325 cycles (~50 B/clk/SM): pulling the fp32 S tile out of TMEM
+//     (650 cycles per 128 x 64 tile and SM sub-partition) costs MORE than its 64 exponentials per lane (512 cycles);
+//     the two overlap across warps, not inside one warp's dependency chain -- hence four warps per sub-partition.
 //   * P is single-buffered per tile: the write of P(j+1) waits for the commit of P(j) V (pv_done), which also is the
 //     "O is stable" condition the rare rescale path needs.
 //
-//   TMEM columns: [t * 64, +64) = S of tile t, [QT * 64 + t * dN, +dN) = O of tile t  (d = 40: 224 -> 256 columns,
-//   two CTAs per SM).
+//   TMEM columns: [t * 64, +64) = S of tile t, [QT * 64 + t * o_stride, +dN) = O of tile t, o_stride = dN rounded up to
+//   32 columns (d = 40: 2 x 64 + 2 x 64 = 256 columns, two CTAs per SM).
 #pragma once
 
 namespace es {
 
 constexpr int kAtt2KV = 64;  // keys per K/V tile
-
-__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
-  uint32_t y;
-  asm("ex2.approx.ftz.f16x2 %0, %1;" : "=r"(y) : "r"(x));
-  return y;
-}
-__device__ __forceinline__ uint32_t hadd2_u(uint32_t a, uint32_t b) {
-  uint32_t y;
-  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b));
-  return y;
-}
-__device__ __forceinline__ uint32_t hmax2_u(uint32_t a, uint32_t b) {
-  uint32_t y;
-  asm("max.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b));
-  return y;
-}
-// pack two fp32 into f16x2 (lo = a, hi = b)
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  uint32_t y;
-  asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(y) : "f"(a), "f"(b));
-  return y;
-}
-__device__ __forceinline__ float2 unpack_h2(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
-
-template <typename T>
-struct AttPacked {
-  static constexpr bool value = false;
-};
-template <>
-struct AttPacked<__half> {
-  static constexpr bool value = true;
-};
 
 template <typename T, int NA, int QT>
 __global__ void __launch_bounds__(64 + 128 * QT, (NA == 1) ? 2 : 1)
@@ -61,7 +32,6 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                   const __grid_constant__ CUtensorMap tmV, const AttParams p) {
   constexpr int kKV = kAtt2KV;
   constexpr int kKVAtom = kKV * 128;  // bytes of one 64-column atom of a K / V tile
-  constexpr bool kPacked = AttPacked<T>::value;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                              // QT tiles x NA atoms x [128 rows x 128 B]
   uint8_t* sK = sQ + QT * NA * kAtomBytes;         // 2 stages x NA atoms x [64 rows x 128 B]
@@ -89,7 +59,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const uint32_t tmem_cols = p.tmem_cols;
   const int o_col0 = QT * kKV;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -120,7 +90,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
   if (warp == 0) {
     // ================================ TMA producer ==============================================================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(&q_full, QT * NA * kAtomBytes);
 #pragma unroll
       for (int t = 0; t < QT; ++t)
@@ -144,19 +114,42 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================================================
-    if (lane == 0) {
+    // The issuing thread's own instruction stream is the critical resource (measured, tools/att_trace.py: with shared-
+    // memory descriptors rebuilt per MMA the thread needed ~3000 cycles per key tile for its 14 MMAs and was what every
+    // softmax warpgroup waited for).  Everything loop-invariant is therefore hoisted: a descriptor is its constant high
+    // word plus a low word that is one add away from a precomputed base.  The thread is chosen with elect.sync, not
+    // `lane == 0`: under a lane test the compiler must assume a divergent region and wraps EVERY uniform-datapath
+    // instruction (UTCHMMA, UTCBAR, R2UR) in an ELECT / BRA.U.ANY serialisation loop (~95 cycles per tcgen05.mma).
+    if (elect_one()) {
       const uint32_t idesc_qk = make_idesc_f16(128, kKV, Cvt<T>::kFmt, 0, 0);
       const uint32_t idesc_pv = make_idesc_f16(128, p.dN, Cvt<T>::kFmt, 0, 1);
       const int kq = (p.d + 15) / 16;  // MMAs along the head dim
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+      const uint32_t hi_kmaj = static_cast<uint32_t>(smem_desc_sw128(0, 16, 1024) >> 32);
+      const uint32_t hi_v = static_cast<uint32_t>(smem_desc_sw128(0, kKVAtom, 1024) >> 32);
+      auto lo_of = [](uint32_t saddr, uint32_t lbo) {
+        return static_cast<uint32_t>(smem_desc_sw128(saddr, lbo, 1024) & 0xffffffffull);
+      };
+      auto mk = [](uint32_t lo, uint32_t hi) { return (static_cast<uint64_t>(hi) << 32) | lo; };
+      uint32_t q_lo[QT][NA], k_lo0[NA], p_lo[QT];
+#pragma unroll
+      for (int t = 0; t < QT; ++t) {
+        p_lo[t] = lo_of(smem_u32(sP) + t * kAtomBytes, 16);
+#pragma unroll
+        for (int a = 0; a < NA; ++a) q_lo[t][a] = lo_of(smem_u32(sQ) + (t * NA + a) * kAtomBytes, 16);
+      }
+#pragma unroll
+      for (int a = 0; a < NA; ++a) k_lo0[a] = lo_of(smem_u32(sK) + a * kKVAtom, 16);
+      const uint32_t v_lo0 = lo_of(smem_u32(sV), kKVAtom);
+      constexpr uint32_t kStageLo = (NA * kKVAtom) >> 4;  // low-word distance between the two K (or V) stages
       // a second tile that lies entirely beyond nq still runs (its rows are never stored): uniform control flow
-      auto issue_qk = [&](int t, int j) {
-        const int s = j & 1;
-        for (int k = 0; k < kq; ++k) {
-          const uint64_t ad = smem_desc_sw128(aQ + (t * NA + (k >> 2)) * kAtomBytes, 16, 1024) + 2 * (k & 3);
-          const uint64_t bd = smem_desc_sw128(aK + (s * NA + (k >> 2)) * kKVAtom, 16, 1024) + 2 * (k & 3);
-          umma_f16(tmem_base + t * kKV, ad, bd, idesc_qk, k != 0);
-        }
+      auto issue_qk = [&](int t, int st) {
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            if (a * 4 + k4 < kq)
+              umma_f16(tmem_base + t * kKV, mk(q_lo[t][a] + 2 * k4, hi_kmaj), mk(k_lo0[a] + st * kStageLo + 2 * k4, hi_kmaj),
+                       idesc_qk, (a | k4) != 0);
         umma_commit(&s_full[t]);
       };
       mbar_wait(&q_full, 0);
@@ -169,28 +162,33 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         if (j + 1 < n_tiles) {  // S(j+1) = Q K(j+1)^T as soon as S(j) has been pulled into registers
-          mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          mbar_wait(&k_full[s ^ 1], ((j + 1) >> 1) & 1);
+          ATT_TRACE(3, 8 * (j & 7) + 0);
 #pragma unroll
           for (int t = 0; t < QT; ++t) {
             mbar_wait(&s_free[t], j & 1);
             tc_fence_after();
-            issue_qk(t, j + 1);
+            ATT_TRACE(3, 8 * (j & 7) + 1 + 2 * t);
+            issue_qk(t, s ^ 1);
+            ATT_TRACE(3, 8 * (j & 7) + 2 + 2 * t);
           }
-          umma_commit(&k_empty[(j + 1) & 1]);
+          umma_commit(&k_empty[s ^ 1]);
         }
+        ATT_TRACE(0, 4 * j + 0);  // S(j) of both tiles consumed, Q K(j+1)^T issued
         mbar_wait(&v_full[s], ph);
+        ATT_TRACE(0, 4 * j + 1);
+        const uint32_t v_lo = v_lo0 + s * kStageLo;
 #pragma unroll
         for (int t = 0; t < QT; ++t) {
           mbar_wait(&p_full[t], j & 1);  // P(j) of tile t in smem
           tc_fence_after();
+          ATT_TRACE(3, 8 * (j & 7) + 5 + t);
 #pragma unroll
-          for (int k = 0; k < kKV / 16; ++k) {
-            const uint64_t ad = smem_desc_sw128(aP + t * kAtomBytes, 16, 1024) + 2 * k;
-            // V: MN-major, 16 keys = 2048 B along K; N atoms (64 of d) kKVAtom apart
-            const uint64_t bd = smem_desc_sw128(aV + s * NA * kKVAtom + k * 2048, kKVAtom, 1024);
-            umma_f16(tmem_base + o_col0 + t * p.dN, ad, bd, idesc_pv, (j | k) != 0);
-          }
+          for (int k = 0; k < kKV / 16; ++k)  // V: MN-major, 16 keys = 2048 B along K; N atoms (64 of d) kKVAtom apart
+            umma_f16(tmem_base + o_col0 + t * p.o_stride, mk(p_lo[t] + 2 * k, hi_kmaj), mk(v_lo + k * (2048 >> 4), hi_v),
+                     idesc_pv, (j | k) != 0);
           umma_commit(&pv_done[t]);
+          ATT_TRACE(0, 4 * j + 2 + (t ? 1 : 0));  // P(j) V of tile t issued
         }
         umma_commit(&v_empty[s]);
       }
@@ -202,7 +200,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int r = qd * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
     const uint32_t t_s = t_row + t * kKV;
-    const uint32_t t_o = t_row + o_col0 + t * p.dN;
+    const uint32_t t_o = t_row + o_col0 + t * p.o_stride;
     float m_run = -INFINITY;  // shift of the exponent (scaled, log2 units): within 2^kSlack of the running row max
     float l_run = 0.f;        // running row sum of P (fp32)
     const float sl2 = p.scale_log2;
@@ -214,162 +212,76 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const bool full_tile = kv_valid == kKV;
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
+      if (lane == 0 && (j == 8 || j == 9)) ATT_TRACE(j - 7, (warp - 2) * 4 + 0);
       uint32_t va[32], vb[32];
-      if (j == 0) {  // first tile: a max pass to establish the shift
-        float mx = -INFINITY;
-        tmem_ld_x32(t_s, va);
-        tmem_ld_wait();
-        tmem_ld_x32(t_s + 32, vb);
+      tmem_ld_x32(t_s, va);
+      tmem_ld_x32(t_s + 32, vb);
+      tmem_ld_wait();
+      // row max of the tile (raw scores); a partial last tile masks its tail
+      float mx = -INFINITY;
+      if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (full_tile || i < kv_valid) mx = fmaxf(mx, __uint_as_float(va[i]));
-        tmem_ld_wait();
+        for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(va[i]), __uint_as_float(va[i + 1]));
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (full_tile || 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(vb[i]));
-        m_run = mx * sl2;
+        for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(vb[i]), __uint_as_float(vb[i + 1]));
       } else {
-        tmem_ld_x32(t_s, va);
-        tmem_ld_wait();
-        tmem_ld_x32(t_s + 32, vb);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i >= kv_valid) va[i] = 0xff800000u;       // -inf: exp -> 0, max ignores it
+          if (32 + i >= kv_valid) vb[i] = 0xff800000u;
+          mx = fmaxf(mx, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
+        }
       }
-      uint32_t pk[32];  // packed 16-bit pairs: exponent arguments (fp16 path) or probabilities
-      float sum = 0.f;
+      uint32_t pk[32];  // P as packed 16-bit pairs
       bool pv_waited = false;
-      if (kPacked) {
-        // ---- fp16: x = s * scale - m in fp32 -> f16x2; the tile max is taken on the packed values -------------
-        auto pack_x = [&](const uint32_t (&v)[32], int c, float neg_m, uint32_t* out) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float a0 = fmaf(__uint_as_float(v[i]), sl2, neg_m), a1 = fmaf(__uint_as_float(v[i + 1]), sl2, neg_m);
-            if (!full_tile) {
-              if (c + i >= kv_valid) a0 = -60000.f;
-              if (c + i + 1 >= kv_valid) a1 = -60000.f;
-            }
-            out[i >> 1] = pack_h2(a0, a1);
-          }
-        };
-        float neg_m = -m_run;
-        if (j > 0) tmem_ld_wait();  // va complete (vb in flight)
-        pack_x(va, 0, neg_m, pk);
-        tmem_ld_wait();
-        pack_x(vb, 32, neg_m, pk + 16);
-        if (j > 0) {
-          uint32_t mx2 = pk[0];
-#pragma unroll
-          for (int i = 1; i < 32; ++i) mx2 = hmax2_u(mx2, pk[i]);
-          const float2 mf = unpack_h2(mx2);
-          const float rel = fmaxf(mf.x, mf.y);  // tile max relative to the current shift
-          if (__any_sync(0xffffffffu, rel > kSlack)) {
-            // rare path: raise the shift of the rows that need it, rescale their O, redo the arguments from TMEM
-            mbar_wait(&pv_done[t], (j - 1) & 1);  // P(j-1) V retired: O is stable, P is free
-            pv_waited = true;
-            tc_fence_after();
-            const float m_new = rel > 0.f ? m_run + rel : m_run;
-            const float alpha = ex2_approx(m_run - m_new);
+      const float m_tile = mx * sl2;
+      if (j == 0) {
+        m_run = m_tile;  // first tile: its own max is the shift
+      } else if (__any_sync(0xffffffffu, m_tile > m_run + kSlack)) {
+        // rare path: raise the shift of the rows that need it and rescale their O (softmax is shift-invariant: the
+        // shift only has to stay within 2^kSlack of the running max, so that P <= 2^kSlack fits 16-bit floats)
+        mbar_wait(&pv_done[t], (j - 1) & 1);  // P(j-1) V retired: O is stable (and P is free)
+        pv_waited = true;
+        tc_fence_after();
+        const float m_new = fmaxf(m_run, m_tile);
+        const float alpha = ex2_approx(m_run - m_new);
 #pragma unroll 1
-            for (int c = 0; c < p.dN; c += 16) {
-              uint32_t o[16];
-              tmem_ld_x16(t_o + c, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_x16(t_o + c, o);
-            }
-            tmem_st_wait();
-            l_run *= alpha;
-            m_run = m_new;
-            neg_m = -m_run;
-            tmem_ld_x32(t_s, va);
-            tmem_ld_wait();
-            tmem_ld_x32(t_s + 32, vb);
-            pack_x(va, 0, neg_m, pk);
-            tmem_ld_wait();
-            pack_x(vb, 32, neg_m, pk + 16);
-          }
-        }
-        // S(j) is in registers: the MMA warp may overwrite it with S(j+1)
-        tc_fence_before();
-        mbar_arrive(&s_free[t]);
-        // ---- P = 2^x, two per MUFU op; row sum through an HADD2 tree per 16 pairs, then fp32 ----------------
-#pragma unroll
-        for (int i = 0; i < 32; ++i) pk[i] = ex2_f16x2(pk[i]);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t s8[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) s8[i] = hadd2_u(pk[h * 16 + 2 * i], pk[h * 16 + 2 * i + 1]);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) s8[i] = hadd2_u(s8[2 * i], s8[2 * i + 1]);
-          const float2 f0 = unpack_h2(hadd2_u(s8[0], s8[1])), f1 = unpack_h2(hadd2_u(s8[2], s8[3]));
-          sum += (f0.x + f0.y) + (f1.x + f1.y);
-        }
-      } else {
-        // ---- bf16 (and any other storage type): fp32 exponentials, one per score -------------------------------
-        auto tile_max = [&](const uint32_t (&v)[32], int c, float mx) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            if (full_tile) {
-              mx = fmax3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-            } else {
-              if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-              if (c + i + 1 < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i + 1]));
-            }
-          }
-          return mx;
-        };
-        float mx = -INFINITY;
-        if (j > 0) {
+        for (int c = 0; c < p.dN; c += 16) {
+          uint32_t o[16];
+          tmem_ld_x16(t_o + c, o);
           tmem_ld_wait();
-          mx = tile_max(va, 0, mx);
-        }
-        tmem_ld_wait();
-        if (j > 0) {
-          mx = tile_max(vb, 32, mx);
-          const float m_tile = mx * sl2;
-          if (__any_sync(0xffffffffu, m_tile > m_run + kSlack)) {
-            mbar_wait(&pv_done[t], (j - 1) & 1);
-            pv_waited = true;
-            tc_fence_after();
-            const float m_new = fmaxf(m_run, m_tile);
-            const float alpha = ex2_approx(m_run - m_new);
-#pragma unroll 1
-            for (int c = 0; c < p.dN; c += 16) {
-              uint32_t o[16];
-              tmem_ld_x16(t_o + c, o);
-              tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_x16(t_o + c, o);
-            }
-            tmem_st_wait();
-            l_run *= alpha;
-            m_run = m_new;
-          }
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_x16(t_o + c, o);
         }
-        tc_fence_before();
-        mbar_arrive(&s_free[t]);
-        const float neg_m = -m_run;
-        float s0 = 0.f, s1 = 0.f;
-        auto emit = [&](const uint32_t (&v)[32], int c, uint32_t* out) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, neg_m));
-            float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, neg_m));
-            if (!full_tile) {
-              if (c + i >= kv_valid) p0 = 0.f;
-              if (c + i + 1 >= kv_valid) p1 = 0.f;
-            }
-            s0 += p0;
-            s1 += p1;
-            out[i >> 1] = Cvt<T>::pack2(p0, p1);
-          }
-        };
-        emit(va, 0, pk);
-        emit(vb, 32, pk + 16);
-        sum = s0 + s1;
+        tmem_st_wait();
+        l_run *= alpha;
+        m_run = m_new;
       }
-      l_run += sum;
+      // S(j) is in registers: the MMA warp may overwrite it with S(j+1) while the exponentials run
+      tc_fence_before();
+      mbar_arrive(&s_free[t]);
+      if (lane == 0 && (j == 8 || j == 9)) ATT_TRACE(j - 7, (warp - 2) * 4 + 1);
+      const float neg_m = -m_run;
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(va[i]), sl2, neg_m));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(va[i + 1]), sl2, neg_m));
+        s0 += p0;
+        s1 += p1;
+        pk[i >> 1] = Cvt<T>::pack2(p0, p1);
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(vb[i]), sl2, neg_m));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(vb[i + 1]), sl2, neg_m));
+        s0 += p0;
+        s1 += p1;
+        pk[16 + (i >> 1)] = Cvt<T>::pack2(p0, p1);
+      }
+      l_run += s0 + s1;
+      if (lane == 0 && (j == 8 || j == 9)) ATT_TRACE(j - 7, (warp - 2) * 4 + 2);
       // ---- P(j) -> smem (canonical K-major SWIZZLE_128B: row r at r * 128 B, 16 B chunk index XOR (r & 7)) ----------
       if (j > 0 && !pv_waited) mbar_wait(&pv_done[t], (j - 1) & 1);  // the MMAs reading P(j-1) have retired
 #pragma unroll
@@ -379,6 +291,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       mbar_arrive(&p_full[t]);
+      if (lane == 0 && (j == 8 || j == 9)) ATT_TRACE(j - 7, (warp - 2) * 4 + 3);
     }
     // ---- epilogue: O / l ---------------------------------------------------------------------------------------
     mbar_wait(&pv_done[t], (n_tiles - 1) & 1);
@@ -443,7 +356,8 @@ static int launch_attention2(const EsAttention* a, cudaStream_t stream) {
   p.out = a->out;
   p.ldo = a->ldo;
   p.bso = a->bso;
-  const int need = QT * (kAtt2KV + p.dN);
+  p.o_stride = (p.dN + 31) / 32 * 32;
+  const int need = QT * (kAtt2KV + p.o_stride);
   p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
   ES_CHECK(need <= 512, "es_attention: TMEM budget exceeded (d %d, %d query tiles)", a->d, QT);
   // Q + P per tile, 2 stages of K and V, barriers

@@ -196,7 +196,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 2 && lane == 0)  // constant data: no need to wait for the previous kernel
     l2_prefetch_slice(p.prefetch, p.prefetch_bytes, (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x,
                       gridDim.x * gridDim.y * gridDim.z);
-  if (warp == 0 && lane == 0) {
+  // (elect.sync, not `lane == 0`: a lane test makes the region divergent for the compiler, which then wraps every
+  // uniform-datapath instruction -- UTMALDG, UTCHMMA, UTCBAR -- in an ELECT / BRA.U.ANY serialisation loop)
+  if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (p.kblocks2 > 0) {
@@ -233,12 +235,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // =============================== TMA producer ===========================================
-    if (lane == 0) {
+    if (elect_one()) {
       for (int kb = kb_prefill; kb < kb_end; ++kb) produce(kb);
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =============================================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N, Cvt<T>::kFmt, 0, 0);
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         const int it = kb - kb_begin;
@@ -494,6 +496,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) GEMM_TRACE(9);
         if (has_res) mbar_wait(&res_bar, 0);
         const float* vrow = ln_in ? vec_s : vec_s + q * BLOCK_N;
         const float* srow = vec_s + BLOCK_N;  // LayerNorm-folded GEMM: column sums
@@ -644,12 +647,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
+        if (threadIdx.x == 64) GEMM_TRACE(10);
         if (ln_out && row_ok) {
           atomicAdd(p.rowstat_out + 2 * row, rs_acc);
           atomicAdd(p.rowstat_out + 2 * row + 1, rq_acc);
         }
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) GEMM_TRACE(11);
         if (threadIdx.x == 64) {
           for (int pn = 0; pn < full_panels; ++pn) tma_store_4d(&tmO, smem + pn * 16384, oc0 + pn * 64, x0, y0, i0);
           if (rem) tma_store_4d(&tmOp, smem + full_panels * 16384, oc0 + full_panels * 64, x0, y0, i0);
@@ -711,6 +716,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
+        if (threadIdx.x == 64) GEMM_TRACE(12);
         if (threadIdx.x == 64) tma_store_wait_read0();
       } else if (p.act == ES_ACT_GEGLU) {
         constexpr int HALF = BLOCK_N / 2;
@@ -937,6 +943,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 
 }  // namespace es
 #include "gemm_pair.cuh"
+#include "gemm_persist.cuh"
 namespace es {
 
 static int pick_block_n(int n, int m_tiles, int act, int kb_total) {
@@ -1097,6 +1104,17 @@ static int gemm_dispatch(const EsGemm* g, cudaStream_t stream) {
   ES_CHECK(g->act == ES_ACT_NONE || g->act == ES_ACT_GEGLU || g->act == ES_ACT_SILU, "es_gemm: unknown activation %d", g->act);
 
   int bn_tile = g->block_n > 0 ? g->block_n : pick_block_n(g->n, m_tiles, g->act, g->taps * ceil_div(g->c1, kBlockK));
+  // block_n == 1000 + BN selects the persistent kernel (one CTA per SM, two accumulators in TMEM) with BN-wide tiles;
+  // problems it cannot run fall back to the one-tile kernel of the same width
+  int persist = 0;
+  if (bn_tile >= 1000) {
+    const int bn = bn_tile - 1000;
+    ES_CHECK(bn == 128 || bn == 160 || bn == 256, "es_gemm: unsupported persistent tile width %d", bn);
+    const bool ok = bn == 128 ? gemm_persist_eligible<128>(g, kp) : bn == 160 ? gemm_persist_eligible<160>(g, kp)
+                                                                             : gemm_persist_eligible<256>(g, kp);
+    if (ok) persist = bn;
+    bn_tile = bn;
+  }
   // block_n == 320 selects the CTA-pair kernel (256 x 320 tiles, cta_group::2); problems it cannot run fall back
   bool pair = false;
   if (bn_tile == kPairN) {
@@ -1123,8 +1141,8 @@ static int gemm_dispatch(const EsGemm* g, cudaStream_t stream) {
     if (encode_tmap_16b(&tmA, g->a, 4, dims, strides, box)) return -3;
   }
   kp.b_blocked = g->b_blocked;
-  if (pair) {
-    tmB = tmA;  // the pair launcher builds its own weight maps (80-row boxes)
+  if (pair || persist) {
+    tmB = tmA;  // the pair / persistent launchers build their own weight maps
   } else if (g->b_blocked) {
     // K-block-major weights: [taps * kblocks1][n_total_b][64] -- every B tile is one contiguous BLOCK_N x 128 B chunk
     uint64_t dims[3] = {64, static_cast<uint64_t>(g->n_total_b), static_cast<uint64_t>(g->taps) * kp.kblocks1};
@@ -1155,7 +1173,13 @@ static int gemm_dispatch(const EsGemm* g, cudaStream_t stream) {
     uint64_t dimsb[3] = {static_cast<uint64_t>(g->c2), 1, static_cast<uint64_t>(g->n_total_b2)};
     uint64_t stridesb[3] = {0, static_cast<uint64_t>(g->c2) * 2, static_cast<uint64_t>(g->c2) * 2};
     uint32_t boxb[3] = {static_cast<uint32_t>(kBlockK), 1u, static_cast<uint32_t>(bn_tile)};
-    if (!pair && encode_tmap_16b(&tmB2, g->b2, 3, dimsb, stridesb, boxb)) return -3;
+    if (!pair && !persist && encode_tmap_16b(&tmB2, g->b2, 3, dimsb, stridesb, boxb)) return -3;
+  }
+  if (persist) {
+    ES_CHECK(g->n_total_b >= g->n, "es_gemm: n_total_b < n");
+    if (persist == 128) return launch_gemm_persist<T, 128>(tmA, tmA2, kp, m_tiles, g, stream);
+    if (persist == 160) return launch_gemm_persist<T, 160>(tmA, tmA2, kp, m_tiles, g, stream);
+    return launch_gemm_persist<T, 256>(tmA, tmA2, kp, m_tiles, g, stream);
   }
   if (pair) {
     ES_CHECK(g->n_total_b >= g->n, "es_gemm: n_total_b < n");

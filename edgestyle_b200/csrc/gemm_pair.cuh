@@ -123,7 +123,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 2 && lane == 0) l2_prefetch_slice(p.prefetch, p.prefetch_bytes, blockIdx.x, gridDim.x);
   if (threadIdx.x == 0) PAIR_TRACE(0);
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (p.kblocks2 > 0) {
@@ -153,7 +153,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // =============================== TMA producer (both CTAs) ===============================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t full0 = mapa_u32(&full_bar[0], 0);  // the leader's full barriers
       int it = 0;
       for (int u = cluster_id; u < n_units; u += n_clusters) {
@@ -192,7 +192,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // =============================== MMA issuer (leader CTA only) ===========================
-    if (leader && lane == 0) {
+    if (leader && elect_one()) {
       constexpr uint32_t idesc = make_idesc_f16(2 * kBlockM, kPairNH, Cvt<T>::kFmt, 0, 0);
       const uint32_t peer_full = mapa_u32(&tmem_full_bar, 1);
       int it = 0, ui = 0;

@@ -152,6 +152,11 @@ class GemmTuner:
             if tiles <= 148 and kb_total >= 16:
                 sks += sorted({s for s in (2, 3, 4, 6, 8, 12, 16, 24, 296 // tiles) if 2 <= s <= kb_total // 4 and s * tiles <= 2 * 296})
             out += [(bn, sk) for sk in sks]
+        # persistent kernel (block_n = 1000 + width: one CTA per SM, two TMEM accumulators, the epilogue of tile i under
+        # the MMAs of tile i + 1): only for grids that fill the machine (it owns its SMs while it runs)
+        for bn in ((fixed_bn,) if fixed_bn in (128, 160, 256) else (() if fixed_bn else (128, 160, 256))):
+            if not (act and bn % 32) and m_tiles * ((n + bn - 1) // bn) >= 120 and bn <= max(128, 2 * n):
+                out.append((1000 + bn, 1))
         # CTA-pair kernel (256 x 320 tiles, one persistent cluster per TPC); GEGLU weights must be packed in 160-tiles
         if n % 320 == 0 and (not fixed_bn or fixed_bn in (160, 320)) and m_tiles >= 2:
             units = ((m_tiles + 1) // 2) * (n // 320)

@@ -358,7 +358,10 @@ def test_gemm_folded_layernorm(M, C, N, bn, geglu):
 @pytest.mark.parametrize("batch,heads,d,nq,nkv", [(2, 8, 40, 4096, 4096), (2, 8, 80, 1024, 1024), (3, 8, 160, 256, 256),
                                                   (2, 8, 160, 64, 64), (2, 8, 40, 4096, 77), (2, 8, 80, 1024, 77),
                                                   (1, 8, 160, 64, 77), (2, 4, 8, 200, 300), (1, 2, 16, 130, 129),
-                                                  (1, 8, 32, 64, 16)])
+                                                  (1, 8, 32, 64, 16),
+                                                  # two query tiles per CTA (>= 148 CTAs of 256 queries), all head-dim classes
+                                                  (8, 8, 80, 1024, 1024), (10, 8, 160, 512, 512), (4, 8, 40, 1300, 1000),
+                                                  (8, 8, 40, 4096, 77), (20, 8, 24, 300, 64)])
 def test_attention(batch, heads, d, nq, nkv, dtype):
     from edgestyle_b200 import ops
 

@@ -8,11 +8,10 @@ from edgestyle_b200 import ops  # noqa: E402
 lib = ext.load()
 lib.es_gemm_trace.restype = C.c_int
 lib.es_gemm_trace.argtypes = [C.c_void_p]
-names = ["start", "setup done", "first stage full (MMA)", "last MMA issued", "accum visible (epi)", "epilogue done", "dealloc/all units", "kb8 full", "kb24 full"]
-for (M, N, K, res, bn, conv) in [(32768, 320, 320, False, 320, (64, 64, 8)), (32768, 320, 320, False, 320, None), (32768, 320, 1280, False, 320, None),
-                                 (8192, 640, 640, False, 320, (32, 32, 8)), (32768, 320, 320, True, 160, None), (32768, 320, 320, False, 160, None), (32768, 320, 320, False, 32, None),
-                                 (8192, 320, 320, True, 32, None), (32768, 320, 1280, True, 160, None),
-                                 (2048, 1280, 1280, True, 128, None), (512, 1280, 1280, True, 32, None),
+names = ["start", "setup done", "first stage full (MMA)", "last MMA issued", "accum visible (epi)", "epilogue done", "dealloc/all units", "kb8 full", "kb24 full",
+         "epi: vec staged", "epi: TMEM drained", "epi: panels complete", "epi: stats done"]
+for (M, N, K, res, bn, conv) in [(32768, 320, 320, True, 160, None), (32768, 320, 320, False, 160, None), (32768, 960, 320, False, 256, None),
+                                 (32768, 320, 1280, True, 160, None), (2048, 1280, 1280, True, 128, None),
                                  (32768, 320, 320, False, 160, (64, 64, 8)), (8192, 640, 640, False, 160, (32, 32, 8))]:
     taps = 9 if conv else 1
     a = torch.randn(M, K, device="cuda", dtype=torch.float16)
@@ -34,6 +33,6 @@ for (M, N, K, res, bn, conv) in [(32768, 320, 320, False, 320, (64, 64, 8)), (32
     torch.cuda.synchronize()
     buf = (C.c_longlong * 16)()
     lib.es_gemm_trace(buf)
-    t = list(buf)[:9]
+    t = list(buf)[:13]
     print(f"M={M} N={N} K={K}x{taps} bn={bn} residual={res}: {e0.elapsed_time(e1) * 50:.1f} us/launch; CTA(1,0) cycles:",
           ", ".join(f"{n}=+{t[i] - t[0]}" for i, n in enumerate(names)))
