@@ -310,9 +310,109 @@ def test_conv3x3_pair(n_img, h, w, cin, cout, split_k):
     _close(out2, conv + xs.float() @ wsc.float().t(), 6e-3, 6e-3, "pair conv3x3 + shortcut")
 
 
+# ------------------------------------------------------------------------------------------ persistent kernel
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K,bn", [(256, 320, 320, 160), (32768, 320, 320, 160), (20000, 640, 640, 128), (4096, 960, 320, 256),
+                                      (300, 200, 72, 128), (24576, 320, 1280, 160), (2048, 1280, 1280, 256), (130, 96, 40, 160)])
+def test_gemm_persist_flat(M, N, K, bn, dtype):
+    """block_n = 1000 + width: one CTA per SM looping over tiles, two TMEM accumulators (the epilogue of tile i overlaps
+    the mainloop of tile i + 1), 8 epilogue warps; bias + residual, tails in M and N, many tiles per CTA."""
+    from edgestyle_b200 import ops
+
+    a = _rand(M, K, dtype=dtype, seed=401)
+    b = _rand(N, K, dtype=dtype, scale=K ** -0.5, seed=402)
+    bias = _rand(N, dtype=torch.float32, seed=403)
+    res = _rand(M, N, dtype=dtype, seed=404)
+    want = a.float() @ b.float().t() + bias + res.float()
+    tol = 2e-2 if dtype == torch.bfloat16 else 5e-3
+    for _ in range(2):
+        out = torch.zeros(M, N, device=DEV, dtype=dtype)
+        ops.gemm(a, b, N, out=out, bias=bias, residual=res, block_n=1000 + bn)
+        _close(out, want, tol, tol, f"persistent gemm {M}x{N}x{K} bn={bn}")
+
+
+def test_gemm_persist_geglu_rowvec_alpha_segments_lora():
+    from edgestyle_b200 import ops
+
+    M, C, bn = 4096, 320, 160
+    a = _rand(M, C, seed=405)
+    w = _rand(8 * C, C, scale=C ** -0.5, seed=406)
+    bias = _rand(8 * C, dtype=torch.float32, seed=407)
+    half = bn // 2
+    idx = []
+    for t in range(8 * C // bn):
+        idx += list(range(t * half, (t + 1) * half)) + list(range(4 * C + t * half, 4 * C + (t + 1) * half))
+    idx = torch.tensor(idx, device=DEV)
+    u = a.float() @ w.float().t() + bias
+    want = u[:, :4 * C] * F.gelu(u[:, 4 * C:])
+    out = torch.zeros(M, 4 * C, device=DEV, dtype=torch.float16)
+    ops.gemm(a, w[idx].contiguous(), 8 * C, out=out, bias=bias[idx].contiguous(), act=1, block_n=1160)
+    _close(out, want, 6e-3, 6e-3, "persistent geglu")
+    # per-image row vector + alpha
+    N, K = 640, 192
+    a = _rand(2048, K, seed=408)
+    b = _rand(N, K, scale=K ** -0.5, seed=409)
+    rowvec = _rand(8, N, dtype=torch.float32, seed=410)
+    for bn in (128, 160, 256):
+        out = torch.zeros(2048, N, device=DEV, dtype=torch.float16)
+        ops.gemm(a, b, N, out=out, rowvec=rowvec, rows_per_img=256, alpha=0.5, block_n=1000 + bn)
+        _close(out, 0.5 * (a.float() @ b.float().t() + rowvec.repeat_interleave(256, 0)), 4e-3, 4e-3, f"persistent rowvec {bn}")
+    # row segments select weight copies (fused ControlLoRA) + a K-extension on the last two (unfused LoRA)
+    rows = [0, 512, 1024, 2048]
+    x = _rand(2048, 320, seed=411)
+    w3 = _rand(3 * 320, 320, scale=320 ** -0.5, seed=412)
+    b3 = _rand(3 * 320, dtype=torch.float32, seed=413)
+    out = torch.zeros(2048, 320, device=DEV, dtype=torch.float16)
+    ops.gemm(x, w3, 320, out=out, bias=b3, segs=(rows, [0, 320, 640], None), block_n=1160)
+    for s in range(3):
+        sl = slice(rows[s], rows[s + 1])
+        _close(out[sl], x[sl].float() @ w3[s * 320:(s + 1) * 320].float().t() + b3[s * 320:(s + 1) * 320], 4e-3, 4e-3,
+               f"persistent segment {s}")
+    t = _rand(2048, 32, seed=414)
+    up = _rand(2 * 320, 32, scale=0.2, seed=415)
+    out = torch.zeros(2048, 320, device=DEV, dtype=torch.float16)
+    ops.gemm(x, w3[:320].contiguous(), 320, out=out, bias=b3[:320].contiguous(), a2=t, b2=up,
+             segs=(rows, [0, 0, 0], [-1, 0, 320]), block_n=1128)
+    base = x.float() @ w3[:320].float().t() + b3[:320]
+    _close(out[:512], base[:512], 4e-3, 4e-3, "persistent lora seg 0")
+    _close(out[512:1024], base[512:1024] + t[512:1024].float() @ up[:320].float().t(), 4e-3, 4e-3, "persistent lora seg 1")
+    _close(out[1024:], base[1024:] + t[1024:].float() @ up[320:].float().t(), 4e-3, 4e-3, "persistent lora seg 2")
+
+
+@pytest.mark.parametrize("n_img,h,w,cin,cout,bn", [(8, 64, 64, 320, 320, 160), (3, 32, 32, 64, 640, 128), (8, 16, 16, 640, 320, 160),
+                                                   (8, 8, 8, 128, 640, 256), (2, 24, 128, 64, 320, 160)])
+def test_conv3x3_persist(n_img, h, w, cin, cout, bn):
+    from edgestyle_b200 import ops
+
+    x = _rand(n_img * h * w, cin, seed=416)
+    wt = _rand(cout, 9 * cin, scale=(9 * cin) ** -0.5, seed=417)
+    bias = _rand(cout, dtype=torch.float32, seed=418)
+    rowvec = _rand(n_img, cout, dtype=torch.float32, seed=419)
+    res = _rand(n_img * h * w, cout, seed=420)
+    cx = 192
+    xs = _rand(n_img * h * w, cx, seed=421)
+    wsc = _rand(cout, cx, scale=cx ** -0.5, seed=422)
+    conv = F.conv2d(x.float().view(n_img, h, w, cin).permute(0, 3, 1, 2), wt.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2),
+                    bias, padding=1) + rowvec[:, :, None, None]
+    conv = conv.permute(0, 2, 3, 1).reshape(-1, cout)
+    ws = torch.zeros(n_img, 32, 2, device=DEV)
+    out = torch.zeros(n_img * h * w, cout, device=DEV, dtype=torch.float16)
+    ops.gemm(x, wt, cout, out=out, taps=9, whn=(w, h, n_img), bias=bias, rowvec=rowvec, residual=res, c1=cin,
+             block_n=1000 + bn, gn_ws=ws if (h * w) % 32 == 0 and cout // 32 >= 8 else None, gn_groups=32)
+    _close(out, conv + res.float(), 6e-3, 6e-3, "persistent conv3x3 + residual")
+    if (h * w) % 32 == 0 and cout // 32 >= 8:
+        o = out.float().view(n_img, h * w, 32, cout // 32)
+        _close(ws, torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1), 0.05, 2e-3, "persistent fused gn stats")
+    out2 = torch.zeros(n_img * h * w, cout, device=DEV, dtype=torch.float16)
+    ops.gemm(x, wt, cout, out=out2, taps=9, whn=(w, h, n_img), bias=bias, rowvec=rowvec, a2=xs, b2=wsc, c1=cin,
+             block_n=1000 + bn)
+    _close(out2, conv + xs.float() @ wsc.float().t(), 6e-3, 6e-3, "persistent conv3x3 + shortcut")
+
+
 # ------------------------------------------------------------------------------------------ folded LayerNorm
 @pytest.mark.parametrize("M,C,N,bn,geglu", [(512, 320, 960, 0, False), (1024, 640, 640, 320, False), (256, 1280, 1280, 64, False),
-                                            (768, 320, 2560, 160, True), (768, 320, 2560, 320, True), (2048, 640, 1920, 320, False)])
+                                            (768, 320, 2560, 160, True), (768, 320, 2560, 320, True), (2048, 640, 1920, 320, False),
+                                            (4096, 320, 960, 1256, False), (4096, 320, 2560, 1160, True), (2048, 640, 640, 1128, False)])
 def test_gemm_folded_layernorm(M, C, N, bn, geglu):
     """producer GEMM accumulates row (sum, sumsq) of its output; consumer GEMM == Linear(LayerNorm(x)) without a LayerNorm pass."""
     from edgestyle_b200 import ops
@@ -325,7 +425,8 @@ def test_gemm_folded_layernorm(M, C, N, bn, geglu):
     res = _rand(M, C, seed=304) * 3 + 1.5  # a mean well away from zero exercises the mean * colsum term
     x = torch.empty(M, C, device=DEV, dtype=torch.float16)
     stat = torch.zeros(M, 2, device=DEV)
-    ops.gemm(a, wp, C, out=x, bias=bp, residual=res, rowstat_out=stat, block_n=320 if C % 320 == 0 and bn == 320 else 0)
+    ops.gemm(a, wp, C, out=x, bias=bp, residual=res, rowstat_out=stat,
+             block_n=320 if C % 320 == 0 and bn == 320 else (1160 if bn > 1000 else 0))
     xf = x.float()
     _close(stat[:, 0], xf.sum(1), 0.05, 2e-3, "row sums")
     _close(stat[:, 1], (xf * xf).sum(1), 0.5, 2e-3, "row sums of squares")

@@ -49,8 +49,8 @@ for kind, M, N, K, whn, geglu, res in cases:
     flops = 2.0 * M * N * K * taps
     name = f"{kind} M={M} N={N} K={K * taps}{' geglu' if geglu else ''}{' +res' if res else ''}"
     best = None
-    for bn in ([160, 320] if geglu else [64, 128, 160, 256, 320]):
-        for sk in (1, 0):
+    for bn in ([160, 320, 1160] if geglu else [64, 128, 160, 256, 320, 1128, 1160, 1256]):
+        for sk in ((1,) if bn >= 1000 else (1, 0)):
             kw = dict(out=out, bias=bias, residual=r, block_n=bn, split_k=sk, act=1 if geglu else 0)
             if kind == "conv":
                 kw.update(taps=9, whn=whn, c1=K)
