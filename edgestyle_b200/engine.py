@@ -39,20 +39,21 @@ def pack_merge_block(sd: Dict[str, torch.Tensor], Cc: int, h: int, w: int, dtype
     The reference's interleaved channel index is c*6 + net; first_conv group g = c*3 + p consumes nets
     (2p, 2p+1) of channel c.  LayerNorm affine [3C, H, W] / [C, H, W] become channels-last [hw, 3, C] / [hw, C].
     """
-    f32 = dict(device=device, dtype=torch.float32)
     hw = h * w
-    dd = dict(device=device, dtype=dtype)
+    # (permute + cast on the host, one copy to the device: no packing kernels on the GPU)
+    f32 = lambda t: t.detach().to("cpu", torch.float32).contiguous().to(device)
+    dd = lambda t: t.detach().to("cpu", dtype).contiguous().to(device)
     return {
-        "w1": sd["first_conv.weight"].reshape(Cc, 3, 2).permute(1, 2, 0).to(**f32).contiguous(),   # [3 pairs][2 nets][C]
-        "b1": sd["first_conv.bias"].reshape(Cc, 3).permute(1, 0).to(**f32).contiguous(),            # [3][C]
-        "g1": sd["first_normalization.weight"].reshape(Cc, 3, hw).permute(2, 1, 0).to(**dd).contiguous(),
-        "be1": sd["first_normalization.bias"].reshape(Cc, 3, hw).permute(2, 1, 0).to(**dd).contiguous(),
-        "w2": sd["second_conv.weight"].reshape(Cc, 3).permute(1, 0).to(**f32).contiguous(),         # [3][C]
-        "b2": sd["second_conv.bias"].reshape(Cc).to(**f32).contiguous(),
-        "g2": sd["second_normalization.weight"].reshape(Cc, hw).permute(1, 0).to(**dd).contiguous(),
-        "be2": sd["second_normalization.bias"].reshape(Cc, hw).permute(1, 0).to(**dd).contiguous(),
-        "w3": sd["third_conv.weight"].reshape(Cc).to(**f32).contiguous(),
-        "b3": sd["third_conv.bias"].reshape(Cc).to(**f32).contiguous(),
+        "w1": f32(sd["first_conv.weight"].reshape(Cc, 3, 2).permute(1, 2, 0)),   # [3 pairs][2 nets][C]
+        "b1": f32(sd["first_conv.bias"].reshape(Cc, 3).permute(1, 0)),            # [3][C]
+        "g1": dd(sd["first_normalization.weight"].reshape(Cc, 3, hw).permute(2, 1, 0)),
+        "be1": dd(sd["first_normalization.bias"].reshape(Cc, 3, hw).permute(2, 1, 0)),
+        "w2": f32(sd["second_conv.weight"].reshape(Cc, 3).permute(1, 0)),         # [3][C]
+        "b2": f32(sd["second_conv.bias"].reshape(Cc)),
+        "g2": dd(sd["second_normalization.weight"].reshape(Cc, hw).permute(1, 0)),
+        "be2": dd(sd["second_normalization.bias"].reshape(Cc, hw).permute(1, 0)),
+        "w3": f32(sd["third_conv.weight"].reshape(Cc)),
+        "b3": f32(sd["third_conv.bias"].reshape(Cc)),
     }
 
 
@@ -147,14 +148,15 @@ class _Packer:
         self.fold_ln = fold_ln
 
     def f32(self, k):
-        return self.sd[k].to(device=self.device, dtype=torch.float32).contiguous()
+        # (cast on the host, then one copy: packing issues no conversion kernels on the device)
+        return self.sd[k].detach().to("cpu", torch.float32).contiguous().to(self.device)
 
     def conv3(self, k):
         w = self.sd[k]  # [cout, cin, 3, 3] -> [cout, 9*cin] with column = tap*cin + c
         return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(device=self.device, dtype=self.dtype).contiguous()
 
     def mat(self, t):
-        return t.to(device=self.device, dtype=self.dtype).contiguous()
+        return t.detach().to("cpu", self.dtype).contiguous().to(self.device)
 
     def _lora_parts(self, name, k_in):
         """[(down [rp,k], up [n,rp])] per LoRA group, rank zero-padded to a multiple of 8; None if absent."""
@@ -430,8 +432,12 @@ class DenoiseEngine:
         prio = [int(v) for v in os.environ.get("ES_PRIO", "0,0").split(",")]
         self._chain_streams = [torch.cuda.Stream(device=self.dev, priority=prio[0])]  # the pose pass
         self._merge_stream = torch.cuda.Stream(device=self.dev, priority=prio[1])
+        # zero-convs run level by level on their own streams as the two encoder passes produce their residual levels
+        # (ES_ZC_EARLY=0: after both passes, on the merge stream)
+        self.zc_early = os.environ.get("ES_ZC_EARLY", "1") != "0"
+        self._zc_streams = [torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)]
         self._side_ws = []
-        for st in self._chain_streams + [self._merge_stream]:  # concurrent launches must not share split-K scratch
+        for st in self._chain_streams + [self._merge_stream] + self._zc_streams:  # concurrent launches must not share split-K scratch
             ws = torch.zeros(128 << 20, dtype=torch.uint8, device=self.dev)
             self._side_ws.append(ws)
             ops.set_stream_workspace(st, ws)
@@ -494,7 +500,7 @@ class DenoiseEngine:
         return E
 
     def _mat(self, t):
-        return t.to(device=self.dev, dtype=self.dtype).contiguous()
+        return t.detach().to("cpu", self.dtype).contiguous().to(self.dev)
 
     def _pack_pose_embedder(self, sd):
         """ControlNetConditioningEmbedding of the openpose net (diffusers controlnet.py; reached from
@@ -522,7 +528,7 @@ class DenoiseEngine:
         return layers
 
     def _f32(self, t):
-        return t.to(device=self.dev, dtype=torch.float32).contiguous()
+        return t.detach().to("cpu", torch.float32).contiguous().to(self.dev)
 
     def _pack(self, unet_sd, lora_sds, pose_sd, merge_sd):
         cfg = self.cfg
@@ -1106,7 +1112,42 @@ class DenoiseEngine:
             grp = 0 if k is None else (1 if k == 0 else 2)
             self._convw_block(ci, col, xb[pos * B * hw:(pos + 1) * B * hw], grp, f"{geo.btag}.ci{pos}",
                               residual=None if k is None else cond(k))
-        outs_b = self._encoder(Eb, xb, nb_b * B, temb_base, self.ctx_base[: nb_b * B * nt], geo.seg, geo.btag)
+        n_lora = nb_b - 1
+        zres = {}  # ("b" | "p", level) -> zero-conv output of the ControlLoRA / openpose image blocks
+        zc_used = set()
+
+        def zero_conv(kind, li, t):
+            """controllora.py:240-254 for residual level li of one pass: the ControlLoRA image blocks (agn | clo | clo)
+            are one GEMM with the weight set selected per row segment, the openpose blocks one GEMM."""
+            c, H, W = self.res_shapes[li]
+            n = B * H * W
+            if kind == "b":
+                rb = self.buf(f"zres_b{li}.{n_lora}", n_lora * n, c)
+                n_agn = n if geo.seg[1] else 0
+                zw, zb = self.zero_base[li]
+                ops.gemm(t[n:], zw, c, out=rb, bias=zb, segs=([0, n_agn, n_lora * n], [0, c], None))
+                zres[("b", li)] = rb
+            else:
+                rp = self.buf(f"zres_p{li}.{nb_p}", nb_p * n, c)
+                ops.gemm(t, self.zero_pose[li][0], c, out=rp, bias=self.zero_pose[li][1])
+                zres[("p", li)] = rp
+
+        def early(kind, zst):
+            """Callback of _encoder: as soon as a residual level is enqueued, its zero-conv goes to the side stream."""
+            if not self.zc_early:
+                return None
+
+            def on_level(li, t):
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                zst.wait_event(ev)
+                zc_used.add(zst)
+                with torch.cuda.stream(zst):
+                    zero_conv(kind, li, t)
+            return on_level
+
+        outs_b = self._encoder(Eb, xb, nb_b * B, temb_base, self.ctx_base[: nb_b * B * nt], geo.seg, geo.btag,
+                               early("b", self._zc_streams[0]) if n_lora else None)
         outs_b = outs_b[0] + [outs_b[1]]
         outs_p = None
         if nb_p:
@@ -1118,7 +1159,8 @@ class DenoiseEngine:
                 for pos, k in enumerate(geo.pose_nets):
                     ops.gemm(col, Ep.conv_in.w, c0, out=xp[pos * B * hw:(pos + 1) * B * hw], bias=Ep.conv_in.bias,
                              residual=cond(k))
-                sk, md = self._encoder(Ep, xp, nb_p * B, temb_pose, self.ctx_pose[: nb_p * B * nt], None, geo.ptag)
+                sk, md = self._encoder(Ep, xp, nb_p * B, temb_pose, self.ctx_pose[: nb_p * B * nt], None, geo.ptag,
+                                       early("p", self._zc_streams[1]))
                 outs_p = sk + [md]
                 ev = torch.cuda.Event()
                 ev.record(st)
@@ -1159,7 +1201,11 @@ class DenoiseEngine:
             side.wait_event(ev)
         split = min(self.merge_split, nlev) if mode == "step" else 0
         level_groups = [list(reversed(range(split, nlev)))] + ([list(reversed(range(split)))] if split > 0 else [])
-        n_lora = len(geo.base_nets) - 1
+        if self.zc_early:  # the zero-conv streams join the merge stream
+            for zst in zc_used:
+                ev = torch.cuda.Event()
+                ev.record(zst)
+                side.wait_event(ev)
         z_dtype = torch.float32 if (self.dtype == torch.bfloat16 or not self.merge_z16) else self.dtype
         with torch.cuda.stream(side):
             for lg in level_groups:
@@ -1167,21 +1213,17 @@ class DenoiseEngine:
                 for li in lg:
                     c, H, W = self.res_shapes[li]
                     n = B * H * W
-                    zw, zb = self.zero_base[li]
                     res = [None] * 6
-                    # zero convs (controllora.py:240-254): the ControlLoRA image blocks (agn | clo | clo) are one GEMM
-                    # with the weight set selected per row segment, the openpose blocks one GEMM
                     if n_lora:
-                        rb = self.buf(f"zres_b{li}.{n_lora}", n_lora * n, c)
-                        n_agn = n if geo.seg[1] else 0
-                        ops.gemm(outs_b[li][n:], zw, c, out=rb, bias=zb, segs=([0, n_agn, n_lora * n], [0, c], None))
+                        if ("b", li) not in zres:
+                            zero_conv("b", li, outs_b[li])
                         for pos, k in enumerate(geo.base_nets[1:]):
-                            res[k] = rb[pos * n:(pos + 1) * n]
+                            res[k] = zres[("b", li)][pos * n:(pos + 1) * n]
                     if nb_p:
-                        rp = self.buf(f"zres_p{li}.{nb_p}", nb_p * n, c)
-                        ops.gemm(outs_p[li], self.zero_pose[li][0], c, out=rp, bias=self.zero_pose[li][1])
+                        if ("p", li) not in zres:
+                            zero_conv("p", li, outs_p[li])
                         for pos, k in enumerate(geo.pose_nets):
-                            res[k] = rp[pos * n:(pos + 1) * n]
+                            res[k] = zres[("p", li)][pos * n:(pos + 1) * n]
                     unet_rows = outs_b[li][:n]
                     res = [r if r is not None else unet_rows for r in res]  # never read: their scale is 0
                     z = self.buf(f"merge_z{li}", n, c, z_dtype)

@@ -43,3 +43,11 @@ for n, (c, us, by) in sorted(fam.items(), key=lambda kv: -kv[1][1]):
 print()
 print(f"launches/step {len(step)}; sum of per-launch durations {tot / 1e3:.2f} ms (cold-cache, serialised by ncu); "
       f"DRAM read {sum(l['rd'] for l in step) / 1e9:.2f} GB + write {sum(l['wr'] for l in step) / 1e9:.2f} GB per step")
+# machine-readable copy for bench.py (roofline.traffic is read from this file, never hard-coded there)
+if len(sys.argv) > 2:
+    import json
+
+    json.dump({"dram_bytes_per_step": sum(l["rd"] + l["wr"] for l in step), "launches_per_step": len(step),
+               "sum_of_durations_us": tot, "source": f"{sys.argv[1]} via tools/launch_summary.py (ncu, caches flushed per launch)",
+               "families": {n: {"launches": c, "us": round(us, 1), "dram_mb": round(by / 1e6, 1)} for n, (c, us, by) in fam.items()}},
+              open(sys.argv[2], "w"), indent=1)
