@@ -94,7 +94,7 @@ def test_sharded_units_equal_single_gpu():
     assert (one - full).abs().max().item() <= 1e-3
     # ... and all four units as ONE batch (different tile shapes): the same latents within the parity tolerance
     batch = denoise_units(pipe, UNITS, host, STEPS, 0, 1).cpu()
-    assert (batch - full).abs().max().item() <= 2e-2
+    assert (batch - full).abs().max().item() <= 1e-2 * max(1.0, batch.abs().max().item())
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
@@ -106,4 +106,4 @@ def test_split_cfg_pair_equals_unsplit():
     want = denoise_units(pipe, UNITS[2:3], host, STEPS, 0, 1).cpu()
     print(f"split pair vs unsplit: max |d| {(want - full).abs().max().item():.3e}")
     assert full.shape == want.shape == (1, 4, 16, 16)
-    assert (want - full).abs().max().item() <= 2e-2
+    assert (want - full).abs().max().item() <= 1e-2 * max(1.0, want.abs().max().item())
