@@ -531,58 +531,64 @@ class DenoiseEngine:
         return t.detach().to("cpu", torch.float32).contiguous().to(self.dev)
 
     def _pack(self, unet_sd, lora_sds, pose_sd, merge_sd):
+        """Any component may be None (a stand-alone ControlNet only needs its own encoder and zero-convs): `unet_sd`
+        (base encoder + decoder), `pose_sd` (plain ControlNet encoder), `merge_sd` (EdgeStyle merge blocks); `lora_sds`
+        holds one state dict per ControlLoRA weight group over the UNet's weights."""
         cfg = self.cfg
-        assert len(lora_sds) == 2, "expected [agnostic, clothes] ControlLoRA state dicts"
-        self.enc_base = self._pack_encoder(unet_sd, lora_sds)
-        self.enc_pose = self._pack_encoder(pose_sd, [])
-        self.pose_embed = self._pack_pose_embedder(pose_sd)
-        # UNet decoder
-        P = _Packer(unet_sd, [], self.dtype, self.dev, True, self.fold_ln)
-        nb = len(cfg.block_out_channels)
+        self.full = unet_sd is not None and pose_sd is not None and merge_sd is not None and len(lora_sds) == 2
+        self.enc_base = self._pack_encoder(unet_sd, lora_sds) if unet_sd is not None else None
+        self.enc_pose = self._pack_encoder(pose_sd, []) if pose_sd is not None else None
+        self.pose_embed = self._pack_pose_embedder(pose_sd) if pose_sd is not None else None
+        self.res_shapes = C.residual_shapes(cfg, self.h, self.w)
         self.up_res, self.up_tfm, self.up_conv = [], [], []
-        rev_attn = list(reversed(cfg.down_has_attn))
-        names = []
-        for i in range(nb):
-            self.up_res.append([P.res(f"up_blocks.{i}.resnets.{j}") for j in range(cfg.layers_per_block + 1)])
-            names += [f"up_blocks.{i}.resnets.{j}" for j in range(cfg.layers_per_block + 1)]
-            self.up_tfm.append([P.tfm(f"up_blocks.{i}.attentions.{j}") if rev_attn[i] else None
-                                for j in range(cfg.layers_per_block + 1)])
-            k = f"up_blocks.{i}.upsamplers.0.conv"
-            self.up_conv.append((P.conv3(k + ".weight"), P.f32(k + ".bias")) if k + ".weight" in unet_sd else None)
-        dec_res = [r for lvl in self.up_res for r in lvl]
-        off = self.enc_base.temb_cols
-        for r in dec_res:
-            r.temb_off = off
-            off += r.cout
-        self.dec_temb_cols = off - self.enc_base.temb_cols
-        # decoder time_emb_proj appended to the UNet group's (group 0) concatenated matrix
-        self.enc_base.temb_w[0] = torch.cat(
-            [self.enc_base.temb_w[0]] + [self._mat(unet_sd[n + ".time_emb_proj.weight"].float()) for n in names], 0)
-        self.enc_base.temb_b[0] = torch.cat(
-            [self.enc_base.temb_b[0]] + [self._f32(unet_sd[n + ".time_emb_proj.bias"].float()) for n in names], 0)
-        self.norm_out = (P.f32("conv_norm_out.weight"), P.f32("conv_norm_out.bias"))
-        co = cfg.out_channels
-        wco = torch.zeros(16, 9 * cfg.block_out_channels[0])
-        wco[:co] = unet_sd["conv_out.weight"].float().cpu().permute(0, 2, 3, 1).reshape(co, -1)
-        self.conv_out = (self._mat(wco), self._f32(torch.cat([unet_sd["conv_out.bias"].float().cpu(),
-                                                             torch.zeros(16 - co)])))
-        # zero convs: base pass stacks [agn; clo] along N, pose separate
+        self.dec_temb_cols = 0
+        if self.full:  # UNet decoder
+            P = _Packer(unet_sd, [], self.dtype, self.dev, True, self.fold_ln)
+            nb = len(cfg.block_out_channels)
+            rev_attn = list(reversed(cfg.down_has_attn))
+            names = []
+            for i in range(nb):
+                self.up_res.append([P.res(f"up_blocks.{i}.resnets.{j}") for j in range(cfg.layers_per_block + 1)])
+                names += [f"up_blocks.{i}.resnets.{j}" for j in range(cfg.layers_per_block + 1)]
+                self.up_tfm.append([P.tfm(f"up_blocks.{i}.attentions.{j}") if rev_attn[i] else None
+                                    for j in range(cfg.layers_per_block + 1)])
+                k = f"up_blocks.{i}.upsamplers.0.conv"
+                self.up_conv.append((P.conv3(k + ".weight"), P.f32(k + ".bias")) if k + ".weight" in unet_sd else None)
+            dec_res = [r for lvl in self.up_res for r in lvl]
+            off = self.enc_base.temb_cols
+            for r in dec_res:
+                r.temb_off = off
+                off += r.cout
+            self.dec_temb_cols = off - self.enc_base.temb_cols
+            # decoder time_emb_proj appended to the UNet group's (group 0) concatenated matrix
+            self.enc_base.temb_w[0] = torch.cat(
+                [self.enc_base.temb_w[0]] + [self._mat(unet_sd[n + ".time_emb_proj.weight"].float()) for n in names], 0)
+            self.enc_base.temb_b[0] = torch.cat(
+                [self.enc_base.temb_b[0]] + [self._f32(unet_sd[n + ".time_emb_proj.bias"].float()) for n in names], 0)
+            self.norm_out = (P.f32("conv_norm_out.weight"), P.f32("conv_norm_out.bias"))
+            co = cfg.out_channels
+            wco = torch.zeros(16, 9 * cfg.block_out_channels[0])
+            wco[:co] = unet_sd["conv_out.weight"].float().cpu().permute(0, 2, 3, 1).reshape(co, -1)
+            self.conv_out = (self._mat(wco), self._f32(torch.cat([unet_sd["conv_out.bias"].float().cpu(),
+                                                                 torch.zeros(16 - co)])))
+        # zero convs: base pass stacks the LoRA groups ([agn; clo]) along N, pose separate
         zc = C.zero_conv_channels(cfg) + [cfg.block_out_channels[-1]]
         keys = [f"controlnet_down_blocks.{i}" for i in range(len(zc) - 1)] + ["controlnet_mid_block"]
         self.zero_base, self.zero_pose = [], []
         for k, c in zip(keys, zc):
-            wb = torch.cat([l[k + ".weight"].float().cpu().reshape(c, c) for l in lora_sds], 0)
-            bb = torch.cat([l[k + ".bias"].float().cpu() for l in lora_sds], 0)
-            self.zero_base.append((self._mat(wb), self._f32(bb)))
-            self.zero_pose.append((self._mat(pose_sd[k + ".weight"].float().reshape(c, c)), self._f32(pose_sd[k + ".bias"])))
+            if lora_sds:
+                wb = torch.cat([l[k + ".weight"].float().cpu().reshape(c, c) for l in lora_sds], 0)
+                bb = torch.cat([l[k + ".bias"].float().cpu() for l in lora_sds], 0)
+                self.zero_base.append((self._mat(wb), self._f32(bb)))
+            if pose_sd is not None:
+                self.zero_pose.append((self._mat(pose_sd[k + ".weight"].float().reshape(c, c)), self._f32(pose_sd[k + ".bias"])))
         # merge blocks
-        shapes = C.residual_shapes(cfg, self.h, self.w)
-        pfx = [f"multi_controlnet_down_blocks.{i}." for i in range(len(shapes) - 1)] + ["multi_controlnet_mid_block."]
         self.merge = []
-        for p, (c, hh, ww) in zip(pfx, shapes):
-            sub = {k[len(p):]: v for k, v in merge_sd.items() if k.startswith(p)}
-            self.merge.append(pack_merge_block(sub, c, hh, ww, self.dtype, self.dev))
-        self.res_shapes = shapes
+        if merge_sd is not None:
+            pfx = [f"multi_controlnet_down_blocks.{i}." for i in range(len(self.res_shapes) - 1)] + ["multi_controlnet_mid_block."]
+            for p, (c, hh, ww) in zip(pfx, self.res_shapes):
+                sub = {k[len(p):]: v for k, v in merge_sd.items() if k.startswith(p)}
+                self.merge.append(pack_merge_block(sub, c, hh, ww, self.dtype, self.dev))
 
     # ------------------------------------------------------------------------------------ buffers
     def buf(self, name: str, rows: int, cols: int, dtype=None) -> torch.Tensor:
@@ -635,6 +641,8 @@ class DenoiseEngine:
         """prompt_embeds [B, n_text, ctx] (negative rows first, edgestyle_pipeline.py:330)."""
         B, nt = self.B, self.n_text
         assert prompt_embeds.shape == (B, nt, self.cfg.cross_attention_dim), prompt_embeds.shape
+        if not self.full:
+            raise RuntimeError("set_prompt belongs to the fused step; a stand-alone net takes the prompt per call")
         pe = prompt_embeds.to(device=self.dev, dtype=self.dtype).reshape(B * nt, -1)
         for g in range(4):
             self.ctx_base[g * B * nt:(g + 1) * B * nt].copy_(pe)
@@ -1066,6 +1074,9 @@ class DenoiseEngine:
         (controllora.py:257-265) instead of a uniform scale.  zero_uncond: the pipeline's guess mode under CFG
         (edgestyle_pipeline.py:453-459, 487-497) -- the merged residuals of the unconditional rows (first half of the
         batch) are dropped, i.e. those rows keep the plain UNet skips."""
+        if not self.full:
+            raise RuntimeError("this engine was built for a stand-alone ControlNet: the fused step needs the UNet, both "
+                               "ControlLoRA nets, the openpose net and the merge blocks")
         cfg, B = self.cfg, self.B
         h, w = self.h, self.w
         hw = h * w

@@ -108,6 +108,51 @@ class UNet2DConditionModel:
         return cls(_config_from_dict(cfg), sd)
 
 
+class _StandaloneOwner:
+    """Engine cache of a net that is used on its own (the stock ControlNet pipeline calls one net alone:
+    /root/reference/test_text2image_pretrained_openpose.py:263), outside an EdgeStyleMultiControlNetModel.  The engine
+    packs only what that net needs: its own encoder + zero-convs, or -- for a ControlLoRA net -- the UNet's encoder with
+    the net's LoRA and zero-convs."""
+
+    def __init__(self, net, dtype=torch.float16, n_text: int = 77):
+        self.net, self.dtype, self.n_text = net, dtype, n_text
+        self._engines: Dict[tuple, Any] = {}
+
+    def engine(self, rows: int, h: int, w: int):
+        from ..engine import DenoiseEngine
+
+        key = (rows, h, w)
+        eng = self._engines.get(key)
+        if eng is None:
+            net = self.net
+            if net.uses_lora:
+                if net._unet is None:
+                    raise RuntimeError("tie_weights(unet) first: the base weights of a ControlLoRA net are the UNet's")
+                eng = DenoiseEngine(net.config, net._unet.state_dict(), [net.state_dict()], None, None, rows=rows, h=h, w=w,
+                                    dtype=self.dtype, n_text=self.n_text, fuse_lora=True)
+            else:
+                eng = DenoiseEngine(net.config, None, [], net.state_dict(), None, rows=rows, h=h, w=w, dtype=self.dtype,
+                                    n_text=self.n_text)
+            self._engines[key] = eng
+        return eng
+
+    def embed_engine(self, rows: int, h: int, w: int):
+        for (_, hh, ww), eng in self._engines.items():
+            if (hh, ww) == (h, w):
+                return eng
+        return self.engine(rows, h, w)
+
+    def lora_group(self, net) -> Optional[int]:
+        return 0 if net.uses_lora else None
+
+    def _single_forward(self, net, sample, timestep, ehs, cond, scale, guess_mode):
+        B, _, h, w = sample.shape
+        return self.engine(B, h, w).single_controlnet(self.lora_group(net), sample, timestep, ehs, cond, scale, guess_mode)
+
+    def _invalidate_engines(self):
+        self._engines.clear()
+
+
 class CachedControlNetModel:
     """ControlNet whose conditioning embedder is skipped when `controlnet_cond` is already latent-sized
     (controllora.py:199-201) -- the only mode the hot path uses (conds are cached by the pipeline)."""
@@ -156,9 +201,8 @@ class CachedControlNetModel:
                 raise NotImplementedError(f"{name} is not used by SD1.5 and not implemented")
         if cross_attention_kwargs and cross_attention_kwargs.get("scale", 1.0) != 1.0:
             raise NotImplementedError('cross_attention_kwargs["scale"] != 1')
-        if self._owner is None:
-            raise RuntimeError("register this net in an EdgeStyleMultiControlNetModel before calling forward "
-                               "(the CUDA engine is built per multi-ControlNet model)")
+        if self._owner is None:  # used on its own: a private engine holding just this net's weights
+            self._owner = _StandaloneOwner(self)
         if tuple(controlnet_cond.shape[2:]) != tuple(sample.shape[2:]):  # raw image: run the embedder (:199-201)
             if self.controlnet_conditioning_channel_order == "bgr":
                 controlnet_cond = torch.flip(controlnet_cond, dims=[1])
@@ -182,7 +226,7 @@ class CachedControlNetModel:
         (edgestyle_pipeline.py:657-662), so its two CFG rows carry independently sampled embeddings.
         `noise` ([repeats * n, 4, H/8, W/8]) replaces the RNG draw (parity tests); the openpose path ignores both."""
         if self._owner is None:
-            raise RuntimeError("register this net in an EdgeStyleMultiControlNetModel before calling preprocess_image")
+            self._owner = _StandaloneOwner(self)
         n, _, H, W = image.shape
         if not self.uses_lora:
             emb = self._owner.embed_engine(n, H // 8, W // 8).embed_openpose(image)

@@ -118,6 +118,38 @@ def test_conv_lora_single_net_and_embedder():
             assert torch.allclose(fused[k].float().cpu(), v.float().cpu(), atol=1e-5), k
 
 
+def test_standalone_nets_without_a_multi_model():
+    """A ControlNet / ControlLoRA net called on its own, as the stock ControlNet pipeline does
+    (/root/reference/test_text2image_pretrained_openpose.py:263): a private engine with only that net's weights."""
+    from edgestyle_b200 import config as C
+    from edgestyle_b200.model import CachedControlNetModel, ControlLoRAModel, UNet2DConditionModel
+    from oracle.sd15 import SD15Config
+    from oracle.step import build_models, synthetic_inputs
+
+    ocfg = SD15Config(block_out_channels=(64, 128, 256, 256), cross_attention_dim=96)
+    h = w = 16
+    m = build_models(ocfg, (h, w), rank=4)
+    inp = synthetic_inputs(ocfg, 1, h, w)
+    cfg = C.UNetConfig.from_any(ocfg)
+    unet = UNet2DConditionModel(cfg, m.unet.state_dict())
+    clo = ControlLoRAModel(cfg, m.lora_clothes.state_dict(), 4, unet=unet)
+    pose = CachedControlNetModel(cfg, m.openpose.state_dict())
+    m.unet.to(DEV)
+    m.controlnet.to(DEV)
+    x = torch.cat([inp.latents] * 2).to(DEV)
+    pe = inp.prompt_embeds.to(DEV)
+    conds = [c.to(DEV) for c in inp.conds]
+    t = torch.tensor(301, device=DEV)
+    for net, onet, cond in ((clo, m.lora_clothes, conds[2]), (pose, m.openpose, conds[1])):
+        for guess in (False, True):
+            wd, wm = onet(x, t, pe, cond, 0.8, guess_mode=guess)
+            gd, gm = net(x, t, pe, cond, conditioning_scale=0.8, guess_mode=guess, return_dict=False)
+            for a, b in zip(list(gd) + [gm], wd + [wm]):
+                assert (a - b).abs().max().item() <= 1e-2 * max(1.0, b.abs().max().item())
+    with pytest.raises(RuntimeError):  # a stand-alone engine cannot run the fused six-net step
+        pose._owner.engine(2, h, w).step(x, t)
+
+
 def test_gated_nets_are_skipped_and_match(monkeypatch):
     """control_guidance gating (/root/reference/model/edgestyle_pipeline.py:418-427) sets a net's scale to 0: the
     engine drops that net's image block from the batched passes (fewer launches' worth of rows) and the result is the
