@@ -24,7 +24,7 @@ constexpr int kGnSlots = 34;  // GroupNorm groups one output tile can touch (fus
 
 // Optional event trace (clock64 stamps of CTA (1,0,0)) for pipeline analysis: build with -DES_GEMM_TRACE.
 #ifdef ES_GEMM_TRACE
-__device__ long long g_gemm_trace[16];
+__device__ long long g_gemm_trace[64];
 #define GEMM_TRACE(slot)                                                                        \
   do {                                                                                          \
     if (blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0) g_gemm_trace[slot] = clock64();  \
@@ -96,8 +96,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int kMaxStages = 12;
 
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment for SWIZZLE_128B
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for SWIZZLE_128B, computed on the SHARED-window address: going through uintptr_t would make
+  // every later access a generic LD / ST (64-bit address arithmetic, no LDS / STS) -- measured in the epilogues
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t accum_bar;

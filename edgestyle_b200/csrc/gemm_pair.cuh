@@ -100,7 +100,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmRp,
                  const GemmKParams p, const int n_units, const int m_pairs, const int n_tiles) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for SWIZZLE_128B, computed on the SHARED-window address: going through uintptr_t would make
+  // every later access a generic LD / ST (64-bit address arithmetic, no LDS / STS) -- measured in the epilogues
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* panels = smem + kPairStages * kPairStageBytes;
   float* vec_s = reinterpret_cast<float*>(panels + kPairPanelBytes);  // [4 lane quarters][320]
   float* gstat_s = vec_s + 4 * kPairN;

@@ -6,22 +6,34 @@
 // tile of a K = 320 layer, 3.7 k cycles in set-up (barrier init, TMEM allocation, descriptor fetch, cold instruction
 // cache), 2.7 k in the mainloop and 5.4 k in the epilogue (3.2 k of it the TMEM drain by ONE warp per sub-partition:
 // 320 cycles per 16-column chunk, a single warp's dependent-issue latency) -- 12 k cycles of which 2.7 k use the tensor
-// pipe; two CTAs per SM only overlap them pairwise.  Here the set-up is paid once per SM, eight epilogue warps (two per
-// TMEM lane quarter, each half of the tile's columns) drain twice as fast, and nothing but the MMA warp's own issue
+// pipe; two CTAs per SM only overlap them pairwise.  Here the set-up is paid once per SM, sixteen epilogue warps (four per
+// TMEM lane quarter, each a quarter of the tile's columns) drain four times as fast, and nothing but the MMA warp's own issue
 // stream separates the tiles of one SM.
 //
 //   warp 0     : TMA producer over a ring of kStages x (A 16 KB + B BLOCK_N x 128 B); the ring runs on across tiles, so
 //                the first K blocks of the next tile are in flight while the current one finishes.
 //   warp 1     : TMEM allocation (2 x BLOCK_N columns) and single-thread tcgen05.mma issue (128 x BLOCK_N x 16);
 //                accumulator stage = unit & 1, handed over with tmem_full / tmem_empty mbarriers.
-//   warps 2..9 : epilogue into DEDICATED panel smem (the ring belongs to the next tile), TMA store.
+//   warps 2..17: epilogue into DEDICATED panel smem (the ring belongs to the next tile), TMA store.
 //   work units : (m tile, n tile) with m fastest, unit += gridDim.x; grid = min(units, SMs).
 // No split-K here (the launcher only picks this kernel for grids that fill the machine).
 #pragma once
 
 namespace es {
 
-constexpr int kPsThreads = 320;
+#ifdef ES_GEMM_TRACE
+// CTA 0: slots 16 + 12 * unit + k for its first four units
+#define PS_TRACE(ui, k)                                                                   \
+  do {                                                                                    \
+    if (blockIdx.x == 0 && (ui) < 4) g_gemm_trace[16 + 12 * (ui) + (k)] = clock64();       \
+  } while (0)
+#else
+#define PS_TRACE(ui, k) do {} while (0)
+#endif
+
+constexpr int kPsEpiWarps = 8;  // two per TMEM lane quarter (12 or 16 warps need < 128 registers: the epilogue spills and loses, measured): the drain is bound by a warp's dependent-issue latency
+constexpr int kPsEpiThreads = 32 * kPsEpiWarps;
+constexpr int kPsThreads = 64 + kPsEpiThreads;
 
 template <int BLOCK_N>
 struct PsCfg {
@@ -89,7 +101,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   using Cfg = PsCfg<BLOCK_N>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for SWIZZLE_128B, computed on the SHARED-window address: going through uintptr_t would make
+  // every later access a generic LD / ST (64-bit address arithmetic, no LDS / STS) -- measured in the epilogues
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* panels = smem + kStages * Cfg::kStageBytes;
   float* vec_s = reinterpret_cast<float*>(panels + Cfg::kPanelBytes);  // [4 lane quarters][BLOCK_N]
   float* gstat_s = vec_s + 4 * BLOCK_N;
@@ -119,7 +133,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 8);
+      mbar_init(&tmem_empty_bar[a], kPsEpiWarps);
     }
     mbar_init(&res_bar, 1);
     fence_mbar_init();
@@ -175,12 +189,14 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int as = ui & 1;
         mbar_wait(&tmem_empty_bar[as], ((ui >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
         tc_fence_after();
+        PS_TRACE(ui, 0);
         const uint32_t tacc = tmem_base + as * BLOCK_N;
         for (int kb = 0; kb < d.kb_total; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (kb == 0) PS_TRACE(ui, 1);
           const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
           const uint64_t adesc = smem_desc_sw128(sa, 16, 1024);
           const uint64_t bdesc = smem_desc_sw128(sa + Cfg::kABytes, 16, 1024);
@@ -188,6 +204,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < kBlockK / 16; ++k) umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           umma_commit(&empty_bar[s]);
         }
+        PS_TRACE(ui, 2);
         if (d.kb_total > 0) umma_commit(&tmem_full_bar[as]);
         else mbar_arrive(&tmem_full_bar[as]);
       }
@@ -195,9 +212,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     // =============================== epilogue (8 warps) =====================================
     const int q = warp & 3;             // TMEM lane quarter of this warp
-    const int half = (warp - 2) >> 2;   // which part of the tile's column chunks
+    const int part = (warp - 2) >> 2;   // which part of the tile's column chunks (kPsEpiWarps / 4 parts)
     const int r = q * 32 + lane;
-    const int et = threadIdx.x - 64;    // 0..255
+    const int et = threadIdx.x - 64;    // 0..kPsEpiThreads-1
     const bool geglu = p.act == ES_ACT_GEGLU;
     const bool has_res = p.residual != nullptr;
     constexpr int GH = BLOCK_N / 2;     // GEGLU: value columns [0, GH), gate columns [GH, BLOCK_N)
@@ -205,8 +222,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int full_panels = n_tile_out / 64;
     const int rem = n_tile_out % 64;
     const int n_chunks = n_tile_out / 16;  // 16-column output chunks of a tile, split between the two warp halves
-    const int c_begin = half == 0 ? 0 : (n_chunks + 1) / 2;
-    const int c_end = half == 0 ? (n_chunks + 1) / 2 : n_chunks;
+    constexpr int kParts = kPsEpiWarps / 4;
+    const int c_begin = (n_chunks * part) / kParts;
+    const int c_end = (n_chunks * (part + 1)) / kParts;
     const bool gn_panel = p.gn_ws != nullptr;
     const bool ln_in = p.ln_rowstat != nullptr;
     int ui = 0, res_it = 0;
@@ -237,16 +255,17 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         ln_rstd = rsqrtf(fmaxf(sq.y * p.ln_inv_k - ln_mean * ln_mean, 0.f) + p.ln_eps);
       }
       // (A) the previous unit's TMA stores have finished reading the panels (thread 64 waited before this barrier)
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kPsEpiThreads) : "memory");
+      if (threadIdx.x == 64) PS_TRACE(ui, 3);
       if (has_res && threadIdx.x == 64) {  // the residual tile rides in the output panels, fetched while the MMAs run
         mbar_expect_tx(&res_bar, static_cast<uint32_t>(kBlockM * n_tile_out * 2));
         for (int pn = 0; pn < full_panels; ++pn) tma_load_4d(panels + pn * 16384, &tmR, &res_bar, oc0 + pn * 64, x0, y0, i0);
         if (rem) tma_load_4d(panels + full_panels * 16384, &tmRp, &res_bar, oc0 + full_panels * 64, x0, y0, i0);
       }
       if (gn_panel)
-        for (int i = et; i < 4 * kGnSlots * 2; i += 256) gstat_s[i] = 0.f;
+        for (int i = et; i < 4 * kGnSlots * 2; i += kPsEpiThreads) gstat_s[i] = 0.f;
       // per-column epilogue vector: vec[quarter][col] = bias[col] + rowvec[image of the quarter's rows][col]
-      for (int col = et; col < BLOCK_N; col += 256) {
+      for (int col = et; col < BLOCK_N; col += kPsEpiThreads) {
         const bool col_ok = n0 + col < p.N;
         const float bv = (col_ok && p.bias) ? p.bias[b_noff + n0 + col] : 0.f;
         if (ln_in) {  // slot 0: folded bias, slot 1: column sums of the gamma-scaled weights
@@ -273,10 +292,12 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           vec_s[w4 * BLOCK_N + col] = bv + rv;
         }
       }
+      if (threadIdx.x == 64) PS_TRACE(ui, 4);
       mbar_wait(&tmem_full_bar[as], (ui >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 64) PS_TRACE(ui, 5);
       // (B) vec_s visible to every epilogue warp
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kPsEpiThreads) : "memory");
       if (has_res) {
         mbar_wait(&res_bar, res_it & 1);
         ++res_it;
@@ -398,6 +419,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       // every tcgen05.ld of this warp has completed: hand the accumulator back to the MMA issuer
+      if (threadIdx.x == 64) PS_TRACE(ui, 6);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
@@ -407,7 +429,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       fence_proxy_async_smem();
       // (C) panels complete
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kPsEpiThreads) : "memory");
+      if (threadIdx.x == 64) PS_TRACE(ui, 7);
       if (threadIdx.x == 64) {
         for (int pn = 0; pn < full_panels; ++pn) tma_store_4d(&tmO, panels + pn * 16384, oc0 + pn * 64, x0, y0, i0);
         if (rem) tma_store_4d(&tmOp, panels + full_panels * 16384, oc0 + full_panels * 64, x0, y0, i0);
@@ -421,7 +444,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int g_t0 = (p.gn_col0 + n0) / p.gn_cpg;
         const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
         const int img_w = __shfl_sync(0xffffffffu, img, 0);
-        const int cc = half * 32 + lane;  // 8-column chunk of the tile handled by this lane
+        const int cc = part * 32 + lane;  // 8-column chunk of the tile handled by this lane
         const int col0 = n0 + cc * 8;
         if (cc < BLOCK_N / 8 && okmask != 0 && col0 < p.N && img_w - img_t0 < 4) {
           float sv[8], qv[8];
@@ -463,8 +486,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             atomicAdd(gs + 3, q1);
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int i = et; i < 4 * kGnSlots * 2; i += 256) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kPsEpiThreads) : "memory");
+        for (int i = et; i < 4 * kGnSlots * 2; i += kPsEpiThreads) {
           const float v = gstat_s[i];
           if (v != 0.f) {
             const int il4 = i / (kGnSlots * 2), gl = (i >> 1) % kGnSlots;
@@ -472,7 +495,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+      if (threadIdx.x == 64) PS_TRACE(ui, 8);
       if (threadIdx.x == 64) tma_store_wait_read0();
+      if (threadIdx.x == 64) PS_TRACE(ui, 9);
     }
   }
 
