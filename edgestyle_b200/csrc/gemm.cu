@@ -59,6 +59,8 @@ struct GemmKParams {
   int out_fp32;
   int stages;
   int splits;            // split-K factor (grid.z)
+  int k_rotate;          // 1: every tile walks its K blocks from a different starting block (see produce_b)
+  int coop;              // 1: cooperative split-K -- every split CTA reduces and finishes its own column slice of the tile
   float* ws_partial;     // [splits][tiles][128][BLOCK_N] fp32 partial accumulators
   int* ws_counter;       // [tiles] arrival counters (zero on entry, reset by the finishing CTA)
   float* gn_ws;          // optional: GroupNorm statistics of the OUTPUT accumulated here, [img][groups][2] (sum, sumsq)
@@ -156,8 +158,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // TMA load of k-block kb into its ring slot (producer thread only).  The weight tile (B) does not depend on the
   // previous kernel of the stream, the activation tile (A) does: under programmatic dependent launch the first ring
   // fill issues the B loads before griddepcontrol.wait and the A loads after it.
-  auto produce_b = [&](int kb) {
-    const int it = kb - kb_begin;
+  // Small-M launches: the few A tiles (and B tiles) of a K block are wanted by MANY CTAs at the same moment, and L2
+  // serves the requests for one line one after the other (measured: 940 - 4600 cycles per K block on the 8x8-level
+  // convolutions whatever the ring depth, tools/smallm_stages.py).  With k_rotate every (m, n) tile starts its K loop at
+  // a different block and wraps around, so concurrent CTAs read different lines; the MMA warp just accumulates the
+  // stages in ring order (the fp32 summation order differs per tile, deterministically).
+  const int kb_len = max(kb_end - kb_begin, 1);
+  const int k_rot = p.k_rotate ? static_cast<int>((blockIdx.x * 7u + blockIdx.y * 13u) % static_cast<unsigned>(kb_len)) : 0;
+  auto rotated = [&](int kb) {
+    int r = kb + k_rot;
+    return r >= kb_end ? r - kb_len : r;
+  };
+  auto produce_b = [&](int kb_seq) {
+    const int kb = rotated(kb_seq);
+    const int it = kb_seq - kb_begin;
     const int s = it % stages;
     const uint32_t ph = (it / stages) & 1;
     mbar_wait(&empty_bar[s], ph ^ 1);
@@ -172,8 +186,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tma_load_3d(sb, &tmB2, &full_bar[s], (kb - kb1) * kBlockK, 0, b2_noff + n0);
     }
   };
-  auto produce_a = [&](int kb) {
-    const int it = kb - kb_begin;
+  auto produce_a = [&](int kb_seq) {
+    const int kb = rotated(kb_seq);
+    const int it = kb_seq - kb_begin;
     const int s = it % stages;
     uint8_t* sa = smem + s * kStageBytes;
     if (kb < kb1) {
@@ -291,7 +306,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // per-column vector below needs one image per warp (32 rows).
     const bool rv_uniform = !p.rowvec || (p.flat ? (p.rows_per_img > 0 && p.rows_per_img % 32 == 0)
                                                  : ((p.bw * p.bh) % 32 == 0));
-    const bool use_tma_epi = p.tma_epi && rv_uniform && !(p.flat && x0 + kBlockM > x_end && x_end < p.W);
+    const bool use_tma_epi = p.tma_epi && !p.coop && rv_uniform && !(p.flat && x0 + kBlockM > x_end && x_end < p.W);
     // ---- while the mainloop runs: fetch this thread's slice of the per-column epilogue vector
     //      vec[warp][col] = bias[col] + rowvec[image of the warp's rows][col]  (registers now, smem after the MMAs)
     constexpr int kVPT = (BLOCK_N + 127) / 128;
@@ -367,13 +382,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) {
-        const int old = atomicAdd(p.ws_counter + tile_id, 1);
-        splitk_last = (old == p.splits - 1) ? 1 : 0;
-        if (splitk_last) p.ws_counter[tile_id] = 0;  // self-reset for the next launch
+      if (p.coop) {
+        // cooperative reduction: wait until ALL splits of this tile have published (the launcher guarantees that the
+        // whole grid is co-resident), then every CTA sums and finishes its own 16-column chunks.  Counter: 0 .. S-1
+        // while publishing, S .. 2S-1 while reading, reset by the last reader.
+        if (threadIdx.x == 64) {
+          atomicAdd(p.ws_counter + tile_id, 1);
+          const long long t0 = clock64();
+          while (*reinterpret_cast<volatile int*>(p.ws_counter + tile_id) < p.splits) {
+            __nanosleep(64);
+            if (clock64() - t0 > ES_MBAR_TIMEOUT_CYCLES) {
+              printf("edgestyle_b200: cooperative split-K timeout tile %d\n", tile_id);
+              __trap();
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      } else {
+        if (threadIdx.x == 64) {
+          const int old = atomicAdd(p.ws_counter + tile_id, 1);
+          splitk_last = (old == p.splits - 1) ? 1 : 0;
+          if (splitk_last) p.ws_counter[tile_id] = 0;  // self-reset for the next launch
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (!splitk_last) goto epilogue_done;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (!splitk_last) goto epilogue_done;
       __threadfence();
       from_ws = true;
     }
@@ -432,10 +465,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // only needs its apply pass).  Every lane of a warp holds the same 16 output channels of 32 different pixels
       // of ONE image, so each group segment is warp-reduced and lane 0 issues one atomic per (image, group).
       auto gn_accumulate = [&](const float (&o)[16], int c) {
-        const int col0 = n0 + c;
-        int nvalid = p.N - col0;
+        int nvalid = p.N - (n0 + c);
         if (nvalid > 16) nvalid = 16;
         if (nvalid <= 0) return;
+        const int col0 = p.gn_col0 + n0 + c;  // channel of the normalised tensor (this GEMM may write a column slice)
         const int g_first = col0 / p.gn_cpg, g_last = (col0 + nvalid - 1) / p.gn_cpg;
         for (int g = g_first; g <= g_last; ++g) {
           const int lo = max(col0, g * p.gn_cpg) - col0, hi = min(col0 + nvalid, (g + 1) * p.gn_cpg) - col0;
@@ -755,12 +788,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         };
         uint32_t vn[16];
-        fetch_res(0);
+        // cooperative split-K: this CTA finishes chunks [c_lo, c_hi) of the tile, the other splits the rest
+        constexpr int kChunks = BLOCK_N / 16;
+        const int c_lo = (p.coop && from_ws) ? 16 * ((static_cast<int>(blockIdx.z) * kChunks) / p.splits) : 0;
+        const int c_hi = (p.coop && from_ws) ? 16 * (((static_cast<int>(blockIdx.z) + 1) * kChunks) / p.splits) : BLOCK_N;
+        fetch_res(c_lo);
         if (!from_ws) {
           tmem_ld_x16(t_row, vn);
         }
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 16) {
+        for (int c = c_lo; c < c_hi; c += 16) {
           float o[16];
           const uint4 r0 = rn0, r1 = rn1;
           if (!from_ws) {
@@ -771,7 +808,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else {
             load_cols(c, o);
           }
-          if (c + 16 < BLOCK_N) fetch_res(c + 16);
+          if (c + 16 < c_hi) fetch_res(c + 16);
           if (row_ok && n0 + c < p.N) {
             const int valid = p.N - (n0 + c);
             const bool full = valid >= 16;
@@ -823,6 +860,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
+      }
+    }
+    if (p.coop && p.splits > 1) {  // last reader resets the tile counter for the next launch
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        const int old = atomicAdd(p.ws_counter + tile_id, 1);
+        if (old == 2 * p.splits - 1) p.ws_counter[tile_id] = 0;
       }
     }
   epilogue_done:;
@@ -889,7 +933,27 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const int tiles = m_tiles * n_tiles;
   // ---- split-K: small-M layers have too few output tiles to cover 148 SMs; stream K over several CTAs
   int splits = 1;
-  if (g->workspace && g->split_k != 1) {
+  // split_k < 0: COOPERATIVE split-K with -split_k splits -- all split CTAs of a tile wait for each other and each
+  // finishes its own column chunks (no serial last-arriver reduction: that one CTA reads splits x 128 x BLOCK_N x 4 B).
+  // The CTAs spin on each other, so the whole grid must be co-resident, and so must the grids of two such launches on
+  // concurrent streams: at most 148 CTAs of at most half an SM each; only long-K launches qualify (the zero-convs on the
+  // third stream never do).
+  bool coop = false;
+  if (g->workspace && g->split_k < -1) {
+    const int want = -g->split_k;
+    if (tiles * want <= 148 && kb_total >= 32 && want <= kb_total / 2 && g->act != ES_ACT_GEGLU && !g->ln_rowstat &&
+        !g->rowstat_out && BLOCK_N <= 256) {
+      coop = true;
+      splits = want;
+    } else {
+      splits = want <= kb_total / 2 ? want : 1;
+    }
+    const long long need = 65536 + static_cast<long long>(splits) * tiles * kBlockM * BLOCK_N * 4;
+    if (splits > 1 && (need > g->workspace_bytes || tiles > 16384)) {
+      splits = 1;
+      coop = false;
+    }
+  } else if (g->workspace && g->split_k != 1) {
     if (g->split_k > 1) {
       splits = g->split_k;
     } else if (tiles <= 148 && kb_total >= 16) {
@@ -903,6 +967,15 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (splits > 1 && (need > g->workspace_bytes || tiles > 16384)) splits = 1;
   }
   kp.splits = splits;
+  kp.coop = (coop && splits > 1) ? 1 : 0;
+  {
+    static int rot_env = -1;
+    if (rot_env < 0) {
+      const char* e = getenv("ES_K_ROTATE");
+      rot_env = e ? atoi(e) : 1;
+    }
+    kp.k_rotate = (rot_env && m_tiles <= 32 && kb_total >= 16) ? 1 : 0;
+  }
   kp.ws_counter = reinterpret_cast<int*>(g->workspace);
   kp.ws_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(g->workspace) + 65536);
   // ---- pipeline depth: default leaves room for two CTAs per SM so one CTA's epilogue overlaps the other's MMAs

@@ -152,6 +152,11 @@ class GemmTuner:
             if tiles <= 148 and kb_total >= 16:
                 sks += sorted({s for s in (2, 3, 4, 6, 8, 12, 16, 24, 296 // tiles) if 2 <= s <= kb_total // 4 and s * tiles <= 2 * 296})
             out += [(bn, sk) for sk in sks]
+            # cooperative split-K (negative factor): every split CTA finishes its own column chunks; one wave of at most
+            # 148 CTAs, long K only (include/edgestyle_b200.h: EsGemm.split_k)
+            if not act and bn in (128, 256) and kb_total >= 32 and 2 <= 148 // max(tiles, 1) <= kb_total // 2:
+                s_max = 148 // tiles
+                out += [(bn, -s) for s in sorted({s_max, max(2, s_max // 2)})]
         # persistent kernel (block_n = 1000 + width: one CTA per SM, two TMEM accumulators, the epilogue of tile i under
         # the MMAs of tile i + 1): only for grids that fill the machine (it owns its SMs while it runs)
         for bn in ((fixed_bn,) if fixed_bn in (128, 160, 256) else (() if fixed_bn else (128, 160, 256))):

@@ -86,7 +86,8 @@ typedef struct EsGemm {
   int out_fp32;
   int block_n; /* 0 = auto */
   int stages;  /* smem pipeline depth, 0 = auto */
-  int split_k; /* 0 = auto, 1 = off, >1 = forced; needs `workspace` */
+  int split_k; /* 0 = auto, 1 = off, >1 = forced; < -1 = cooperative split-K with -split_k splits (every split CTA
+                  reduces and finishes its own column chunks; at most 148 CTAs, long K); needs `workspace` */
   int b_blocked; /* 1: `b` is stored K-block-major, [taps * ceil(c1/64)][n_total_b][64] (K zero-padded to 64): every
                     weight tile is one contiguous chunk, which is what DRAM wants when weights are streamed once */
   float* gn_ws; /* optional: accumulate GroupNorm statistics of the OUTPUT here ([img][gn_groups][2] sum/sumsq, zeroed

@@ -121,7 +121,7 @@ def test_gemm_segments_and_lora_k_extension():
     _close(out, want, 5e-3, 5e-3, "lora k-extension")
 
 
-@pytest.mark.parametrize("split_k", [0, 2, 5, 16])
+@pytest.mark.parametrize("split_k", [0, 2, 5, 16, -3, -7])  # negative: cooperative split-K (EsGemm.split_k)
 @pytest.mark.parametrize("M,N,K,bn", [(128, 1280, 2304, 128), (512, 640, 11520, 64), (300, 200, 1000, 256)])
 def test_gemm_split_k(M, N, K, bn, split_k):
     """Split-K partial tiles + last-arriver epilogue must equal the single-pass result (and self-reset counters)."""
@@ -152,6 +152,45 @@ def test_conv3x3_split_k_small_m():
     want = F.conv2d(x.float().view(n_img, h, w, cin).permute(0, 3, 1, 2), wt.float().view(cout, 3, 3, cin)
                     .permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, cout)
     _close(out, want, 5e-3, 5e-3, "conv split-k")
+
+
+@pytest.mark.parametrize("bn,sk", [(256, -7), (128, -3), (256, -4)])
+def test_conv3x3_cooperative_split_k(bn, sk):
+    """8x8-level shapes (M = 512, N = 1280, long K): every split CTA reduces and finishes its own 16-column chunks --
+    per-image row vector, residual, fused 1x1 shortcut and GroupNorm statistics (also of a concat column slice) all on
+    the per-thread epilogue; repeated launches re-use the self-resetting tile counters."""
+    from edgestyle_b200 import ops
+
+    ops.set_gemm_workspace(256 << 20)
+    n_img, h, w, cin, cout = 8, 8, 8, 640, 1280
+    x = _rand(n_img * h * w, cin, seed=97)
+    wt = _rand(cout, 9 * cin, scale=(9 * cin) ** -0.5, seed=98)
+    bias = _rand(cout, dtype=torch.float32, seed=99)
+    rowvec = _rand(n_img, cout, dtype=torch.float32, seed=100)
+    res = _rand(n_img * h * w, cout, seed=101)
+    xs = _rand(n_img * h * w, 320, seed=102)
+    wsc = _rand(cout, 320, scale=320 ** -0.5, seed=103)
+    conv = F.conv2d(x.float().view(n_img, h, w, cin).permute(0, 3, 1, 2), wt.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2),
+                    bias, padding=1) + rowvec[:, :, None, None]
+    conv = conv.permute(0, 2, 3, 1).reshape(-1, cout)
+    for rep in range(3):
+        ws = torch.zeros(n_img, 32, 2, device=DEV)
+        out = torch.zeros(n_img * h * w, cout, device=DEV, dtype=torch.float16)
+        ops.gemm(x, wt, cout, out=out, taps=9, whn=(w, h, n_img), bias=bias, rowvec=rowvec, residual=res, c1=cin, block_n=bn,
+                 split_k=sk, gn_ws=ws, gn_groups=32)
+        _close(out, conv + res.float(), 6e-3, 6e-3, "coop conv3x3 + residual")
+        o = (conv + res.float()).view(n_img, h * w, 32, cout // 32)
+        _close(ws, torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1), 0.5, 5e-3, "coop fused gn stats")
+    # fused shortcut, output = the x half of a wider concat buffer whose GroupNorm covers 2 * cout channels
+    cat = torch.zeros(n_img * h * w, 2 * cout, device=DEV, dtype=torch.float16)
+    ws = torch.zeros(n_img, 32, 2, device=DEV)
+    ops.gemm(x, wt, cout, out=cat[:, cout:], taps=9, whn=(w, h, n_img), bias=bias, rowvec=rowvec, a2=xs, b2=wsc, c1=cin,
+             block_n=bn, split_k=sk, gn_ws=ws, gn_groups=32, gn_cpg=2 * cout // 32, gn_col0=cout)
+    want = conv + xs.float() @ wsc.float().t()
+    _close(cat[:, cout:], want, 6e-3, 6e-3, "coop conv3x3 + shortcut into a concat slice")
+    o = want.view(n_img, h * w, 16, 2 * cout // 32)
+    _close(ws[:, 16:], torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1), 0.5, 5e-3, "coop gn stats of a slice")
+    assert ws[:, :16].abs().max().item() == 0.0
 
 
 @pytest.mark.parametrize("n_img,h,w,cin,cout", [(2, 64, 64, 320, 320), (3, 32, 32, 64, 128), (2, 16, 16, 640, 320),
