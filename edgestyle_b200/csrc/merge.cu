@@ -12,6 +12,10 @@ namespace es {
 
 constexpr int kMergeThreads = 256;
 constexpr int kMergeIters = 8;  // pixel rows per thread and CTA
+#ifndef ES_MERGE_P2_BLOCKS
+#define ES_MERGE_P2_BLOCKS 2
+#endif
+#define ES_MERGE_P2_BLOCKS_ONLY(PH) ((PH) == 2 ? ES_MERGE_P2_BLOCKS : 2)
 
 template <typename T>
 __device__ __forceinline__ void mload8(const T* p, float (&f)[8]) {
@@ -86,7 +90,7 @@ __device__ __forceinline__ void block_reduce2_to_global(float a, float b, double
 // grid: sum over levels of B * chunks CTAs; block 256 = (C/8 channel vectors) x ny pixel rows.
 // PHASE 1: stats of u.  PHASE 2: z + stats of z.  PHASE 3: output (+ optional GroupNorm statistics of it).
 template <typename T, int PHASE>
-__global__ void __launch_bounds__(kMergeThreads, PHASE == 2 ? 1 : 2) merge_levels_kernel(const __grid_constant__ MergeTable tb) {
+__global__ void __launch_bounds__(kMergeThreads, ES_MERGE_P2_BLOCKS_ONLY(PHASE)) merge_levels_kernel(const __grid_constant__ MergeTable tb) {
   pdl_launch_dependents();
   int li = 0;
 #pragma unroll 1
@@ -145,9 +149,31 @@ __global__ void __launch_bounds__(kMergeThreads, PHASE == 2 ? 1 : 2) merge_level
       }
     }
     if (active) {
+      // All loads of a pixel (six residual vectors, and in phase 2 the three g1 / be1 pairs) are issued back to back
+      // and UNCONDITIONALLY before the first use: with the loads inside `if (scale != 0)` blocks the compiler kept
+      // them in six dependent groups and the pass ran at 12 % of the DRAM peak (ncu, profiles/r2p).  A gated net's slab
+      // points at valid memory (the engine passes the UNet rows); its values are dropped with a select, not by 0 * x.
+      const T* rp[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) rp[k] = reinterpret_cast<const T*>(L.res[k]);
 #pragma unroll 2
       for (int p = p0 + ty; p < p1; p += ny) {
         const long long off = img_off + static_cast<long long>(p) * C + ch;
+        uint4 rv[6], gv[3], bv[3];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) rv[k] = __ldg(reinterpret_cast<const uint4*>(rp[k] + off));
+        if (PHASE == 2) {
+#pragma unroll
+          for (int pr = 0; pr < 3; ++pr) {
+            const long long goff = (static_cast<long long>(p) * 3 + pr) * C + ch;
+            gv[pr] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(L.g1) + goff));
+            bv[pr] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(L.be1) + goff));
+          }
+        }
+        auto unpack8 = [](const uint4& u, float (&f)[8]) {
+          const float2 a = Cvt<T>::unpack2(u.x), b2 = Cvt<T>::unpack2(u.y), c2 = Cvt<T>::unpack2(u.z), d2 = Cvt<T>::unpack2(u.w);
+          f[0] = a.x; f[1] = a.y; f[2] = b2.x; f[3] = b2.y; f[4] = c2.x; f[5] = c2.y; f[6] = d2.x; f[7] = d2.y;
+        };
         float zacc[8];
         if (PHASE == 2) {
 #pragma unroll
@@ -156,21 +182,12 @@ __global__ void __launch_bounds__(kMergeThreads, PHASE == 2 ? 1 : 2) merge_level
 #pragma unroll
         for (int pr = 0; pr < 3; ++pr) {
           float ra[8], rb[8];
-          if (on_a[pr]) {
-            mload8<T>(reinterpret_cast<const T*>(L.res[2 * pr]) + off, ra);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ra[j] = 0.f;
-          }
-          if (on_b[pr]) {
-            mload8<T>(reinterpret_cast<const T*>(L.res[2 * pr + 1]) + off, rb);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) rb[j] = 0.f;
-          }
+          unpack8(rv[2 * pr], ra);
+          unpack8(rv[2 * pr + 1], rb);
           float u[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) u[j] = fmaf(wa[pr][j], ra[j], fmaf(wb[pr][j], rb[j], bb[pr][j]));
+          for (int j = 0; j < 8; ++j)
+            u[j] = fmaf(wa[pr][j], on_a[pr] ? ra[j] : 0.f, fmaf(wb[pr][j], on_b[pr] ? rb[j] : 0.f, bb[pr][j]));
           if (PHASE == 1) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -179,9 +196,8 @@ __global__ void __launch_bounds__(kMergeThreads, PHASE == 2 ? 1 : 2) merge_level
             }
           } else {
             float g[8], be[8];
-            const long long goff = (static_cast<long long>(p) * 3 + pr) * C + ch;
-            mload8<T>(reinterpret_cast<const T*>(L.g1) + goff, g);
-            mload8<T>(reinterpret_cast<const T*>(L.be1) + goff, be);
+            unpack8(gv[pr], g);
+            unpack8(bv[pr], be);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float y = fmaf((u[j] - mu1) * r1, g[j], be[j]);
@@ -199,12 +215,7 @@ __global__ void __launch_bounds__(kMergeThreads, PHASE == 2 ? 1 : 2) merge_level
             u4.x = Cvt<T>::pack2(zacc[0], zacc[1]); u4.y = Cvt<T>::pack2(zacc[2], zacc[3]);
             u4.z = Cvt<T>::pack2(zacc[4], zacc[5]); u4.w = Cvt<T>::pack2(zacc[6], zacc[7]);
             *reinterpret_cast<uint4*>(reinterpret_cast<T*>(L.z) + off) = u4;
-            // statistics of the values phase 3 will read
-            float2 f;
-            f = Cvt<T>::unpack2(u4.x); zacc[0] = f.x; zacc[1] = f.y;
-            f = Cvt<T>::unpack2(u4.y); zacc[2] = f.x; zacc[3] = f.y;
-            f = Cvt<T>::unpack2(u4.z); zacc[4] = f.x; zacc[5] = f.y;
-            f = Cvt<T>::unpack2(u4.w); zacc[6] = f.x; zacc[7] = f.y;
+            unpack8(u4, zacc);  // statistics of the values phase 3 will read
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -241,6 +252,13 @@ __global__ void __launch_bounds__(kMergeThreads, PHASE == 2 ? 1 : 2) merge_level
 #pragma unroll 2
       for (int p = p0 + ty; p < p1; p += ny) {
         const long long off = img_off + static_cast<long long>(p) * C + ch;
+        // (all loads of the pixel first, then the arithmetic)
+        const long long goff = static_cast<long long>(p) * C + ch;
+        const long long row = static_cast<long long>(b) * hw + p;
+        const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(L.g2) + goff));
+        const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(L.be2) + goff));
+        uint4 s4 = make_uint4(0, 0, 0, 0);
+        if (L.skip) s4 = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(L.skip) + row * L.lds + ch));
         float zz[8];
         if (L.z_f32) {
           const float4 z0 = __ldcs(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(L.z) + off));
@@ -250,15 +268,16 @@ __global__ void __launch_bounds__(kMergeThreads, PHASE == 2 ? 1 : 2) merge_level
           mload8_cs<T>(reinterpret_cast<const T*>(L.z) + off, zz);
         }
         float g[8], be[8], sk[8];
-        const long long goff = static_cast<long long>(p) * C + ch;
-        mload8<T>(reinterpret_cast<const T*>(L.g2) + goff, g);
-        mload8<T>(reinterpret_cast<const T*>(L.be2) + goff, be);
-        const long long row = static_cast<long long>(b) * hw + p;
-        if (L.skip) {
-          mload8<T>(reinterpret_cast<const T*>(L.skip) + row * L.lds + ch, sk);
-        } else {
+        {
+          const uint4 uu[3] = {g4, b4, s4};
+          float* dst3[3] = {g, be, sk};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) sk[j] = 0.f;
+          for (int q3 = 0; q3 < 3; ++q3) {
+            const float2 a = Cvt<T>::unpack2(uu[q3].x), b2 = Cvt<T>::unpack2(uu[q3].y), c2 = Cvt<T>::unpack2(uu[q3].z),
+                         d2 = Cvt<T>::unpack2(uu[q3].w);
+            dst3[q3][0] = a.x; dst3[q3][1] = a.y; dst3[q3][2] = b2.x; dst3[q3][3] = b2.y;
+            dst3[q3][4] = c2.x; dst3[q3][5] = c2.y; dst3[q3][6] = d2.x; dst3[q3][7] = d2.y;
+          }
         }
         float o[8];
 #pragma unroll
