@@ -10,11 +10,12 @@
 //     issues Q K^T of the next key tile into the same columns, while the exponentials of the current one run.
 //     (Consuming the row in four 16-column chunks with the release after the last load measured slower: 491 vs 440 us.)
 //   * one exponential per score on the MUFU pipe in fp32 (ex2.approx.ftz.f32).  Measured on B200
-//     (tools/ubench_softmax.cu, profiles/r2d_ubench_softmax.txt): ex2.approx.f16x2 is NOT faster -- 16 packed
-//     instructions take the 256 cycles of 32 scalar ones (it is two MUFU operations plus pack/unpack moves) -- and
-//     tcgen05.ld 32x32b.x32 delivers 4 KB per warp in ~325 cycles (~50 B/clk/SM): pulling the fp32 S tile out of TMEM
-//     (650 cycles per 128 x 64 tile and SM sub-partition) costs MORE than its 64 exponentials per lane (512 cycles);
-//     the two overlap across warps, not inside one warp's dependency chain -- hence four warps per sub-partition.
+//     (tools/ubench_softmax.cu, profiles/r2r_ubench_softmax.txt): ex2.approx.f16x2 is NOT faster -- 16 packed
+//     instructions take the 256 cycles of 32 scalar ones (it is two MUFU operations plus pack/unpack moves).  Pulling
+//     the fp32 S tile out of TMEM is cheap (tcgen05.ld 32x32b.x32: 20-38 cycles per warp, overlapping the exponentials);
+//     the floor is the MUFU pipe, 512 cycles per 128 x 64 tile and SM sub-partition, and what a warp loses on top is its
+//     own dependency chain (load -> max -> exp -> pack -> st.shared -> fence -> mbarrier) -- hence four warps per
+//     sub-partition.
 //   * P is single-buffered per tile: the write of P(j+1) waits for the commit of P(j) V (pv_done), which also is the
 //     "O is stable" condition the rare rescale path needs.
 //

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(512, 1) k(int iters, float* sink, long long* c
     }
     if (MODE == 2 || MODE == 3 || MODE == 4 || (MODE == 5 && (warp & 4))) {
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      acc += __uint_as_float(v[it & 31] & 0x3fffffffu);
+      acc += __uint_as_float(v[0] & 0x3fffffffu) + __uint_as_float(v[31] & 0x3fffffffu);
     }
   }
   const long long t1 = clock64();
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(512, 1) kld(int iters, float* sink, long long*
           : "r"(taddr) : "memory");
     }
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    acc += __uint_as_float(v[it & 7] & 0x3fffffffu);
+    acc += __uint_as_float(v[0] & 0x3fffffffu) + __uint_as_float(v[7] & 0x3fffffffu);
   }
   const long long t1 = clock64();
   if (acc == 12345.678f) sink[0] = acc;
