@@ -418,6 +418,14 @@ class DenoiseEngine:
         # them), levels < merge_split the second (the heavy 64x64-level merges, under the decoder's deep levels);
         # 0 = a single group
         self.merge_split = int(os.environ.get("ES_MERGE_SPLIT", "3"))
+        # ES_MERGE_BY_LEVEL=1 (default): one merge group per decoder level instead (4 groups = 12 launches at SD1.5's
+        # 13 residual levels): the decoder starts after the 8x8-level group alone -- 165 us after the encoders instead of
+        # 350 us (tools/timeline.py), 9.81 vs 9.92 ms/step
+        self.merge_by_level = os.environ.get("ES_MERGE_BY_LEVEL", "1") != "0"
+        # ES_ZC_CHAIN=1: after its encoder pass each chain runs its own zero-convs (deepest group first) on a stream of
+        # its own instead of queueing them on the merge stream in front of each group's merge.  Default off -- measured
+        # 9.91 vs 9.81 ms/step: the extra concurrency only competes with the decoder's first kernels
+        self.zc_chain = os.environ.get("ES_ZC_CHAIN", "0") != "0"
         self.merge_z16 = os.environ.get("ES_MERGE_Z16", "1") != "0"  # fp16 engines keep the merge's z tensor in fp16
         self._stats_of = {}
         self._cat_slot = {}
@@ -1208,11 +1216,43 @@ class DenoiseEngine:
         side = self._merge_stream
         ev_main = torch.cuda.Event()
         ev_main.record(main)
+        if mode != "step":
+            level_groups = [list(reversed(range(nlev)))]
+        elif self.merge_by_level:
+            # one group per decoder level: (mid + the deepest level's skips), then the skips of each shallower level
+            order_all = list(reversed(range(nlev)))
+            rest = order_all[1 + n_up:]
+            level_groups = [order_all[:1 + n_up]] + [rest[i:i + n_up] for i in range(0, len(rest), n_up)]
+        else:
+            split = min(self.merge_split, nlev)
+            level_groups = [list(reversed(range(split, nlev)))] + ([list(reversed(range(split)))] if split > 0 else [])
+        # zero-convs: each encoder pass does its own, deepest group first, on a stream that is idle once the encoders are
+        # through (the ControlLoRA blocks on a side stream behind the main pass, the openpose blocks on the pose
+        # stream behind its pass); the merge stream waits group by group
+        zc_ready = [[] for _ in level_groups]
+        if self.zc_chain and not self.zc_early:
+            if n_lora:
+                zst = self._zc_streams[0]
+                zst.wait_event(ev_main)
+                with torch.cuda.stream(zst):
+                    for g, lg in enumerate(level_groups):
+                        for li in lg:
+                            zero_conv("b", li, outs_b[li])
+                        ev = torch.cuda.Event()
+                        ev.record(zst)
+                        zc_ready[g].append(ev)
+            if nb_p:
+                st = self._chain_streams[0]
+                with torch.cuda.stream(st):
+                    for g, lg in enumerate(level_groups):
+                        for li in lg:
+                            zero_conv("p", li, outs_p[li])
+                        ev = torch.cuda.Event()
+                        ev.record(st)
+                        zc_ready[g].append(ev)
         side.wait_event(ev_main)
         for ev in done_events:
             side.wait_event(ev)
-        split = min(self.merge_split, nlev) if mode == "step" else 0
-        level_groups = [list(reversed(range(split, nlev)))] + ([list(reversed(range(split)))] if split > 0 else [])
         if self.zc_early:  # the zero-conv streams join the merge stream
             for zst in zc_used:
                 ev = torch.cuda.Event()
@@ -1220,7 +1260,9 @@ class DenoiseEngine:
                 side.wait_event(ev)
         z_dtype = torch.float32 if (self.dtype == torch.bfloat16 or not self.merge_z16) else self.dtype
         with torch.cuda.stream(side):
-            for lg in level_groups:
+            for g, lg in enumerate(level_groups):
+                for ev in zc_ready[g]:
+                    side.wait_event(ev)
                 table = []
                 for li in lg:
                     c, H, W = self.res_shapes[li]
