@@ -2,8 +2,9 @@
 
 `__call__` keeps the reference's keyword surface (:92-120).  The hot-path subset is implemented
 (`prompt_embeds` / `negative_prompt_embeds` / `latents` / cached conditioning embeddings / `guidance_scale`
-/ `num_inference_steps` / `controlnet_conditioning_scale` / `control_guidance_start|end` / `generator` /
-`output_type` / `callback_on_step_end`); the per-call stages either side of the loop run on
+/ `num_inference_steps` / `num_images_per_prompt` / `eta` / `controlnet_conditioning_scale` /
+`control_guidance_start|end` / `generator` (one or a list) / `guess_mode` / `output_type` / `callback_on_step_end`);
+`timesteps=` raises the reference's own ValueError (neither of its schedulers takes a custom schedule); the per-call stages either side of the loop run on
 `edgestyle_b200.vae.AutoencoderKL` (raw control images of the ControlLoRA nets -> VAE conditioning embedding; final
 latents -> image for `output_type` "pt" / "np" / "pil"); CLIP text encoding and the safety checker are outside the
 path and raise NotImplementedError instead of being silently ignored.
@@ -80,24 +81,36 @@ class EdgeStyleStableDiffusionControlNetPipeline:
             raise ValueError(f"unknown output_type {output_type!r}")
         if output_type != "latent" and self.vae is None:
             raise ValueError('output_type != "latent" needs the pipeline\'s vae (edgestyle_b200.vae.AutoencoderKL)')
-        for name, val in (("ip_adapter_image", ip_adapter_image), ("clip_skip", clip_skip), ("timesteps", timesteps)):
+        for name, val in (("ip_adapter_image", ip_adapter_image), ("clip_skip", clip_skip)):
             if val is not None:
                 raise NotImplementedError(f"{name} is not implemented")
-        if eta != 0.0:
-            raise NotImplementedError("eta != 0 (stochastic DDIM) is not implemented")
+        if timesteps is not None:
+            # retrieve_timesteps (:698-706): neither scheduler the reference uses (DDIM, UniPC of diffusers 0.26.3) takes a
+            # custom schedule -- the reference raises this ValueError
+            raise ValueError(f"The current scheduler class {self.scheduler.__class__}'s `set_timesteps` does not support custom"
+                             f" timestep schedules. Please check whether you are using the correct scheduler.")
         if cross_attention_kwargs and cross_attention_kwargs.get("scale", 1.0) != 1.0:
             raise NotImplementedError('cross_attention_kwargs["scale"] != 1')
-        if num_images_per_prompt != 1:
-            raise NotImplementedError("num_images_per_prompt != 1: batch the prompt_embeds instead")
         if not isinstance(image, (list, tuple)) or len(image) != 6:
             raise ValueError("`image` must be the list of six conditioning tensors")
-        self.h2d_bytes = self.d2h_bytes = 0
-        dev = torch.device("cuda", torch.cuda.current_device())
         self._guidance_scale = guidance_scale
         cfg_on = self.do_classifier_free_guidance  # guidance_scale <= 1 disables CFG (:319,329,443-447): one row per image
-        n_img = prompt_embeds.shape[0]
+        n_prompts = prompt_embeds.shape[0]
+        n_per = int(num_images_per_prompt)
+        if n_per < 1:
+            raise ValueError("num_images_per_prompt must be >= 1")
+        n_img = n_prompts * n_per
         if cfg_on and negative_prompt_embeds is None:
             raise ValueError("negative_prompt_embeds is required when guidance_scale > 1")
+        if n_per > 1:  # encode_prompt: repeat(1, n, 1).view(bs * n, seq, -1) -- the copies of a prompt are adjacent
+            prompt_embeds = prompt_embeds.repeat_interleave(n_per, dim=0)
+            if negative_prompt_embeds is not None:
+                negative_prompt_embeds = negative_prompt_embeds.repeat_interleave(n_per, dim=0)
+        if isinstance(generator, (list, tuple)) and len(generator) != n_img:  # prepare_latents (:613-617)
+            raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an effective batch"
+                             f" size of {n_img}. Make sure the batch size matches the length of the generators.")
+        self.h2d_bytes = self.d2h_bytes = 0
+        dev = torch.device("cuda", torch.cuda.current_device())
         B = 2 * n_img if cfg_on else n_img
         nets = 6
         # align control guidance (edgestyle_pipeline.py:264-283)
@@ -120,6 +133,11 @@ class EdgeStyleStableDiffusionControlNetPipeline:
         conds = []
         for net, c in zip(self.controlnet.nets, image):
             c = self._to_dev(c, dev)
+            # prepare_image (:645-653): one control image serves the whole batch, one per prompt serves its copies
+            if c.shape[0] == 1 and n_img > 1:
+                c = c.repeat_interleave(n_img, dim=0)
+            elif n_per > 1 and c.shape[0] == n_prompts:
+                c = c.repeat_interleave(n_per, dim=0)
             if c.shape[1] != c0:
                 # raw control image [n, 3, 8h, 8w]: the per-call precompute of prepare_image (:629-664): openpose nets
                 # run their ControlNetConditioningEmbedding, ControlLoRA nets the VAE encoder + conv_vae_out.  The
@@ -140,15 +158,16 @@ class EdgeStyleStableDiffusionControlNetPipeline:
         sch = self.scheduler
         ts = sch.set_timesteps(num_inference_steps)
         if latents is None:
-            latents = torch.randn((n_img, self.unet.config.in_channels, h, w), generator=generator,
-                                  device=generator.device if generator is not None else "cpu")
+            latents = self._randn((n_img, self.unet.config.in_channels, h, w), generator)
+        elif latents.shape[0] != n_img:
+            raise ValueError(f"latents has {latents.shape[0]} rows, expected {n_img}")
         latents = self._to_dev(latents, dev).to(torch.float32).clone() * sch.init_noise_sigma
         if cfg_on:
             g = guidance_scale if torch.is_tensor(guidance_scale) else torch.full((n_img,), float(guidance_scale))
             eng.guidance.copy_(self._to_dev(g.to(torch.float32), dev).reshape(-1).expand(n_img))
             self.h2d_bytes += 0 if torch.is_tensor(guidance_scale) else 4 * n_img
-        elif hasattr(sch, "device_step"):
-            raise NotImplementedError("guidance_scale <= 1 is implemented for the DDIM scheduler only")
+        # prepare_extra_step_kwargs (:411): eta reaches scheduler.step only if it takes one -- DDIM does, UniPC ignores it
+        eta = float(eta) if not hasattr(sch, "device_step") else 0.0
         n_t = len(ts)
         for i, t in enumerate(ts):
             keeps = [1.0 - float(i / n_t < s or (i + 1) / n_t > e)
@@ -158,15 +177,17 @@ class EdgeStyleStableDiffusionControlNetPipeline:
             # guess_mode (:453-459, 487-497): logspace-scaled ControlNet outputs; under CFG the ControlNets only act on
             # the conditional rows, the unconditional rows keep the plain UNet skips
             eng.step(x, float(t), cond_scale, guess_mode=guess_mode, zero_uncond=guess_mode and cfg_on)
-            if not cfg_on:                    # DDIM without CFG: x' = (a'/a) x + (s' - a' s / a) eps, a = sqrt(abar)
+            if hasattr(sch, "device_step"):     # UniPC: x0-prediction + predictor/corrector linear combinations
+                sch.device_step(eng.eps_out, latents, eng.guidance if cfg_on else None)
+            elif eta != 0.0:                  # stochastic DDIM (the rare path: a few small torch kernels)
+                self._ddim_eta_update(latents, eng.eps_out, eng.guidance if cfg_on else None, sch, int(t), eta, generator)
+            elif not cfg_on:                  # DDIM without CFG: x' = (a'/a) x + (s' - a' s / a) eps, a = sqrt(abar)
                 import math
 
                 from .. import ops
                 a_t, a_prev = sch.coefficients(int(t))
                 al, sg, alp, sgp = math.sqrt(a_t), math.sqrt(1 - a_t), math.sqrt(a_prev), math.sqrt(1 - a_prev)
                 ops.lincomb(latents, [(alp / al, latents), (sgp - alp * sg / al, eng.eps_out)])
-            elif hasattr(sch, "device_step"):   # UniPC: x0-prediction + predictor/corrector linear combinations
-                sch.device_step(eng.eps_out, latents, eng.guidance)
             else:                             # DDIM: fused CFG + update
                 a_t, a_prev = sch.coefficients(int(t))
                 eng.cfg_ddim_update(latents, a_t, a_prev)
@@ -193,6 +214,30 @@ class EdgeStyleStableDiffusionControlNetPipeline:
         if not return_dict:
             return (images, None)
         return StableDiffusionPipelineOutput(images=images, nsfw_content_detected=None)
+
+    @staticmethod
+    def _randn(shape, generator, device="cpu"):
+        """diffusers randn_tensor: a list of generators draws one image each; a CPU generator draws on the CPU (the
+        result is copied to the device by the caller)."""
+        if isinstance(generator, (list, tuple)):
+            one = (1,) + tuple(shape[1:])
+            return torch.cat([torch.randn(one, generator=g, device=g.device) for g in generator])
+        return torch.randn(shape, generator=generator, device=generator.device if generator is not None else device)
+
+    def _ddim_eta_update(self, latents, eps, guidance, sch, t: int, eta: float, generator):
+        """DDIMScheduler.step with eta > 0 (formulas (12), (16) of the DDIM paper as diffusers 0.26.3 writes them):
+        sigma_t = eta sqrt((1 - a') / (1 - a)) sqrt(1 - a / a'), direction sqrt(1 - a' - sigma_t^2) eps, plus sigma_t z."""
+        import math
+
+        a_t, a_prev = sch.coefficients(t)
+        if guidance is not None:
+            u, c = eps.chunk(2)
+            eps = u + guidance.view(-1, 1, 1, 1) * (c - u)
+        std = eta * math.sqrt((1 - a_prev) / (1 - a_t) * (1 - a_t / a_prev))
+        x0 = (latents - math.sqrt(1 - a_t) * eps) / math.sqrt(a_t)
+        z = self._randn(tuple(latents.shape), generator, device=latents.device)
+        z = self._to_dev(z, latents.device).to(latents.dtype)
+        latents.copy_(math.sqrt(a_prev) * x0 + math.sqrt(max(1 - a_prev - std * std, 0.0)) * eps + std * z)
 
     def _postprocess(self, image: torch.Tensor, output_type: str):
         """VaeImageProcessor.postprocess (diffusers image_processor.py): denormalise to [0, 1], then "pt" (NCHW

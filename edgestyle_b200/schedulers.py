@@ -117,7 +117,8 @@ class UniPCMultistepScheduler:
         return np.stack(R), np.array(b), h_phi_1, B_h
 
     def device_step(self, eps, latents, guidance):
-        """One scheduler.step on the device: `eps` [2*imgs, ...] raw UNet output, `latents` updated in place."""
+        """One scheduler.step on the device: `eps` [2*imgs, ...] raw UNet output (or [imgs, ...] with `guidance` None:
+        no classifier-free guidance), `latents` updated in place."""
         import torch
 
         from . import ops
@@ -128,7 +129,10 @@ class UniPCMultistepScheduler:
             self._last_sample = torch.empty_like(latents)
             self._x0 = torch.empty_like(latents)
         alpha_t, sigma_t = self._alpha_sigma(self.sigmas[i])
-        ops.cfg_x0(eps, latents, guidance, alpha_t, sigma_t, self._x0)      # model_output_convert (on the pre-corrector sample)
+        if guidance is None:                                                # x0 = (x - sigma eps) / alpha
+            ops.lincomb(self._x0, [(1.0 / alpha_t, latents), (-sigma_t / alpha_t, eps)])
+        else:
+            ops.cfg_x0(eps, latents, guidance, alpha_t, sigma_t, self._x0)  # model_output_convert (on the pre-corrector sample)
         m_prev, m_prev2 = self._m[1], self._m[0]                            # model_outputs[-1], [-2] before the shift
         if i > 0 and self._have_last:                                       # UniC corrector with the previous order
             order = self.this_order

@@ -49,12 +49,18 @@ class DDIMScheduler:
         a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
         return a_t, a_prev
 
-    def step(self, eps, t, sample):
+    def step(self, eps, t, sample, eta: float = 0.0, variance_noise=None):
+        """diffusers 0.26.3 DDIMScheduler.step: sigma_t = eta sqrt((1 - a') / (1 - a) (1 - a / a')), direction
+        sqrt(1 - a' - sigma_t^2) eps, plus sigma_t z when eta > 0 (formulas (12), (16) of the DDIM paper)."""
         a_t, a_prev = self.coefficients(int(t))
         a_t = a_t.to(sample.dtype)
         a_prev = a_prev.to(sample.dtype)
         x0 = (sample - (1 - a_t) ** 0.5 * eps) / a_t ** 0.5
-        return a_prev ** 0.5 * x0 + (1 - a_prev) ** 0.5 * eps
+        std = eta * ((1 - a_prev) / (1 - a_t) * (1 - a_t / a_prev)) ** 0.5
+        prev = a_prev ** 0.5 * x0 + (1 - a_prev - std ** 2) ** 0.5 * eps
+        if eta > 0:
+            prev = prev + std * variance_noise
+        return prev
 
 
 class UniPCMultistepScheduler:

@@ -452,6 +452,97 @@ def test_pipeline_without_cfg_matches_oracle():
     assert _psnr(out.images, lat) >= 40.0
 
 
+def _tiny_pipeline(scheduler=None, h=16, w=16, images=1):
+    from edgestyle_b200 import config as C
+    from edgestyle_b200.model import (CachedControlNetModel, ControlLoRAModel, EdgeStyleMultiControlNetModel,
+                                      EdgeStyleStableDiffusionControlNetPipeline, UNet2DConditionModel)
+    from oracle.sd15 import SD15Config
+    from oracle.step import build_models, synthetic_inputs
+
+    ocfg = SD15Config(block_out_channels=(64, 128, 256, 256), cross_attention_dim=96)
+    m = build_models(ocfg, (h, w), rank=4)
+    inp = synthetic_inputs(ocfg, images, h, w)
+    cfg = C.UNetConfig.from_any(ocfg)
+    unet = UNet2DConditionModel(cfg, m.unet.state_dict())
+    agn = ControlLoRAModel(cfg, m.lora_agnostic.state_dict(), 4, unet=unet)
+    clo = ControlLoRAModel(cfg, m.lora_clothes.state_dict(), 4, unet=unet)
+    pose = CachedControlNetModel(cfg, m.openpose.state_dict())
+    multi = EdgeStyleMultiControlNetModel([agn, pose, clo, pose, clo, pose], m.controlnet.merge_state_dict(), (h, w))
+    pipe = EdgeStyleStableDiffusionControlNetPipeline(unet=unet, controlnet=multi, scheduler=scheduler)
+    return pipe, m, inp
+
+
+def test_pipeline_stochastic_ddim_matches_oracle():
+    """eta > 0 (edgestyle_pipeline.py:411, 520-522: prepare_extra_step_kwargs hands eta and the generator to
+    DDIMScheduler.step): same per-step noise draws from the same CPU generator -> same latents as the oracle loop."""
+    from oracle.schedulers import DDIMScheduler
+    from oracle.step import cfg_combine, fused_step
+
+    pipe, m, inp = _tiny_pipeline()
+    steps, eta, gs = 5, 0.7, 3.0
+    out = pipe(image=inp.conds, prompt_embeds=inp.prompt_embeds[1:], negative_prompt_embeds=inp.prompt_embeds[:1],
+               latents=inp.latents, num_inference_steps=steps, guidance_scale=gs, eta=eta, output_type="latent",
+               generator=torch.Generator().manual_seed(77))
+    m.unet.to(DEV)
+    m.controlnet.to(DEV)
+    g = torch.Generator().manual_seed(77)
+    sch = DDIMScheduler()
+    lat, pe, conds = inp.latents.to(DEV), inp.prompt_embeds.to(DEV), [c.to(DEV) for c in inp.conds]
+    for t in sch.set_timesteps(steps):
+        e = cfg_combine(fused_step(m, torch.cat([lat] * 2), t.to(DEV), pe, [1.0] * 6, conds), gs)
+        z = torch.randn(lat.shape, generator=g).to(DEV)
+        lat = sch.step(e, t, lat, eta=eta, variance_noise=z)
+    psnr = _psnr(out.images, lat)
+    print(f"stochastic DDIM eta {eta}: latent PSNR {psnr:.1f} dB")
+    assert psnr >= 40.0
+    # and eta really changes the result
+    det = pipe(image=inp.conds, prompt_embeds=inp.prompt_embeds[1:], negative_prompt_embeds=inp.prompt_embeds[:1],
+               latents=inp.latents, num_inference_steps=steps, guidance_scale=gs, output_type="latent")
+    assert (det.images - out.images).abs().max().item() > 1e-2
+
+
+def test_pipeline_unipc_without_cfg_matches_oracle():
+    """guidance_scale <= 1 under the reference's default scheduler (UniPC): one row per image, no CFG combine."""
+    from edgestyle_b200.schedulers import UniPCMultistepScheduler
+    from oracle.schedulers import UniPCMultistepScheduler as OracleUniPC
+    from oracle.step import fused_step
+
+    pipe, m, inp = _tiny_pipeline(scheduler=UniPCMultistepScheduler())
+    conds1 = [c[1:] for c in inp.conds]
+    out = pipe(image=conds1, prompt_embeds=inp.prompt_embeds[1:], latents=inp.latents, num_inference_steps=6,
+               guidance_scale=1.0, output_type="latent")
+    m.unet.to(DEV)
+    m.controlnet.to(DEV)
+    sch = OracleUniPC()
+    lat, pe, conds = inp.latents.to(DEV), inp.prompt_embeds[1:].to(DEV), [c.to(DEV) for c in conds1]
+    for t in sch.set_timesteps(6):
+        lat = sch.step(fused_step(m, lat, t.to(DEV), pe, [1.0] * 6, conds), t, lat)
+    psnr = _psnr(out.images, lat)
+    print(f"UniPC without CFG: latent PSNR {psnr:.1f} dB")
+    assert psnr >= 40.0
+
+
+def test_pipeline_num_images_per_prompt_and_generator_list():
+    """encode_prompt / prepare_image / prepare_latents (edgestyle_pipeline.py:315-330, 600-653): num_images_per_prompt
+    copies of a prompt are adjacent rows, one control image serves the whole batch, a list of generators draws one
+    image's initial noise each -- the call equals the explicitly batched one."""
+    pipe, m, inp = _tiny_pipeline()
+    pos, neg = inp.prompt_embeds[1:], inp.prompt_embeds[:1]
+    conds1 = [c[1:] for c in inp.conds]          # one (conditional-row) embedding per net
+    gens = [torch.Generator().manual_seed(5), torch.Generator().manual_seed(6)]
+    out = pipe(image=conds1, prompt_embeds=pos, negative_prompt_embeds=neg, num_images_per_prompt=2, generator=gens,
+               num_inference_steps=3, guidance_scale=4.0, output_type="latent")
+    assert out.images.shape[0] == 2
+    lat = torch.cat([torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(s)) for s in (5, 6)])
+    want = pipe(image=[c.repeat(2, 1, 1, 1) for c in conds1], prompt_embeds=pos.repeat(2, 1, 1),
+                negative_prompt_embeds=neg.repeat(2, 1, 1), latents=lat, num_inference_steps=3, guidance_scale=4.0,
+                output_type="latent")
+    # run-to-run spread of the kernels (atomics order) only
+    assert (out.images - want.images).abs().max().item() <= 1e-2 * max(1.0, want.images.abs().max().item())
+    # different seeds -> different images
+    assert (out.images[0] - out.images[1]).abs().max().item() > 1e-2
+
+
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_step_parity_768x1024(dtype, monkeypatch):
     """BASELINE config 5: 96 x 128 latent (768 x 1024 image), full SD1.5 widths -- long-sequence self-attention

@@ -127,8 +127,11 @@ def test_pipeline_rejects_out_of_scope_arguments(models):
         pipe(image=conds, prompt_embeds=pe, negative_prompt_embeds=pe, output_type="pil")
     with pytest.raises(ValueError):
         pipe(image=conds, prompt_embeds=pe, negative_prompt_embeds=pe, output_type="jpeg")
-    with pytest.raises(NotImplementedError):
-        pipe(image=conds, prompt_embeds=pe, negative_prompt_embeds=pe, output_type="latent", eta=0.5)
+    with pytest.raises(ValueError, match="does not support custom"):  # retrieve_timesteps (edgestyle_pipeline.py:698-706)
+        pipe(image=conds, prompt_embeds=pe, negative_prompt_embeds=pe, output_type="latent", timesteps=[900, 500, 100])
+    with pytest.raises(ValueError, match="list of generators"):      # prepare_latents (:613-617)
+        pipe(image=conds, prompt_embeds=pe, negative_prompt_embeds=pe, output_type="latent", num_images_per_prompt=2,
+             generator=[torch.Generator().manual_seed(0)])
     with pytest.raises(NotImplementedError):
         pipe(image=conds, prompt_embeds=pe, negative_prompt_embeds=pe, output_type="latent", clip_skip=1)
     with pytest.raises(ValueError):
