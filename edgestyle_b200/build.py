@@ -31,6 +31,8 @@ PDL_TRIGGER_MAX_CTAS = int(os.environ.get("ES_PDL_TRIGGER_MAX_CTAS", "0"))
 NVCC_FLAGS.append(f"-DES_PDL_TRIGGER_MAX_CTAS={PDL_TRIGGER_MAX_CTAS}")
 # fraction of the softmax exponentials taken off the MUFU pipe (attention.cu): 0 = none, n = every n-th score
 NVCC_FLAGS.append(f"-DES_ATT_POLY_EVERY={int(os.environ.get('ES_ATT_POLY_EVERY', '0'))}")
+if os.environ.get("ES_ATT2_POLY_MASK"):  # which score pairs of the softmax take the FMA-pipe exponential (attention2.cuh)
+    NVCC_FLAGS.append(f"-DES_ATT2_POLY_MASK={int(os.environ['ES_ATT2_POLY_MASK'], 0)}")
 NVCC_FLAGS.append(f"-DES_PDL_LATE_TRIGGER={int(os.environ.get('ES_PDL_LATE_TRIGGER', '0'))}")
 # resident CTAs per SM the merge's phase 2 is compiled for (1: 222 registers, no spills; 2: 128 registers, 196 B spilled)
 NVCC_FLAGS.append(f"-DES_MERGE_P2_BLOCKS={int(os.environ.get('ES_MERGE_P2_BLOCKS', '2'))}")

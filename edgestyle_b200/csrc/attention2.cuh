@@ -26,6 +26,11 @@
 namespace es {
 
 constexpr int kAtt2KV = 64;  // keys per K/V tile
+#ifndef ES_ATT2_POLY_MASK
+#define ES_ATT2_POLY_MASK 0x1084
+#endif
+// which of the 16 score pairs of a 32-score half row take the FMA-pipe exponential (bit p = pair p); 0 = none
+constexpr uint32_t kAtt2PolyMask = ES_ATT2_POLY_MASK;
 
 template <typename T, int NA, int QT>
 __global__ void __launch_bounds__(64 + 128 * QT, (NA == 1) ? 2 : 1)
@@ -221,10 +226,17 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       // row max of the tile (raw scores); a partial last tile masks its tail
       float mx = -INFINITY;
       if (full_tile) {
+        // four independent chains: one chain of 32 dependent FMNMX3 is ~190 cycles in which the warp issues nothing else
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(va[i]), __uint_as_float(va[i + 1]));
+        for (int i = 0; i < 32; i += 8) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(vb[i]), __uint_as_float(vb[i + 1]));
+          for (int c = 0; c < 4; ++c) {
+            m4[c] = fmax3(m4[c], __uint_as_float(va[i + 2 * c]), __uint_as_float(va[i + 2 * c + 1]));
+            m4[c] = fmax3(m4[c], __uint_as_float(vb[i + 2 * c]), __uint_as_float(vb[i + 2 * c + 1]));
+          }
+        }
+        mx = fmaxf(fmax3(m4[0], m4[1], m4[2]), m4[3]);
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -264,23 +276,49 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_arrive(&s_free[t]);
       if (lane == 0 && (j == 8 || j == 9)) ATT_TRACE(j - 7, (warp - 2) * 4 + 1);
       const float neg_m = -m_run;
-      float s0 = 0.f, s1 = 0.f;
+      uint64_t sum2 = pk2(0.f, 0.f);
+      // exponentials: the score pairs selected by kAtt2PolyMask go through a polynomial on the FMA pipe (packed fp32
+      // pairs: Cody-Waite split with the 1.5 * 2^23 rounding constant, degree-3 minimax of 2^f on [-0.5, 0.5], relative
+      // error 7.5e-5 < half an ulp of the 16-bit P it feeds), the rest through MUFU ex2 -- the MUFU pipe (16 ex2 / clk / SM)
+      // is this kernel's floor, the FMA pipe has 8 x its rate
+      const uint64_t sl2_2 = pk2(sl2, sl2), negm_2 = pk2(neg_m, neg_m);
+      auto exp_pair = [&](uint32_t a, uint32_t b, bool poly, float& p0, float& p1) {
+        float x0, x1;
+        upk2(fma2(pk2(__uint_as_float(a), __uint_as_float(b)), sl2_2, negm_2), x0, x1);
+        if (!poly) {
+          p0 = ex2_approx(x0);
+          p1 = ex2_approx(x1);
+          return;
+        }
+        const uint64_t x2 = pk2(fmaxf(x0, -120.f), fmaxf(x1, -120.f));  // (-inf of a masked tail included)
+        const uint64_t t2 = add2(x2, pk2(12582912.f, 12582912.f));      // n = round(x) in the low mantissa bits
+        const uint64_t n2 = add2(t2, pk2(-12582912.f, -12582912.f));
+        const uint64_t f2 = fma2(n2, pk2(-1.f, -1.f), x2);              // f = x - n in [-0.5, 0.5]
+        uint64_t q2 = fma2(f2, pk2(0.0551716685f, 0.0551716685f), pk2(0.2426111251f, 0.2426111251f));
+        q2 = fma2(q2, f2, pk2(0.6932609677f, 0.6932609677f));
+        q2 = fma2(q2, f2, pk2(0.9999280572f, 0.9999280572f));
+        float q0, q1, t0, t1;
+        upk2(q2, q0, q1);
+        upk2(t2, t0, t1);
+        p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));  // q * 2^n
+        p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+      };
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(va[i]), sl2, neg_m));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(va[i + 1]), sl2, neg_m));
-        s0 += p0;
-        s1 += p1;
+        float p0, p1;
+        exp_pair(va[i], va[i + 1], (kAtt2PolyMask >> (i >> 1)) & 1u, p0, p1);
+        sum2 = add2(sum2, pk2(p0, p1));
         pk[i >> 1] = Cvt<T>::pack2(p0, p1);
       }
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(vb[i]), sl2, neg_m));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(vb[i + 1]), sl2, neg_m));
-        s0 += p0;
-        s1 += p1;
+        float p0, p1;
+        exp_pair(vb[i], vb[i + 1], (kAtt2PolyMask >> (i >> 1)) & 1u, p0, p1);
+        sum2 = add2(sum2, pk2(p0, p1));
         pk[16 + (i >> 1)] = Cvt<T>::pack2(p0, p1);
       }
+      float s0, s1;
+      upk2(sum2, s0, s1);
       l_run += s0 + s1;
       if (lane == 0 && (j == 8 || j == 9)) ATT_TRACE(j - 7, (warp - 2) * 4 + 2);
       // ---- P(j) -> smem (canonical K-major SWIZZLE_128B: row r at r * 128 B, 16 B chunk index XOR (r & 7)) ----------

@@ -288,6 +288,26 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int ab_fmt, 
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- packed fp32 pairs (FFMA2 / FADD2 of sm_100)
+// One instruction, two fp32 lanes: HALVES THE ISSUE SLOTS of elementwise fp32 work; the fp32 rate of the SM stays
+// ~128 FMA / clk (tools/ubench_f32x2.cu).
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // ---------------------------------------------------------------- misc math
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 // Exact (erf) GELU.  erf through Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, branch-free: one rcp, one ex2, six FMAs)
