@@ -36,6 +36,7 @@ if os.environ.get("ES_ATT2_POLY_MASK"):  # which score pairs of the softmax take
 NVCC_FLAGS.append(f"-DES_PDL_LATE_TRIGGER={int(os.environ.get('ES_PDL_LATE_TRIGGER', '0'))}")
 # resident CTAs per SM the merge's phase 2 is compiled for (1: 222 registers, no spills; 2: 128 registers, 196 B spilled)
 NVCC_FLAGS.append(f"-DES_MERGE_P2_BLOCKS={int(os.environ.get('ES_MERGE_P2_BLOCKS', '2'))}")
+NVCC_FLAGS += os.environ.get("ES_EXTRA_NVCC_FLAGS", "").split()  # experiments: extra -D switches for a side build
 OUT = os.environ.get("ES_LIB_OUT", OUT)
 OBJ = os.environ.get("ES_OBJ_DIR", OBJ)
 

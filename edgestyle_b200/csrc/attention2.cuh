@@ -31,6 +31,9 @@ constexpr int kAtt2KV = 64;  // keys per K/V tile
 #endif
 // which of the 16 score pairs of a 32-score half row take the FMA-pipe exponential (bit p = pair p); 0 = none
 constexpr uint32_t kAtt2PolyMask = ES_ATT2_POLY_MASK;
+#ifndef ES_ATT2_STAGGER
+#define ES_ATT2_STAGGER 1  // 1: the two query tiles of a CTA run half a key tile apart (see the MMA issuer)
+#endif
 
 template <typename T, int NA, int QT>
 __global__ void __launch_bounds__(64 + 128 * QT, (NA == 1) ? 2 : 1)
@@ -103,15 +106,21 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
         for (int a = 0; a < NA; ++a)
           tma_load_4d(sQ + (t * NA + a) * kAtomBytes, &tmQ, &q_full, a * 64, head, q0 + t * 128, b);
-      for (int j = 0; j < n_tiles; ++j) {
+      // K runs one key tile ahead of V: K(j+1) is wanted right after S(j) has been pulled, V(j) only once P(j) is in smem,
+      // and a V stage is held until the LATER of the two query tiles has issued its P V
+      auto load_k = [&](int j) {
         const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(&k_full[s], NA * kKVAtom);
 #pragma unroll
         for (int a = 0; a < NA; ++a)
           tma_load_4d(sK + (s * NA + a) * kKVAtom, &tmK, &k_full[s], a * 64, head, j * kKV, b);
-        mbar_wait(&v_empty[s], ph ^ 1);
+      };
+      load_k(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        if (j + 1 < n_tiles) load_k(j + 1);
+        mbar_wait(&v_empty[s], ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(&v_full[s], NA * kKVAtom);
 #pragma unroll
         for (int a = 0; a < NA; ++a)
@@ -158,45 +167,89 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                        idesc_qk, (a | k4) != 0);
         umma_commit(&s_full[t]);
       };
+      auto issue_pv = [&](int t, int j) {  // O(t) (+)= P(j) V(j); V: MN-major, 16 keys = 2048 B along K; N atoms kKVAtom apart
+        const uint32_t v_lo = v_lo0 + (j & 1) * kStageLo;
+#pragma unroll
+        for (int k = 0; k < kKV / 16; ++k)
+          umma_f16(tmem_base + o_col0 + t * p.o_stride, mk(p_lo[t] + 2 * k, hi_kmaj), mk(v_lo + k * (2048 >> 4), hi_v),
+                   idesc_pv, (j | k) != 0);
+        umma_commit(&pv_done[t]);
+      };
       mbar_wait(&q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
+      if constexpr (QT == 2 && ES_ATT2_STAGGER) {
+        // The two query tiles run HALF A KEY TILE APART.  In phase, the four softmax warps of a sub-partition (two tiles
+        // x two CTAs) all pull S, then all want the MUFU pipe, then all store P: a period of ~500 + 4 x 416 + 450
+        // cycles with the pipe idle through the first and last part (tools/att_trace.py).  Tile 1 therefore starts
+        // after tile 0 has released S(0), and the issue order below -- QK0(j+1), PV1(j-1), QK1(j+1), PV0(j), each
+        // behind its own barrier -- keeps it there: one tile's exponentials run under the other's TMEM / smem phases.
+        issue_qk(0, 0);
+        for (int j = 0; j < n_tiles; ++j) {
+          const int s = j & 1;
+          if (j + 1 < n_tiles) {  // [A] S0(j+1) as soon as tile 0 has pulled S0(j)
+            mbar_wait(&k_full[s ^ 1], ((j + 1) >> 1) & 1);
+            mbar_wait(&s_free[0], j & 1);
+            tc_fence_after();
+            issue_qk(0, s ^ 1);
+          }
+          ATT_TRACE(0, 4 * j + 0);
+          if (j == 0) {           // [B] tile 1 starts here ...
+            issue_qk(1, 0);
+            umma_commit(&k_empty[0]);
+          } else {                //     ... and stays one P V behind
+            mbar_wait(&p_full[1], (j - 1) & 1);
+            tc_fence_after();
+            issue_pv(1, j - 1);
+            umma_commit(&v_empty[s ^ 1]);
+          }
+          ATT_TRACE(0, 4 * j + 1);
+          if (j + 1 < n_tiles) {  // [C] S1(j+1)
+            mbar_wait(&s_free[1], j & 1);
+            tc_fence_after();
+            issue_qk(1, s ^ 1);
+            umma_commit(&k_empty[s ^ 1]);
+          }
+          ATT_TRACE(0, 4 * j + 2);
+          mbar_wait(&v_full[s], (j >> 1) & 1);  // [D] O0 += P0(j) V(j)
+          mbar_wait(&p_full[0], j & 1);
+          tc_fence_after();
+          issue_pv(0, j);
+          ATT_TRACE(0, 4 * j + 3);
+        }
+        mbar_wait(&p_full[1], (n_tiles - 1) & 1);
+        tc_fence_after();
+        issue_pv(1, n_tiles - 1);
+        umma_commit(&v_empty[(n_tiles - 1) & 1]);
+      } else {
 #pragma unroll
-      for (int t = 0; t < QT; ++t) issue_qk(t, 0);
-      umma_commit(&k_empty[0]);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        if (j + 1 < n_tiles) {  // S(j+1) = Q K(j+1)^T as soon as S(j) has been pulled into registers
-          mbar_wait(&k_full[s ^ 1], ((j + 1) >> 1) & 1);
-          ATT_TRACE(3, 8 * (j & 7) + 0);
+        for (int t = 0; t < QT; ++t) issue_qk(t, 0);
+        umma_commit(&k_empty[0]);
+        for (int j = 0; j < n_tiles; ++j) {
+          const int s = j & 1;
+          const uint32_t ph = (j >> 1) & 1;
+          if (j + 1 < n_tiles) {  // S(j+1) = Q K(j+1)^T as soon as S(j) has been pulled into registers
+            mbar_wait(&k_full[s ^ 1], ((j + 1) >> 1) & 1);
+#pragma unroll
+            for (int t = 0; t < QT; ++t) {
+              mbar_wait(&s_free[t], j & 1);
+              tc_fence_after();
+              issue_qk(t, s ^ 1);
+            }
+            umma_commit(&k_empty[s ^ 1]);
+          }
+          ATT_TRACE(0, 4 * j + 0);  // S(j) of both tiles consumed, Q K(j+1)^T issued
+          mbar_wait(&v_full[s], ph);
+          ATT_TRACE(0, 4 * j + 1);
 #pragma unroll
           for (int t = 0; t < QT; ++t) {
-            mbar_wait(&s_free[t], j & 1);
+            mbar_wait(&p_full[t], j & 1);  // P(j) of tile t in smem
             tc_fence_after();
-            ATT_TRACE(3, 8 * (j & 7) + 1 + 2 * t);
-            issue_qk(t, s ^ 1);
-            ATT_TRACE(3, 8 * (j & 7) + 2 + 2 * t);
+            issue_pv(t, j);
+            ATT_TRACE(0, 4 * j + 2 + (t ? 1 : 0));  // P(j) V of tile t issued
           }
-          umma_commit(&k_empty[s ^ 1]);
+          umma_commit(&v_empty[s]);
         }
-        ATT_TRACE(0, 4 * j + 0);  // S(j) of both tiles consumed, Q K(j+1)^T issued
-        mbar_wait(&v_full[s], ph);
-        ATT_TRACE(0, 4 * j + 1);
-        const uint32_t v_lo = v_lo0 + s * kStageLo;
-#pragma unroll
-        for (int t = 0; t < QT; ++t) {
-          mbar_wait(&p_full[t], j & 1);  // P(j) of tile t in smem
-          tc_fence_after();
-          ATT_TRACE(3, 8 * (j & 7) + 5 + t);
-#pragma unroll
-          for (int k = 0; k < kKV / 16; ++k)  // V: MN-major, 16 keys = 2048 B along K; N atoms (64 of d) kKVAtom apart
-            umma_f16(tmem_base + o_col0 + t * p.o_stride, mk(p_lo[t] + 2 * k, hi_kmaj), mk(v_lo + k * (2048 >> 4), hi_v),
-                     idesc_pv, (j | k) != 0);
-          umma_commit(&pv_done[t]);
-          ATT_TRACE(0, 4 * j + 2 + (t ? 1 : 0));  // P(j) V of tile t issued
-        }
-        umma_commit(&v_empty[s]);
       }
     }
   } else {
@@ -245,7 +298,6 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           mx = fmaxf(mx, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
         }
       }
-      uint32_t pk[32];  // P as packed 16-bit pairs
       bool pv_waited = false;
       const float m_tile = mx * sl2;
       if (j == 0) {
@@ -303,31 +355,29 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));  // q * 2^n
         p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
       };
+      // P(j) goes to smem chunk by chunk as it is produced (canonical K-major SWIZZLE_128B: row r at r * 128 B, 16 B
+      // chunk index XOR (r & 7)): the eight 16-byte stores run under the exponentials instead of after them (the
+      // separate store phase was ~300 of the ~2400 cycles of a key tile).  The MMAs reading P(j-1) must have retired.
+      if (j > 0 && !pv_waited) mbar_wait(&pv_done[t], (j - 1) & 1);
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        float p0, p1;
-        exp_pair(va[i], va[i + 1], (kAtt2PolyMask >> (i >> 1)) & 1u, p0, p1);
-        sum2 = add2(sum2, pk2(p0, p1));
-        pk[i >> 1] = Cvt<T>::pack2(p0, p1);
-      }
+      for (int q4 = 0; q4 < 8; ++q4) {
+        uint32_t w[4];
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        float p0, p1;
-        exp_pair(vb[i], vb[i + 1], (kAtt2PolyMask >> (i >> 1)) & 1u, p0, p1);
-        sum2 = add2(sum2, pk2(p0, p1));
-        pk[16 + (i >> 1)] = Cvt<T>::pack2(p0, p1);
+        for (int e = 0; e < 4; ++e) {
+          const int i = (q4 & 3) * 8 + 2 * e;  // element pair inside the 32-score half row
+          float p0, p1;
+          if (q4 < 4) exp_pair(va[i], va[i + 1], (kAtt2PolyMask >> (i >> 1)) & 1u, p0, p1);
+          else exp_pair(vb[i], vb[i + 1], (kAtt2PolyMask >> (i >> 1)) & 1u, p0, p1);
+          sum2 = add2(sum2, pk2(p0, p1));
+          w[e] = Cvt<T>::pack2(p0, p1);
+        }
+        const int chunk = q4 ^ (r & 7);
+        *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(w[0], w[1], w[2], w[3]);
       }
       float s0, s1;
       upk2(sum2, s0, s1);
       l_run += s0 + s1;
       if (lane == 0 && (j == 8 || j == 9)) ATT_TRACE(j - 7, (warp - 2) * 4 + 2);
-      // ---- P(j) -> smem (canonical K-major SWIZZLE_128B: row r at r * 128 B, 16 B chunk index XOR (r & 7)) ----------
-      if (j > 0 && !pv_waited) mbar_wait(&pv_done[t], (j - 1) & 1);  // the MMAs reading P(j-1) have retired
-#pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) {
-        const int chunk = q4 ^ (r & 7);
-        *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
-      }
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       mbar_arrive(&p_full[t]);
       if (lane == 0 && (j == 8 || j == 9)) ATT_TRACE(j - 7, (warp - 2) * 4 + 3);
