@@ -14,6 +14,7 @@
 
 #include "common.h"
 #include "ptx.cuh"
+#include "epilogue.cuh"
 
 namespace es {
 

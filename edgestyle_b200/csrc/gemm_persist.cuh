@@ -42,7 +42,7 @@ struct PsCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kPanels = (BLOCK_N + 63) / 64;
   static constexpr int kPanelBytes = kPanels * 16384;
-  static constexpr int kVecBytes = 4 * BLOCK_N * 4;
+  static constexpr int kVecBytes = 2 * 4 * BLOCK_N * 4;  // two units' epilogue vectors (the next one is staged early)
   static constexpr int kGnBytes = 4 * kGnSlots * 2 * 4;
   static constexpr int kFixed = kPanelBytes + kVecBytes + kGnBytes + 2048;
   static constexpr int kStagesRaw = (227 * 1024 - kFixed) / kStageBytes;
@@ -105,8 +105,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // every later access a generic LD / ST (64-bit address arithmetic, no LDS / STS) -- measured in the epilogues
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* panels = smem + kStages * Cfg::kStageBytes;
-  float* vec_s = reinterpret_cast<float*>(panels + Cfg::kPanelBytes);  // [4 lane quarters][BLOCK_N]
-  float* gstat_s = vec_s + 4 * BLOCK_N;
+  float* vec_s0 = reinterpret_cast<float*>(panels + Cfg::kPanelBytes);  // [2 units][4 lane quarters][BLOCK_N]
+  float* gstat_s = vec_s0 + 2 * 4 * BLOCK_N;
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];   // MMA -> epilogue
@@ -228,12 +228,23 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool gn_panel = p.gn_ws != nullptr;
     const bool ln_in = p.ln_rowstat != nullptr;
     int ui = 0, res_it = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+    // Everything a unit's epilogue needs from global memory besides the accumulator -- the LayerNorm statistics of the
+    // thread's input row and the per-column vector (bias / folded bias + column sums / bias + time-embedding row) -- is
+    // FETCHED ONE UNIT AHEAD (folded-LayerNorm GEMMs: before the previous unit's drain; the others: at its end, under the
+    // TMA store's read of the panels), the vector into the other half of vec_s: two dependent global loads (~650 cycles each) sat in front of every unit's drain
+    // (tools/persist_trace.py), and an epilogue warp has nothing else to issue meanwhile.  (Holding the prefetched
+    // values in registers across the drain instead spills: 131 vs 110 us on the GEGLU GEMM.)
+    constexpr int kVPT = (BLOCK_N + kPsEpiThreads - 1) / kPsEpiThreads;  // columns of the vector staged by one thread
+    struct UnitRow {
+      int x0, y0, i0, n0, oc0, b_noff, x_end, img;
+      long long row;
+      bool row_ok;
+    };
+    auto unit_row = [&](int u) {
       const PsUnit d = ps_decode(p, u, m_tiles, BLOCK_N);
-      const int as = ui & 1;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
-      const int x0 = d.x0, y0 = d.y0, i0 = d.i0, n0 = d.n0, b_noff = d.b_noff;
-      const int oc0 = geglu ? d.tn * GH : n0;
+      UnitRow ur;
+      ur.x0 = d.x0, ur.y0 = d.y0, ur.i0 = d.i0, ur.n0 = d.n0, ur.b_noff = d.b_noff, ur.x_end = d.x_end;
+      ur.oc0 = geglu ? d.tn * GH : d.n0;
       int xl, yl, il;
       if (p.flat) {
         xl = r;
@@ -244,15 +255,101 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         yl = (r / p.bw) % p.bh;
         il = r / (p.bw * p.bh);
       }
-      const int x = x0 + xl, y = y0 + yl, img_c = i0 + il;
-      const bool row_ok = (x < d.x_end) && (y < p.H) && (img_c < p.NI);
-      const int img = p.flat ? (p.rows_per_img > 0 ? x / p.rows_per_img : 0) : img_c;
-      const long long row = (static_cast<long long>(img_c) * p.H + y) * p.W + x;
+      const int x = d.x0 + xl, y = d.y0 + yl, img_c = d.i0 + il;
+      ur.row_ok = (x < d.x_end) && (y < p.H) && (img_c < p.NI);
+      ur.img = p.flat ? (p.rows_per_img > 0 ? x / p.rows_per_img : 0) : img_c;
+      ur.row = (static_cast<long long>(img_c) * p.H + y) * p.W + x;
+      return ur;
+    };
+    auto fetch_ln = [&](const UnitRow& ur) {  // (sum, sumsq) of this thread's INPUT row (accumulated by the producing GEMM)
+      return (ln_in && ur.row_ok) ? *reinterpret_cast<const float2*>(p.ln_rowstat + 2 * ur.row) : make_float2(0.f, 0.f);
+    };
+    // per-column epilogue vector: vec[quarter][col] = bias[col] + rowvec[image of the quarter's rows][col]; with a folded
+    // LayerNorm slot 0 = folded bias, slot 1 = column sums of the gamma-scaled weights
+    auto fetch_vec = [&](const UnitRow& ur, float (&v)[kVPT][4]) {
+#pragma unroll
+      for (int k = 0; k < kVPT; ++k) {
+        const int col = et + k * kPsEpiThreads;
+        v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.f;
+        if (col >= BLOCK_N) continue;
+        const bool col_ok = ur.n0 + col < p.N;
+        const float bv = (col_ok && p.bias) ? p.bias[ur.b_noff + ur.n0 + col] : 0.f;
+        if (ln_in) {
+          v[k][0] = bv;
+          v[k][1] = col_ok ? p.ln_colsum[ur.b_noff + ur.n0 + col] : 0.f;
+          continue;
+        }
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) {
+          float rv = 0.f;
+          if (col_ok && p.rowvec) {
+            const int r4 = w4 * 32;
+            int ximg;
+            bool ok4;
+            if (p.flat) {
+              ximg = (ur.x0 + r4) / p.rows_per_img;
+              ok4 = ur.x0 + r4 < ur.x_end;
+            } else {
+              ximg = ur.i0 + r4 / (p.bw * p.bh);
+              ok4 = ximg < p.NI;
+            }
+            if (ok4) rv = p.rowvec[static_cast<long long>(ximg) * p.rowvec_ld + ur.n0 + col];
+          }
+          v[k][w4] = bv + rv;
+        }
+      }
+    };
+    auto park_vec = [&](const float (&v)[kVPT][4], float* dst) {
+#pragma unroll
+      for (int k = 0; k < kVPT; ++k) {
+        const int col = et + k * kPsEpiThreads;
+        if (col >= BLOCK_N) continue;
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4)
+          if (!ln_in || w4 < 2) dst[w4 * BLOCK_N + col] = v[k][w4];
+      }
+    };
+    UnitRow cur = unit_row(blockIdx.x < n_units ? blockIdx.x : 0);
+    float2 ln_cur = make_float2(0.f, 0.f);
+    if (blockIdx.x < n_units) {
+      float v0[kVPT][4];
+      ln_cur = fetch_ln(cur);
+      fetch_vec(cur, v0);
+      park_vec(v0, vec_s0);
+    }
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+      const int as = ui & 1;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
+      float* vec_s = vec_s0 + (ui & 1) * 4 * BLOCK_N;
+      const int x0 = cur.x0, y0 = cur.y0, i0 = cur.i0, n0 = cur.n0, oc0 = cur.oc0;
+      const bool row_ok = cur.row_ok;
+      const int img = cur.img;
+      const long long row = cur.row;
       float ln_mean = 0.f, ln_rstd = 1.f;
-      if (ln_in && row_ok) {  // LayerNorm statistics of this thread's INPUT row (accumulated by the producing GEMM)
-        const float2 sq = *reinterpret_cast<const float2*>(p.ln_rowstat + 2 * row);
-        ln_mean = sq.x * p.ln_inv_k;
-        ln_rstd = rsqrtf(fmaxf(sq.y * p.ln_inv_k - ln_mean * ln_mean, 0.f) + p.ln_eps);
+      if (ln_in && row_ok) {
+        ln_mean = ln_cur.x * p.ln_inv_k;
+        ln_rstd = rsqrtf(fmaxf(ln_cur.y * p.ln_inv_k - ln_mean * ln_mean, 0.f) + p.ln_eps);
+      }
+      // Folded-LayerNorm GEMMs (every transformer projection: short K, the epilogue IS the unit): the next unit's row
+      // statistics (two registers) and vector (cp.async straight into the other half of vec_s, no registers) are
+      // requested before this unit's drain
+      const bool have_next = u + static_cast<int>(gridDim.x) < n_units;
+      float2 ln_next = make_float2(0.f, 0.f);
+      if (have_next && ln_in) {
+        const UnitRow nx = unit_row(u + gridDim.x);
+        ln_next = fetch_ln(nx);
+        float* dst = vec_s0 + ((ui + 1) & 1) * 4 * BLOCK_N;
+#pragma unroll
+        for (int k = 0; k < kVPT; ++k) {
+          const int col = et + k * kPsEpiThreads;
+          if (col < BLOCK_N) {
+            const bool col_ok = nx.n0 + col < p.N;
+            const int gc = col_ok ? nx.b_noff + nx.n0 + col : 0;
+            cp_async_4(dst + col, p.bias ? p.bias + gc : p.ln_colsum + gc, col_ok && p.bias != nullptr);
+            cp_async_4(dst + BLOCK_N + col, p.ln_colsum + gc, col_ok);
+          }
+        }
+        cp_async_commit();
       }
       // (A) the previous unit's TMA stores have finished reading the panels (thread 64 waited before this barrier)
       asm volatile("bar.sync 1, %0;" ::"n"(kPsEpiThreads) : "memory");
@@ -264,34 +361,6 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (gn_panel)
         for (int i = et; i < 4 * kGnSlots * 2; i += kPsEpiThreads) gstat_s[i] = 0.f;
-      // per-column epilogue vector: vec[quarter][col] = bias[col] + rowvec[image of the quarter's rows][col]
-      for (int col = et; col < BLOCK_N; col += kPsEpiThreads) {
-        const bool col_ok = n0 + col < p.N;
-        const float bv = (col_ok && p.bias) ? p.bias[b_noff + n0 + col] : 0.f;
-        if (ln_in) {  // slot 0: folded bias, slot 1: column sums of the gamma-scaled weights
-          vec_s[col] = bv;
-          vec_s[BLOCK_N + col] = col_ok ? p.ln_colsum[b_noff + n0 + col] : 0.f;
-          continue;
-        }
-#pragma unroll
-        for (int w4 = 0; w4 < 4; ++w4) {
-          float rv = 0.f;
-          if (col_ok && p.rowvec) {
-            const int r4 = w4 * 32;
-            int ximg;
-            bool ok4;
-            if (p.flat) {
-              ximg = (x0 + r4) / p.rows_per_img;
-              ok4 = x0 + r4 < d.x_end;
-            } else {
-              ximg = i0 + r4 / (p.bw * p.bh);
-              ok4 = ximg < p.NI;
-            }
-            if (ok4) rv = p.rowvec[static_cast<long long>(ximg) * p.rowvec_ld + n0 + col];
-          }
-          vec_s[w4 * BLOCK_N + col] = bv + rv;
-        }
-      }
       if (threadIdx.x == 64) PS_TRACE(ui, 4);
       mbar_wait(&tmem_full_bar[as], (ui >> 1) & 1);
       tc_fence_after();
@@ -304,25 +373,11 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       const float* vrow = ln_in ? vec_s : vec_s + q * BLOCK_N;
       const float* srow = vec_s + BLOCK_N;  // LayerNorm-folded GEMM: column sums
-      float rs_acc = 0.f, rq_acc = 0.f;     // producer side: (sum, sumsq) of this thread's output row
-      // accumulator columns [col, col + 16) -> pre-activation values
+      uint64_t rs2 = pk2(0.f, 0.f), rq2 = pk2(0.f, 0.f);  // producer side: (sum, sumsq) of this thread's output row
+      // accumulator columns [col, col + 16) -> pre-activation values (packed fp32 pairs: epilogue.cuh)
       auto pre16 = [&](int col, float (&a)[16]) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 b = *reinterpret_cast<const float4*>(vrow + col + 4 * j);
-          if (ln_in) {
-            const float4 f = *reinterpret_cast<const float4*>(srow + col + 4 * j);
-            a[4 * j] = (a[4 * j] - ln_mean * f.x) * ln_rstd + b.x;
-            a[4 * j + 1] = (a[4 * j + 1] - ln_mean * f.y) * ln_rstd + b.y;
-            a[4 * j + 2] = (a[4 * j + 2] - ln_mean * f.z) * ln_rstd + b.z;
-            a[4 * j + 3] = (a[4 * j + 3] - ln_mean * f.w) * ln_rstd + b.w;
-          } else {
-            a[4 * j] += b.x;
-            a[4 * j + 1] += b.y;
-            a[4 * j + 2] += b.z;
-            a[4 * j + 3] += b.w;
-          }
-        }
+        if (ln_in) epi_ln_vec16(a, vrow + col, srow + col, ln_mean, ln_rstd);
+        else epi_add_vec16(a, vrow + col);
       };
       // co: output column inside the tile (0..n_tile_out), 16 wide -> this thread's 32 bytes of the smem panel
       auto finish_chunk = [&](int co, float (&o)[16]) {
@@ -341,20 +396,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (has_res) {
           const uint4 r0 = *d0, r1 = *d1;
           const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 f = Cvt<T>::unpack2(rr[j]);
-            o[2 * j] += f.x;
-            o[2 * j + 1] += f.y;
-          }
+          epi_add_res16<T>(o, rr);
         }
-        if (p.rowstat_out) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            rs_acc += o[j];
-            rq_acc += o[j] * o[j];
-          }
-        }
+        if (p.rowstat_out) epi_rowstat16(o, rs2, rq2);
         uint4 w0, w1;
         w0.x = Cvt<T>::pack2(o[0], o[1]); w0.y = Cvt<T>::pack2(o[2], o[3]);
         w0.z = Cvt<T>::pack2(o[4], o[5]); w0.w = Cvt<T>::pack2(o[6], o[7]);
@@ -377,8 +421,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           pre16(ci * 16, av);
           pre16(GH + ci * 16, gv);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = p.alpha * av[j] * gelu_erf_f(gv[j]);
+          epi_geglu16(o, av, gv, p.alpha);
           finish_chunk(ci * 16, o);
         };
         uint32_t va[2][16], vg[2][16];
@@ -400,8 +443,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(a[j]);
           pre16(ci * 16, o);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] *= p.alpha;
+          epi_scale16(o, p.alpha);
           finish_chunk(ci * 16, o);
         };
         uint32_t v[2][16];
@@ -423,9 +465,13 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+
       if (p.rowstat_out && row_ok) {
-        atomicAdd(p.rowstat_out + 2 * row, rs_acc);
-        atomicAdd(p.rowstat_out + 2 * row + 1, rq_acc);
+        float rs_a, rs_b, rq_a, rq_b;
+        upk2(rs2, rs_a, rs_b);
+        upk2(rq2, rq_a, rq_b);
+        atomicAdd(p.rowstat_out + 2 * row, rs_a + rs_b);
+        atomicAdd(p.rowstat_out + 2 * row + 1, rq_a + rq_b);
       }
       fence_proxy_async_smem();
       // (C) panels complete
@@ -496,6 +542,20 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       if (threadIdx.x == 64) PS_TRACE(ui, 8);
+      // the next unit's row statistics and vector: the loads run while the TMA store of this unit reads the panels; the
+      // vector goes to the OTHER half of vec_s (slow warps may still read this unit's half; barrier (B) of the next unit
+      // publishes it)
+      if (have_next) {
+        cur = unit_row(u + gridDim.x);
+        if (ln_in) {
+          ln_cur = ln_next;
+          cp_async_wait_all();
+        } else {
+          float vn[kVPT][4];
+          fetch_vec(cur, vn);
+          park_vec(vn, vec_s0 + ((ui + 1) & 1) * 4 * BLOCK_N);
+        }
+      }
       if (threadIdx.x == 64) tma_store_wait_read0();
       if (threadIdx.x == 64) PS_TRACE(ui, 9);
     }

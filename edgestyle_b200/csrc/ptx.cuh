@@ -97,6 +97,14 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---------------------------------------------------------------- cp.async (LDGSTS), 4-byte elements
+// `valid` false: nothing is read, the destination is zero-filled
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMA
 // Pull `bytes` (multiple of 16) of global memory into L2 without a destination: used to stream the NEXT layer's weights
 // from HBM while the current kernel runs.

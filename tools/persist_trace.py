@@ -3,21 +3,22 @@ import ctypes as C, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from edgestyle_b200 import ext  # noqa: E402
-ext.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgemm_trace.so")
+ext.LIB_PATH = os.environ.get("ES_TRACE_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgemm_trace.so")
 from edgestyle_b200 import ops  # noqa: E402
 lib = ext.load()
 lib.es_gemm_trace.restype = C.c_int
 lib.es_gemm_trace.argtypes = [C.c_void_p]
 names = ["mma: acc free", "mma: first stage full", "mma: last MMA issued", "epi: (A) panels free", "epi: vec staged",
          "epi: acc visible", "epi: drained", "epi: (C) panels complete", "epi: stats done", "epi: store read done"]
-for (M, N, K, res, bn, conv) in [(32768, 320, 320, True, 160, None), (32768, 960, 320, False, 256, None), (32768, 320, 1280, True, 160, None),
-                                 (32768, 320, 320, False, 160, (64, 64, 8))]:
+for (M, N, K, res, bn, conv) in [(32768, 2560, 320, "geglu", 160, None), (32768, 320, 320, True, 160, None), (32768, 960, 320, False, 256, None),
+                                 (32768, 320, 1280, True, 160, None), (32768, 320, 320, False, 160, (64, 64, 8))]:
     taps = 9 if conv else 1
     a = torch.randn(M, K, device="cuda", dtype=torch.float16)
     b = torch.randn(N, K * taps, device="cuda", dtype=torch.float16)
-    out = torch.empty(M, N, device="cuda", dtype=torch.float16)
-    r = torch.randn(M, N, device="cuda", dtype=torch.float16) if res else None
-    kw = dict(out=out, bias=torch.zeros(N, device="cuda"), residual=r, block_n=1000 + bn)
+    geglu = res == "geglu"
+    out = torch.empty(M, N // 2 if geglu else N, device="cuda", dtype=torch.float16)
+    r = torch.randn(M, N, device="cuda", dtype=torch.float16) if (res and not geglu) else None
+    kw = dict(out=out, bias=torch.zeros(N, device="cuda"), residual=r, block_n=1000 + bn, act=1 if geglu else 0)
     if conv:
         kw.update(taps=9, whn=conv, c1=K)
     for _ in range(3):
