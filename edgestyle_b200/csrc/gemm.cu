@@ -507,7 +507,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int full_panels = n_tile_out / 64;
         const int rem = n_tile_out % 64;                   // last, narrower panel (unswizzled, pitch rem*2 B)
         const bool has_res = p.residual != nullptr;
-        if (has_res && threadIdx.x == 64) {
+        // (elect.sync, not a thread-index test, around TMA instructions: see the producer warp)
+        if (has_res && warp == 2 && elect_one()) {
           mbar_expect_tx(&res_bar, static_cast<uint32_t>(kBlockM * n_tile_out * 2));
           for (int pn = 0; pn < full_panels; ++pn) tma_load_4d(smem + pn * 16384, &tmR, &res_bar, oc0 + pn * 64, x0, y0, i0);
           if (rem) tma_load_4d(smem + full_panels * 16384, &tmRp, &res_bar, oc0 + full_panels * 64, x0, y0, i0);
@@ -690,7 +691,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (threadIdx.x == 64) GEMM_TRACE(11);
-        if (threadIdx.x == 64) {
+        if (warp == 2 && elect_one()) {
           for (int pn = 0; pn < full_panels; ++pn) tma_store_4d(&tmO, smem + pn * 16384, oc0 + pn * 64, x0, y0, i0);
           if (rem) tma_store_4d(&tmOp, smem + full_panels * 16384, oc0 + full_panels * 64, x0, y0, i0);
           tma_store_commit();
@@ -752,7 +753,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         if (threadIdx.x == 64) GEMM_TRACE(12);
-        if (threadIdx.x == 64) tma_store_wait_read0();
+        if (warp == 2 && elect_one()) tma_store_wait_read0();  // (the same thread: elect.sync is deterministic per mask)
       } else if (p.act == ES_ACT_GEGLU) {
         constexpr int HALF = BLOCK_N / 2;
         const int oc0 = blockIdx.y * HALF;  // output column base

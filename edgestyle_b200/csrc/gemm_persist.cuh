@@ -354,7 +354,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // (A) the previous unit's TMA stores have finished reading the panels (thread 64 waited before this barrier)
       asm volatile("bar.sync 1, %0;" ::"n"(kPsEpiThreads) : "memory");
       if (threadIdx.x == 64) PS_TRACE(ui, 3);
-      if (has_res && threadIdx.x == 64) {  // the residual tile rides in the output panels, fetched while the MMAs run
+      if (has_res && warp == 2 && elect_one()) {  // the residual tile rides in the output panels, fetched while the MMAs run
         mbar_expect_tx(&res_bar, static_cast<uint32_t>(kBlockM * n_tile_out * 2));
         for (int pn = 0; pn < full_panels; ++pn) tma_load_4d(panels + pn * 16384, &tmR, &res_bar, oc0 + pn * 64, x0, y0, i0);
         if (rem) tma_load_4d(panels + full_panels * 16384, &tmRp, &res_bar, oc0 + full_panels * 64, x0, y0, i0);
@@ -477,7 +477,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // (C) panels complete
       asm volatile("bar.sync 1, %0;" ::"n"(kPsEpiThreads) : "memory");
       if (threadIdx.x == 64) PS_TRACE(ui, 7);
-      if (threadIdx.x == 64) {
+      if (warp == 2 && elect_one()) {  // (elect.sync, not a thread-index test, around TMA instructions)
         for (int pn = 0; pn < full_panels; ++pn) tma_store_4d(&tmO, panels + pn * 16384, oc0 + pn * 64, x0, y0, i0);
         if (rem) tma_store_4d(&tmOp, panels + full_panels * 16384, oc0 + full_panels * 64, x0, y0, i0);
         tma_store_commit();
@@ -556,7 +556,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           park_vec(vn, vec_s0 + ((ui + 1) & 1) * 4 * BLOCK_N);
         }
       }
-      if (threadIdx.x == 64) tma_store_wait_read0();
+      if (warp == 2 && elect_one()) tma_store_wait_read0();  // (the same thread: elect.sync is deterministic per mask)
       if (threadIdx.x == 64) PS_TRACE(ui, 9);
     }
   }
