@@ -418,6 +418,8 @@ class DenoiseEngine:
         # them), levels < merge_split the second (the heavy 64x64-level merges, under the decoder's deep levels);
         # 0 = a single group
         self.merge_split = int(os.environ.get("ES_MERGE_SPLIT", "3"))
+        # next-layer weight prefetch into L2 (ops.WeightPrefetchPlan): "0" off, "1" every GEMM, "decoder" the UNet decoder only
+        self.weight_prefetch = os.environ.get("ES_WEIGHT_PREFETCH", "0")
         # ES_MERGE_BY_LEVEL=1 (default): one merge group per decoder level instead (4 groups = 12 launches at SD1.5's
         # 13 residual levels): the decoder starts after the 8x8-level group alone -- 165 us after the encoders instead of
         # 350 us (tools/timeline.py), 9.81 vs 9.92 ms/step
@@ -1096,6 +1098,7 @@ class DenoiseEngine:
         geo = self._geometry(active)
         self._ensure_text_kv(active)
         self._begin_step_scratch()
+        ops.PREFETCH.gate = self.weight_prefetch != "decoder"
         # -- sample: NCHW fp32 -> NHWC, im2col (K = 36 padded to 64)
         s16 = self.buf("sample16", B * hw, 8)
         ops.nchw_to_nhwc(self.sample_in, s16)
@@ -1317,7 +1320,9 @@ class DenoiseEngine:
             main.wait_event(merged[order[-1]])
             return
         main.wait_event(merged[len(self.res_shapes) - 1])
-        # -- UNet decoder
+        # -- UNet decoder (ES_WEIGHT_PREFETCH=decoder: only here, where one stream runs alone and HBM is idle between the
+        #    layers, does a GEMM pull the next layer's weights into L2)
+        ops.PREFETCH.gate = True
         for i in range(len(boc)):
             H, W = self.levels[len(boc) - 1 - i]
             M = B * H * W
@@ -1355,6 +1360,7 @@ class DenoiseEngine:
         ops.gemm(g, self.conv_out[0], cfg.out_channels, out=o, taps=9, whn=(w, h, B), bias=self.conv_out[1], c1=c0,
                  block_n=32)
         self._nhwc32_to_nchw(o, self.eps_out)
+        ops.PREFETCH.gate = self.weight_prefetch != "decoder"
 
     def _nhwc32_to_nchw(self, o, dst):
         # [B*hw, 16] fp32 (first out_channels valid) -> [B, c, h, w]; tiny (64 KB): a strided copy kernel of torch
@@ -1391,7 +1397,7 @@ class DenoiseEngine:
             self._finish_tuning()
             # next-layer weight prefetch into L2 (ops.WeightPrefetchPlan): measured 11.55 vs 11.40 ms/step -- the extra
             # HBM stream competes with the running layer's own operand traffic -- so it is off unless asked for
-            prefetch = os.environ.get("ES_WEIGHT_PREFETCH", "0") != "0"
+            prefetch = self.weight_prefetch != "0"
             if prefetch:  # second eager pass (tuning is frozen now): record the per-stream order of the weight tensors
                 ops.PREFETCH.begin("record")
                 self._run_step(key)

@@ -44,6 +44,7 @@ class WeightPrefetchPlan:
         self.mode = None
         self.plan = {}
         self.pos = {}
+        self.gate = True  # False: GEMMs launched now get no prefetch hint (the engine opens it for the decoder only)
 
     def begin(self, mode):
         self.mode = mode
@@ -67,7 +68,7 @@ class WeightPrefetchPlan:
             seq = self.plan.get(stream, [])
             if i + 1 < len(seq) and seq[i][0] == ptr:
                 nptr, nb = seq[i + 1]
-                if nb >= self.MIN_BYTES and nptr != ptr:
+                if nb >= self.MIN_BYTES and nptr != ptr and self.gate:
                     return nptr, min(nb, self.MAX_BYTES)
         return None
 
