@@ -427,7 +427,8 @@ class DenoiseEngine:
         # ES_ZC_CHAIN=1: after its encoder pass each chain runs its own zero-convs (deepest group first) on a stream of
         # its own instead of queueing them on the merge stream in front of each group's merge.  Default off -- measured
         # 9.91 vs 9.81 ms/step: the extra concurrency only competes with the decoder's first kernels
-        self.zc_chain = os.environ.get("ES_ZC_CHAIN", "0") != "0"
+        # "first": only the first (deepest) group's zero-convs go to the chains' streams -- the decoder waits for them
+        self.zc_chain = os.environ.get("ES_ZC_CHAIN", "0")
         self.merge_z16 = os.environ.get("ES_MERGE_Z16", "1") != "0"  # fp16 engines keep the merge's z tensor in fp16
         self._stats_of = {}
         self._cat_slot = {}
@@ -1233,12 +1234,12 @@ class DenoiseEngine:
         # through (the ControlLoRA blocks on a side stream behind the main pass, the openpose blocks on the pose
         # stream behind its pass); the merge stream waits group by group
         zc_ready = [[] for _ in level_groups]
-        if self.zc_chain and not self.zc_early:
+        if self.zc_chain != "0" and not self.zc_early:
             if n_lora:
                 zst = self._zc_streams[0]
                 zst.wait_event(ev_main)
                 with torch.cuda.stream(zst):
-                    for g, lg in enumerate(level_groups):
+                    for g, lg in enumerate(level_groups[:1] if self.zc_chain == "first" else level_groups):
                         for li in lg:
                             zero_conv("b", li, outs_b[li])
                         ev = torch.cuda.Event()
@@ -1247,7 +1248,7 @@ class DenoiseEngine:
             if nb_p:
                 st = self._chain_streams[0]
                 with torch.cuda.stream(st):
-                    for g, lg in enumerate(level_groups):
+                    for g, lg in enumerate(level_groups[:1] if self.zc_chain == "first" else level_groups):
                         for li in lg:
                             zero_conv("p", li, outs_p[li])
                         ev = torch.cuda.Event()
