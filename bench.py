@@ -143,8 +143,8 @@ def build_ours(images: int, device, seed: int, h: int = 64, w: int = 64, dtype=t
 
 
 def kernel_rooflines(dev):
-    """Per-kernel roofline entries of the step's dominant kernels at step shapes: CUDA-event time of `reps` back-to-back
-    launches (warm L2, outside the step's timed region), algorithmic FLOPs (2 M N K; attention 4 B h Nq Nkv d) or bytes
+    """Per-kernel roofline entries of the step's dominant kernels at step shapes: CUDA-event time of a CUDA graph of `reps`
+    back-to-back launches (warm L2, outside the step's timed region), algorithmic FLOPs (2 M N K; attention 4 B h Nq Nkv d) or bytes
     against the measured peaks.  Shapes: BASELINE config 2 base pass (8 images)."""
     from edgestyle_b200 import ops
 
@@ -158,12 +158,19 @@ def kernel_rooflines(dev):
     reps = 10
 
     def timeit(fn):
+        # `reps` launches captured into one CUDA graph: an eager loop would time the HOST launch rate (~40 us per call
+        # through ctypes + tensor-map encoding) for every kernel shorter than that
         fn()
+        torch.cuda.synchronize()
+        gph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gph):
+            for _ in range(reps):
+                fn()
+        gph.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(reps):
-            fn()
+        gph.replay()
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) * 1e3 / reps
@@ -204,7 +211,7 @@ def kernel_rooflines(dev):
     x = torch.randn(32768, 320, **f16)
     o = torch.empty_like(x)
     ws = torch.zeros(8, 32, 2, device=dev)
-    ws[..., 1] = 1.0
+    ws[..., 1] = 10.0 * 4096  # (sum, sumsq) of unit-variance data: 10 channels per group x 4096 pixels
     gamma, beta = torch.ones(320, device=dev), torch.zeros(320, device=dev)
     us = timeit(lambda: ops.groupnorm(x, o, gamma, beta, ws, 8, 4096, 32, 1e-5, True, stats_ready=True))
     by = 2.0 * x.numel() * 2

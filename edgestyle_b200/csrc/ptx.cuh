@@ -317,7 +317,9 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
 }
 
 // ---------------------------------------------------------------- misc math
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// (approximate division: the IEEE one takes its slow path whenever exp(-x) overflows -- 2.5 x on a GroupNorm-apply pass
+// over badly scaled data, tools/gn_probe.py -- and the result is stored in 16 bits)
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 // Exact (erf) GELU.  erf through Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, branch-free: one rcp, one ex2, six FMAs)
 // instead of libdevice erff (two divergent polynomial branches): the GEGLU epilogue evaluates 2e8 of these per step on
 // four to eight warps per SM.
