@@ -451,7 +451,9 @@ def test_conv3x3_persist(n_img, h, w, cin, cout, bn):
 # ------------------------------------------------------------------------------------------ folded LayerNorm
 @pytest.mark.parametrize("M,C,N,bn,geglu", [(512, 320, 960, 0, False), (1024, 640, 640, 320, False), (256, 1280, 1280, 64, False),
                                             (768, 320, 2560, 160, True), (768, 320, 2560, 320, True), (2048, 640, 1920, 320, False),
-                                            (4096, 320, 960, 1256, False), (4096, 320, 2560, 1160, True), (2048, 640, 640, 1128, False)])
+                                            (4096, 320, 960, 1256, False), (4096, 320, 2560, 1160, True), (2048, 640, 640, 1128, False),
+                                            # several units per CTA: the next unit's row statistics / vector are prefetched
+                                            (8192, 320, 960, 1160, False), (8192, 640, 1920, 1128, False)])
 def test_gemm_folded_layernorm(M, C, N, bn, geglu):
     """producer GEMM accumulates row (sum, sumsq) of its output; consumer GEMM == Linear(LayerNorm(x)) without a LayerNorm pass."""
     from edgestyle_b200 import ops
