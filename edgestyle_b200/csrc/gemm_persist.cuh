@@ -643,7 +643,12 @@ static int launch_gemm_persist(const CUtensorMap& tmA, const CUtensorMap& tmA2, 
   const int n_units = m_tiles * n_tiles;
   kp.splits = 1;
   kp.stages = Cfg::kStages;
-  int sms = 148;
+  // ES_PERSIST_CTAS (read once): fewer CTAs than SMs leave room for the other streams' kernels next to a persistent GEMM
+  static const int sms = [] {
+    const char* e = getenv("ES_PERSIST_CTAS");
+    const int v = e ? atoi(e) : 148;
+    return v >= 1 && v <= 148 ? v : 148;
+  }();
   const int ctas = n_units < sms ? n_units : sms;
   auto kern = gemm_persist_kernel<T, BLOCK_N>;
   static bool attr_done = false;  // per instantiation
