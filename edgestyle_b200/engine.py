@@ -353,6 +353,21 @@ class _Packer:
         )
 
 
+def merge_level_groups(nlev: int, n_up: int, stepping: bool, by_level: bool, split: int) -> List[List[int]]:
+    """Residual levels (0 .. nlev - 2 = skips, nlev - 1 = mid) grouped into merge launches, in the order the decoder
+    consumes them (mid, then skips nlev - 2 .. 0).  Outside the fused step (mode "residuals") one group; by_level: one
+    group per decoder level -- (mid + the deepest level's n_up skips), then n_up skips each; else the levels >= split and
+    the levels < split (split 0: one group)."""
+    order = list(reversed(range(nlev)))
+    if not stepping:
+        return [order]
+    if by_level:
+        rest = order[1 + n_up:]
+        return [order[:1 + n_up]] + [rest[i:i + n_up] for i in range(0, len(rest), n_up)]
+    split = max(0, min(split, nlev))
+    return [g for g in (list(reversed(range(split, nlev))), list(reversed(range(split)))) if g]
+
+
 @dataclass(frozen=True)
 class StepGeometry:
     base_nets: Tuple[Optional[int], ...]  # net index per image block of the base pass (None = the UNet's own rows)
@@ -1220,16 +1235,7 @@ class DenoiseEngine:
         side = self._merge_stream
         ev_main = torch.cuda.Event()
         ev_main.record(main)
-        if mode != "step":
-            level_groups = [list(reversed(range(nlev)))]
-        elif self.merge_by_level:
-            # one group per decoder level: (mid + the deepest level's skips), then the skips of each shallower level
-            order_all = list(reversed(range(nlev)))
-            rest = order_all[1 + n_up:]
-            level_groups = [order_all[:1 + n_up]] + [rest[i:i + n_up] for i in range(0, len(rest), n_up)]
-        else:
-            split = min(self.merge_split, nlev)
-            level_groups = [list(reversed(range(split, nlev)))] + ([list(reversed(range(split)))] if split > 0 else [])
+        level_groups = merge_level_groups(nlev, n_up, mode == "step", self.merge_by_level, self.merge_split)
         # zero-convs: each encoder pass does its own, deepest group first, on a stream that is idle once the encoders are
         # through (the ControlLoRA blocks on a side stream behind the main pass, the openpose blocks on the pose
         # stream behind its pass); the merge stream waits group by group

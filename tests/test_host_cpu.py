@@ -270,3 +270,21 @@ def test_checkpoint_directory_matches_reference_save_pretrained(models, tmp_path
     assert sorted(os.listdir(out)) == sorted(meta["listing"] + [c[2] for c in saved])
     mine = load_file(str(out / "diffusion_pytorch_model.safetensors"))
     assert set(mine) == set(golden) and all(torch.equal(mine[k], golden[k]) for k in golden)
+
+
+def test_merge_level_groups_follow_the_decoder():
+    """Merge launches are grouped in the order the decoder consumes the residual levels (mid, then skips 11..0); every
+    level appears exactly once whatever the grouping."""
+    from edgestyle_b200.engine import merge_level_groups
+
+    by_level = merge_level_groups(13, 3, True, True, 3)
+    assert by_level == [[12, 11, 10, 9], [8, 7, 6], [5, 4, 3], [2, 1, 0]]
+    assert merge_level_groups(13, 3, True, False, 3) == [[12, 11, 10, 9, 8, 7, 6, 5, 4, 3], [2, 1, 0]]
+    assert merge_level_groups(13, 3, True, False, 0) == [list(range(12, -1, -1))]
+    assert merge_level_groups(13, 3, False, True, 3) == [list(range(12, -1, -1))]      # mode "residuals": one group
+    for nlev, n_up in ((13, 3), (9, 2), (5, 2), (4, 3)):
+        for args in ((True, True, 3), (True, False, 3), (True, False, 99), (False, False, 0)):
+            flat = [li for grp in merge_level_groups(nlev, n_up, *args) for li in grp]
+            assert sorted(flat) == list(range(nlev)) and all(grp for grp in merge_level_groups(nlev, n_up, *args))
+            if args[0] and args[1]:
+                assert flat == list(range(nlev - 1, -1, -1))
