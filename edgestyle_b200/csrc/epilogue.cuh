@@ -61,30 +61,9 @@ __device__ __forceinline__ void epi_rowstat16(const float (&o)[16], uint64_t& rs
     rq2 = fma2(v, v, rq2);
   }
 }
-// Exact (erf) GELU of a pair: Abramowitz-Stegun 7.1.26 as in gelu_erf_f (ptx.cuh), polynomial coefficients negated so
-// that erf|x| = 1 + (p' t) e.  Per pair: 2 rcp + 2 ex2 on the MUFU pipe, 2 FMUL (|x| is a free source modifier there),
-// 2 LOP3 (copysign) and 11 packed instructions -- 10 issue slots per element instead of 19.
-__device__ __forceinline__ uint64_t gelu_erf_2(float x0, float x1) {
-  const float ax0 = fabsf(x0) * 0.70710678118654752f, ax1 = fabsf(x1) * 0.70710678118654752f;
-  const uint64_t ax2 = pk2(ax0, ax1);
-  float d0, d1;
-  upk2(fma2(ax2, bc2(0.3275911f), bc2(1.0f)), d0, d1);
-  const uint64_t t2 = pk2(__fdividef(1.0f, d0), __fdividef(1.0f, d1));
-  uint64_t p2 = fma2(t2, bc2(-1.061405429f), bc2(1.453152027f));
-  p2 = fma2(p2, t2, bc2(-1.421413741f));
-  p2 = fma2(p2, t2, bc2(0.284496736f));
-  p2 = fma2(p2, t2, bc2(-0.254829592f));
-  float m0, m1;
-  upk2(mul2(mul2(ax2, bc2(-1.4426950408889634f)), ax2), m0, m1);  // -ax^2 log2(e)
-  float e0, e1;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(m0));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(m1));
-  float r0, r1;
-  upk2(fma2(mul2(p2, t2), pk2(e0, e1), bc2(1.0f)), r0, r1);       // erf|x|
-  const uint64_t xh2 = mul2(pk2(x0, x1), bc2(0.5f));
-  return fma2(xh2, pk2(copysignf(r0, x0), copysignf(r1, x1)), xh2);  // 0.5 x (1 + erf x)
-}
-// o = alpha * a * gelu(g) over 16 columns, written STAGE BY STAGE across the eight pairs: the epilogue has two warps per
+// o = alpha * a * gelu(g) over 16 columns; exact (erf) GELU through Abramowitz-Stegun 7.1.26 as in gelu_erf_f (ptx.cuh),
+// polynomial coefficients negated so that erf|x| = 1 + (p' t) e: per pair 2 rcp + 2 ex2 on the MUFU pipe, 2 FMUL (|x| is a
+// free source modifier there), 2 LOP3 (copysign) and 11 packed instructions.  Written STAGE BY STAGE across the eight pairs: the epilogue has two warps per
 // sub-partition and nothing else to hide a dependency chain behind -- pair after pair (rcp -> 4 dependent FMAs -> ex2 ->
 // ...) the sixteen GELUs of a chunk took ~1000 cycles (tools/persist_trace.py with the GELU ablated), eight chains wide
 // every instruction has seven independent neighbours.

@@ -614,8 +614,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               load_cols(HALF + c, g);
               pre16(c, a);
               pre16(HALF + c, g);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = p.alpha * a[j] * gelu_erf_f(g[j]);
+              epi_geglu16(o, a, g, p.alpha);  // stage by stage across the eight pairs (epilogue.cuh)
             } else {
               load_cols(c, o);
               pre16(c, o);
@@ -638,8 +637,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             pre16(c, av);
             pre16(HALF + c, gv);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = p.alpha * av[j] * gelu_erf_f(gv[j]);
+            epi_geglu16(o, av, gv, p.alpha);  // stage by stage across the eight pairs (epilogue.cuh)
             finish_chunk(c, o);
           };
 #pragma unroll 1

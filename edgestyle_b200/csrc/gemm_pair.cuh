@@ -494,8 +494,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               load_ws(half * kPairNH + GH + c, g);
               pre16(c, a);
               pre16(GH + c, g);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = p.alpha * a[j] * gelu_erf_f(g[j]);
+              epi_geglu16(o, a, g, p.alpha);  // stage by stage across the eight pairs (epilogue.cuh)
               finish_chunk(half * GH + c, o);
             } else {
               load_ws(half * kPairNH + c, o);
@@ -518,8 +517,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             pre16(c, av);
             pre16(GH + c, gv);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = p.alpha * av[j] * gelu_erf_f(gv[j]);
+            epi_geglu16(o, av, gv, p.alpha);  // stage by stage across the eight pairs (epilogue.cuh)
             finish_chunk(half * GH + c, o);
           };
 #pragma unroll 1
