@@ -30,14 +30,13 @@ torch.cuda.synchronize()
 buf = (C.c_longlong * 256)()
 assert lib.es_attention_trace(buf) == 0
 t = list(buf)
-mma, t8, t9, det = t[:64], t[64:128], t[128:192], t[192:256]
+mma, t8, t9 = t[:64], t[64:128], t[128:192]
 t0 = min(x for x in mma if x > 0)
-print("tile | MMA: qk(j+1)_issued v_full pv0_issued pv1_issued   (cycles)")
+# staggered issue order (attention2.cuh, QT == 2): per key tile j the MMA thread stamps after [A] QK0(j+1), [B] PV1(j-1)
+# (j == 0: QK1(0)), [C] QK1(j+1), [D] PV0(j)
+print("tile | MMA thread: A (QK0(j+1) issued)  B (PV1(j-1) issued)  C (QK1(j+1) issued)  D (PV0(j) issued)   (cycles)")
 for j in range(6, 12):
     print(j, [x - t0 for x in mma[4 * j:4 * j + 4]])
-print("MMA thread detail (tile j & 7): k_full | s_free0 qk0_issued s_free1 qk1_issued | p_full0 p_full1")
-for j in range(8):
-    print(j, [v - t0 for v in det[8 * j:8 * j + 7]])
 for name, arr in (("tile 8", t8), ("tile 9", t9)):
     print(name, "per softmax warp (WG0: warps 2-5, WG1: warps 6-9): s_full s_free exps_done p_full_arrive")
     for w in range(8):
